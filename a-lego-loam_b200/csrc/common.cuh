@@ -1,0 +1,258 @@
+// common.cuh — handle layout, launch/profiling helpers and small device utilities shared by every
+// translation unit of libalego_b200.so.  sm_100a only; the whole library is compiled with --fmad=false so
+// that float/double expressions round exactly like the reference's baseline-x86-64 build (no FMA
+// contraction, CMakeLists.txt:4-5) — the path is HBM/latency bound, the lost FMA throughput is irrelevant.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/alego_b200.h"
+
+#define ALEGO_MAX_RINGS 128
+#define ALEGO_EMPTY_RANGE 3.402823466e+38f  // FLT_MAX: "no return" marker of the range image (reference: DBL_MAX, imageProjection.cpp:33)
+#define ALEGO_LABEL_INVALID 999999          // imageProjection.cpp:311
+
+struct Pose {  // translation + row-major rotation
+  double t[3];
+  double R[9];
+};
+
+// Hashed uniform grid over one point cloud per sequence (replaces pcl::KdTreeFLANN, see grid.cuh)
+struct GridIndex {
+  int table_size = 0;  // power of two
+  int cap = 0;         // points per sequence
+  float cell = 1.0f;
+  int *cell_start = nullptr;  // [B][table_size+1]
+  int *cursor = nullptr;      // [B][table_size]  scratch (counts, then fill cursors)
+  float4 *sorted = nullptr;   // [B][cap]  xyz + original index (int bits in .w)
+};
+
+struct KernelProfile {
+  std::string name;
+  int64_t launches = 0;
+  double total_ms = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct AlegoHandle {
+  AlegoParams P;
+  int dev = 0, B = 0, Nmax = 0, R = 0, C = 0, RC = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<KernelProfile> prof;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t timer[16] = {};
+  int scan_count = 0;
+  int lm_every = 1;
+  bool rebuild_map_every_step = true;
+  bool stage_ip_done = false, stage_feat_done = false;
+  bool want_labels = true;  // materialise label_mat_ (imageProjection.h:25) every sweep
+  int feat_buf = -1;        // buffer index holding the most recent feature clouds
+  std::vector<uint8_t> lm_scan_is_external;  // per seq: inputs set through alego_lm_set_scan
+
+  // precomputed on the host with the host libm so that they match the oracle bit for bit
+  double seg_sin_x, seg_cos_x, seg_sin_y, seg_cos_y;
+
+  // ---------------- ImageProjection ----------------
+  float4 *raw = nullptr;       // [B][Nmax]
+  int *n_pts = nullptr;        // [B]
+  int *first_valid = nullptr;  // [B]
+  int *last_valid = nullptr;   // [B]
+  int *winner = nullptr;       // [B][RC]  index of the last input point that fell in the cell (-1 none)
+  float4 *cloud = nullptr;     // [B][RC]  full_cloud_
+  float *range = nullptr;      // [B][RC]  range_mat_ (f32 is lossless: the reference stores a float sqrt)
+  uint8_t *ground = nullptr;   // [B][RC]  ground_mat_
+  int *parent = nullptr;       // [B][RC]  union-find forest; -1 = not a segmentation candidate
+  int2 *comp_stat = nullptr;   // [B][RC]  at roots: (size, max row)
+  int *comp_id = nullptr;      // [B][RC]  at roots: final label 1..K
+  int *label = nullptr;        // [B][RC]  label_mat_
+  int4 *rowcnt = nullptr;      // [B][R]   (kept, outliers, feasible roots, -)
+  float4 *seg_cloud = nullptr; // [B][RC]
+  uint8_t *seg_ground = nullptr;
+  int *seg_col = nullptr;
+  float *seg_range = nullptr;
+  int *start_ring = nullptr;   // [B][R]
+  int *end_ring = nullptr;     // [B][R]
+  int *M = nullptr;            // [B]
+  float4 *outlier = nullptr;   // [B][out_cap]
+  int out_cap = 0;
+  int *n_outlier = nullptr;    // [B]
+  float *orient = nullptr;     // [B][4] start, end, diff
+
+  // ---------------- LaserOdometry features ----------------
+  float *curv = nullptr;       // [B][RC]  |diff_range| (float); cloud_curvature_ == (double)c*(double)c exactly
+  uint8_t *picked0 = nullptr;  // [B][RC]  cloud_neighbor_picked_ after markOccludedPoints
+  uint8_t *picked = nullptr;   // [B][RC]  ... after extractFeatures
+  int *flabel = nullptr;       // [B][RC]  cloud_label_
+  int *sort_idx = nullptr;     // [B][RC]  cloud_sort_idx_
+  unsigned long long *sort_scratch = nullptr;  // [B][RC]
+  int *ring_feat_cnt = nullptr;  // [B][R][4]  sharp, less_sharp, flat, less_flat_ds per ring
+  int *ring_sharp = nullptr;     // [B][R][12]
+  int *ring_less_sharp = nullptr;// [B][R][120]
+  int *ring_flat = nullptr;      // [B][R][24]
+  int *sharp_idx = nullptr, *less_sharp_idx = nullptr, *flat_idx = nullptr;  // [B][R*12], [B][R*120], [B][R*24]
+  int *n_feat = nullptr;         // [B][4] sharp, less_sharp, flat, less_flat
+  float4 *sharp = nullptr, *flat = nullptr;  // [B][R*12], [B][R*24]
+  float4 *lf_stage = nullptr;    // [B][RC] per-ring voxel output staged at the ring's first kept index
+  unsigned long long *vox_sort = nullptr;  // [B][vox_cap] composite (voxel key << 32 | point) sort buffer
+  int vox_cap = 0;
+  // double-buffered "last" clouds (index = scan parity)
+  float4 *less_sharp[2] = {nullptr, nullptr};  // [B][R*120]  corner_last_ / less_sharp
+  float4 *less_flat[2] = {nullptr, nullptr};   // [B][RC]     surf_last_ / less_flat
+  int *ls_ring_off[2] = {nullptr, nullptr};    // [B][R+1]
+  int *lf_ring_off[2] = {nullptr, nullptr};    // [B][R+1]
+  int cur = 0;                                 // which buffer holds the CURRENT scan's clouds
+
+  // ---------------- LaserOdometry scan-to-scan ----------------
+  GridIndex g_surf_last, g_corner_last;
+  double *lo_params = nullptr;  // [B][6]
+  double *t_w = nullptr;        // [B][3]
+  double *r_w = nullptr;        // [B][9]
+  int *lo_init = nullptr;       // [B]
+  float *lo_surf_res = nullptr;   // [B][R*24][12]  cp, lpj, lpl, lpm
+  int *lo_surf_corr = nullptr;    // [B][R*24][4]   j, closest, idx2, idx3 (closest<0: no residual)
+  float *lo_corner_res = nullptr; // [B][R*12][9]
+  int *lo_corner_corr = nullptr;  // [B][R*12][3]
+  AlegoSolveReport *lo_report = nullptr;  // [B]
+  double *lo_trace = nullptr;     // [B][2*(iters+1)][7]
+  int *lo_trace_n = nullptr;      // [B]
+
+  // ---------------- LaserMapping ----------------
+  int map_cap_c = 0, map_cap_s = 0;
+  float4 *map_corner = nullptr, *map_surf = nullptr;  // [B][cap]
+  int *n_map_corner = nullptr, *n_map_surf = nullptr; // [B]
+  GridIndex g_map_corner, g_map_surf;
+  bool map_index_valid = false;
+  int lm_cap_c = 0, lm_cap_s = 0, lm_cap_o = 0;       // capacities of stand-alone inputs
+  float4 *lm_in_corner = nullptr, *lm_in_surf = nullptr, *lm_in_outlier = nullptr;  // [B][cap]
+  int *lm_in_n = nullptr;      // [B][4] corner, surf, outlier counts of stand-alone inputs
+  int *lm_use_ext = nullptr;   // [B] 1 = read lm_in_*, 0 = read LO outputs
+  float4 *lm_corner_ds = nullptr, *lm_surf_ds = nullptr, *lm_outlier_ds = nullptr, *lm_surf_total = nullptr,
+         *lm_surf_total_ds = nullptr;
+  int ds_cap_c = 0, ds_cap_s = 0, ds_cap_o = 0;
+  int *lm_n = nullptr;         // [B][8] corner_ds, surf_ds, outlier_ds, surf_total, surf_total_ds
+  double *lm_params = nullptr; // [B][6]
+  Pose *m2o = nullptr, *o2l = nullptr, *m2l = nullptr;  // [B]
+  double *lm_edge = nullptr;   // [B][ds_cap_c][10]: valid, cp3, lpj3, lpl3
+  double *lm_plane = nullptr;  // [B][ds_cap_s+o][8]: valid, cp3, n3, d
+  AlegoSolveReport *lm_report = nullptr;
+  int *lm_guard = nullptr;     // [B] scan2MapOptimization guard (laserMapping.cpp:350)
+  double *lm_trace = nullptr;  // [B][outer*(iters+1)][7]
+  int *lm_trace_n = nullptr;
+  int lm_trace_cap = 0, lo_trace_cap = 0;
+
+  // host staging for small D2H results
+  double *h_pose = nullptr;  // pinned [B][12]
+  double *d_pose = nullptr;  // [B][12]
+};
+
+// ------------------------------------------------------------------------------------------------
+#define CUDA_TRY(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                            \
+      return ALEGO_CUDA_ERROR;                                                                  \
+    }                                                                                           \
+  } while (0)
+
+// Bracket a launch with events when profiling is on; always count it.
+struct LaunchScope {
+  AlegoHandle *h;
+  int id = -1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  LaunchScope(AlegoHandle *hh, const char *name) : h(hh) {
+    ++h->launches;
+    if (!h->profiling) return;
+    for (size_t i = 0; i < h->prof.size(); ++i)
+      if (h->prof[i].name == name) { id = (int)i; break; }
+    if (id < 0) {
+      h->prof.push_back(KernelProfile());
+      h->prof.back().name = name;
+      id = (int)h->prof.size() - 1;
+    }
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    e0 = get(); e1 = get();
+    cudaEventRecord(e0, h->stream);
+  }
+  ~LaunchScope() {
+    if (id < 0) return;
+    cudaEventRecord(e1, h->stream);
+    h->prof[id].pending.emplace_back(e0, e1);
+  }
+};
+#define ALEGO_CAT2(a, b) a##b
+#define ALEGO_CAT(a, b) ALEGO_CAT2(a, b)
+#define LAUNCH(h, name) LaunchScope ALEGO_CAT(_ls_, __LINE__)((h), (name))
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_f4(const float4 *p) { return __ldg(p); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exclusive block scan of one int per thread; returns the exclusive prefix, *total gets the block sum.
+// smem: at least 33 ints. All threads of the block must call it.
+__device__ __forceinline__ int block_excl_scan(int v, int *smem, int *total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protect smem reuse across consecutive calls
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem[lane] = winc - w;
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  if (total) *total = smem[32];
+  return smem[wid] + inc - v;
+}
+
+// Rz(yaw)*Ry(pitch)*Rx(roll) and the trig terms, as in every cost function of utility.h:128-158
+struct PoseTrig {
+  double sr, cr, sp, cp, sy, cy;
+  double R[9];
+  __device__ __forceinline__ explicit PoseTrig(const double *x) {
+    sr = sin(x[3]); cr = cos(x[3]);
+    sp = sin(x[4]); cp = cos(x[4]);
+    sy = sin(x[5]); cy = cos(x[5]);
+    R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+    R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+    R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+  }
+};

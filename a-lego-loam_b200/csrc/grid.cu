@@ -1,0 +1,102 @@
+// grid.cu — hashed uniform cell grid over a point cloud, one per sequence: the device replacement for
+// pcl::KdTreeFLANN::setInputCloud (laserOdometry.cpp:321-322,533-534; laserMapping.cpp:356-357).
+// Build = counting sort of the points by hashed cell: count (atomics on a per-sequence table), exclusive
+// scan of the table, fill.  Points are copied next to each other per bucket (xyz + original index), so a
+// query reads whole buckets with coalesced 16-byte loads.  Bucket order is arbitrary; every consumer ranks
+// candidates by (distance, original index), so results do not depend on it.
+#include "common.cuh"
+#include "grid.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) grid_count_kernel(const float4 *__restrict__ pts, size_t pts_stride, const int *__restrict__ n_ptr,
+                                                         int n_stride, int *__restrict__ counts, int T, float inv_cell, int cap) {
+  const int b = blockIdx.y;
+  const int n = min(n_ptr[(size_t)b * n_stride], cap);
+  const float4 *src = pts + (size_t)b * pts_stride;
+  int *cnt = counts + (size_t)b * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = ldg_f4(src + i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+    atomicAdd(cnt + grid_hash(grid_coord(p.x, inv_cell), grid_coord(p.y, inv_cell), grid_coord(p.z, inv_cell), T), 1);
+  }
+}
+
+// one CTA per sequence: exclusive scan of T counters (T a multiple of blockDim); leaves the bucket starts in
+// cell_start[0..T] and in `counts` (which becomes the fill cursor)
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int *__restrict__ counts, int *__restrict__ cell_start, int T) {
+  const int b = blockIdx.x;
+  int *cnt = counts + (size_t)b * T;
+  int *cs = cell_start + (size_t)b * (T + 1);
+  __shared__ int s_scan[34];
+  const int per = T / blockDim.x;  // consecutive counters per thread
+  const int lo = threadIdx.x * per;
+  int sum = 0;
+  for (int k = 0; k < per; ++k) sum += cnt[lo + k];
+  int total;
+  int run = block_excl_scan(sum, s_scan, &total);
+  for (int k = 0; k < per; ++k) {
+    const int c = cnt[lo + k];
+    cs[lo + k] = run;
+    cnt[lo + k] = run;
+    run += c;
+  }
+  if (threadIdx.x == 0) cs[T] = total;
+}
+
+__global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict__ pts, size_t pts_stride, const int *__restrict__ n_ptr,
+                                                        int n_stride, int *__restrict__ cursor, float4 *__restrict__ sorted, int T,
+                                                        float inv_cell, int cap) {
+  const int b = blockIdx.y;
+  const int n = min(n_ptr[(size_t)b * n_stride], cap);
+  const float4 *src = pts + (size_t)b * pts_stride;
+  int *cur = cursor + (size_t)b * T;
+  float4 *dst = sorted + (size_t)b * cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = ldg_f4(src + i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+    const int slot = atomicAdd(cur + grid_hash(grid_coord(p.x, inv_cell), grid_coord(p.y, inv_cell), grid_coord(p.z, inv_cell), T), 1);
+    dst[slot] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+}
+
+}  // namespace
+
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell) {
+  grid_free(g);
+  g->cap = cap;
+  g->cell = cell;
+  int T = next_pow2(cap > 2048 ? cap / 2 : 1024);
+  if (T < 1024) T = 1024;
+  g->table_size = T;
+  CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)h->B * (T + 1) * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&g->cursor, (size_t)h->B * T * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&g->sorted, (size_t)h->B * cap * sizeof(float4)));
+  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)h->B * (T + 1) * sizeof(int), h->stream));
+  return ALEGO_OK;
+}
+
+void grid_free(GridIndex *g) {
+  if (g->cell_start) cudaFree(g->cell_start);
+  if (g->cursor) cudaFree(g->cursor);
+  if (g->sorted) cudaFree(g->sorted);
+  g->cell_start = g->cursor = nullptr;
+  g->sorted = nullptr;
+  g->cap = g->table_size = 0;
+}
+
+int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag) {
+  const int B = h->B, T = g->table_size;
+  cudaStream_t s = h->stream;
+  const float inv = 1.0f / g->cell;
+  const int blocks = min(div_up(g->cap, 256), 1024);
+  std::string t0 = std::string("grid_count_") + tag, t1 = std::string("grid_scan_") + tag, t2 = std::string("grid_fill_") + tag;
+  CUDA_TRY(h, cudaMemsetAsync(g->cursor, 0, (size_t)B * T * sizeof(int), s));
+  { LAUNCH(h, t0.c_str());
+    grid_count_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cursor, T, inv, g->cap); }
+  { LAUNCH(h, t1.c_str()); grid_scan_kernel<<<B, 1024, 0, s>>>(g->cursor, g->cell_start, T); }
+  { LAUNCH(h, t2.c_str());
+    grid_fill_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cursor, g->sorted, T, inv, g->cap); }
+  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}

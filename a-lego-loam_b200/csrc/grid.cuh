@@ -1,0 +1,23 @@
+// grid.cuh — device-side lookup helpers of the hashed cell grid (see grid.cu) and the host build entry.
+#pragma once
+#include "common.cuh"
+
+__host__ __device__ __forceinline__ int grid_coord(float v, float inv_cell) { return (int)floorf(v * inv_cell); }
+__host__ __device__ __forceinline__ int grid_hash(int ix, int iy, int iz, int T) {
+  const unsigned h = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+  return (int)(h & (unsigned)(T - 1));
+}
+
+// squared distance accumulated in float exactly like ::flann::L2_Simple<float> (diff = a-b; result += diff*diff)
+__device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const float4 &p) {
+  float r = 0.f, d;
+  d = qx - p.x; r += d * d;
+  d = qy - p.y; r += d * d;
+  d = qz - p.z; r += d * d;
+  return r;
+}
+
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell);
+void grid_free(GridIndex *g);
+// pts: [B] clouds `pts_stride` points apart; point count of sequence b = n_ptr[b * n_stride]
+int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag);

@@ -1,0 +1,427 @@
+// ip_kernels.cu — ImageProjection on the device: replaces ImageProjection::pcCB + labelComponents
+// (src/imageProjection.cpp:49-208, 210-316).  All kernels carry the sequence index in blockIdx.y so one
+// launch serves the whole batch of independent sequences.
+//
+// K1a ip_project   : per input point row/col binning (:76-104), deterministic "last writer wins" by atomicMax
+// K1b ip_gather    : per cell — organised cloud, range image, resets of the per-scan images (:24-33,:197-205)
+// K2  ip_ground    : vertical-neighbour slope test (:106-132)
+// K3  ccl_*        : connected components by lock-free union-find (:134-156, 210-280)
+// K4/K5 ip_rowcount + ip_compact : feasibility (:282-315), raster-order label numbering, ring-major stream
+//                    compaction into the cloud_info arrays (:158-191)
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ip_kernels.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// row / column of one point.  The reference evaluates atan2f / hypotf (float overloads, SURVEY Appendix
+// A.1) then scales in double and truncates.  Fast path: float intrinsics, accepted when the fractional
+// cell coordinate is > 2e-3 away from an integer (their error is < 3e-4 cell); otherwise the slow path
+// recomputes with correctly rounded float results obtained through double precision.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool near_integer(double v, double eps) {
+  const double f = v - floor(v);
+  return f < eps || f > 1.0 - eps;
+}
+
+__device__ bool project_rowcol(float x, float y, float z, const IpDev &P, int &row, int &col) {
+  // ---- row (imageProjection.cpp:79-85)
+  float hyp = sqrtf(x * x + y * y);
+  float va = atan2f(z, hyp);
+  double row_f = ((double)va * 180.0 / CUDART_PI + P.ang_bottom) / P.ang_res_y + 0.5;
+  if (!(row_f > -1.0e6 && row_f < 1.0e6)) return false;
+  if (near_integer(row_f, 2e-3)) {
+    hyp = (float)sqrt((double)x * (double)x + (double)y * (double)y);
+    va = (float)atan2((double)z, (double)hyp);
+    row_f = ((double)va * 180.0 / CUDART_PI + P.ang_bottom) / P.ang_res_y + 0.5;
+  }
+  row = (int)row_f;
+  if (row < 0 || row >= P.R) return false;
+  // ---- column (:87-97)
+  float ha = atan2f(y, x);
+  double col_f = (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
+  if (near_integer(col_f, 2e-3)) {
+    ha = (float)atan2((double)y, (double)x);
+    col_f = (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
+  }
+  col = (int)col_f;
+  if (col >= P.C) col -= P.C;
+  if (col < 0 || col >= P.C) return false;
+  return true;
+}
+
+__global__ void ip_reset_kernel(int *first_valid, int *last_valid, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    first_valid[b] = 0x7fffffff;
+    last_valid[b] = -1;
+  }
+}
+
+__device__ __forceinline__ bool finite3(const float4 &p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
+
+__global__ void __launch_bounds__(256) ip_project_kernel(const float4 *__restrict__ raw, const int *__restrict__ n_pts,
+                                                         int *__restrict__ winner, int *first_valid, int *last_valid, int Nmax,
+                                                         IpDev P) {
+  const int b = blockIdx.y;
+  const int n = min(n_pts[b], Nmax);
+  const float4 *src = raw + (size_t)b * Nmax;
+  int *win = winner + (size_t)b * P.RC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = ldg_f4(src + i);
+    if (!finite3(p)) continue;  // pcl::removeNaNFromPointCloud (:59)
+    // first / last valid point (orientation, :62-63): only run boundaries touch the atomics
+    if (i == 0 || !finite3(ldg_f4(src + i - 1))) atomicMin(first_valid + b, i);
+    if (i == n - 1 || !finite3(ldg_f4(src + i + 1))) atomicMax(last_valid + b, i);
+    int row, col;
+    if (!project_rowcol(p.x, p.y, p.z, P, row, col)) continue;
+    atomicMax(win + row * P.C + col, i);  // the later point of a cell wins (:103)
+  }
+}
+
+__global__ void __launch_bounds__(256) ip_gather_kernel(const float4 *__restrict__ raw, int *__restrict__ winner,
+                                                        float4 *__restrict__ cloud, float *__restrict__ range,
+                                                        uint8_t *__restrict__ ground, int Nmax, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
+    const int w = winner[base + cell];
+    float4 o = make_float4(0.f, 0.f, 0.f, -1.f);  // nan_p (:24-27)
+    float r = ALEGO_EMPTY_RANGE;
+    if (w >= 0) {
+      winner[base + cell] = -1;  // ready for the next sweep
+      const float4 p = ldg_f4(raw + (size_t)b * Nmax + w);
+      const int row = cell / P.C, col = cell - row * P.C;
+      r = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);                      // (:99) float sum, float sqrt
+      o = make_float4(p.x, p.y, p.z, (float)((double)row + (double)col / 10000.0));  // (:101)
+    }
+    cloud[base + cell] = o;
+    range[base + cell] = r;
+    ground[base + cell] = 0;
+  }
+}
+
+// (:106-132) one thread per vertical pair (i, i+1), i < ground_scan_id
+__global__ void __launch_bounds__(256) ip_ground_kernel(const float4 *__restrict__ cloud, uint8_t *__restrict__ ground, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  const int rows = min(P.ground_scan_id, P.R - 1);
+  const int total = rows * P.C;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const float4 lo = cloud[base + t], up = cloud[base + t + P.C];
+    if (lo.w == -1.f || up.w == -1.f) continue;
+    const float fx = up.x - lo.x, fy = up.y - lo.y, fz = up.z - lo.z;  // float differences, then widened
+    // fast float estimate; the exact double evaluation only near the 10 degree threshold
+    const float af = atan2f(fz, sqrtf(fx * fx + fy * fy)) * 57.29577951f;
+    bool is_ground;
+    const float da = fabsf(af - (float)P.sensor_mount_ang);
+    if (fabsf(da - 10.f) > 1e-2f) {
+      is_ground = da < 10.f;
+    } else {
+      const double dx = fx, dy = fy, dz = fz;
+      const double angle = atan2(dz, hypot(dx, dy)) * 180.0 / CUDART_PI;
+      is_ground = fabs(angle - P.sensor_mount_ang) < 10.;
+    }
+    if (is_ground) {
+      ground[base + t] = 1;
+      ground[base + t + P.C] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// connected components.  parent[] holds cell indices local to the sequence; the root of a component is
+// its smallest raster index (links always point to smaller indices → no cycles).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int *L, int x) {
+  const volatile int *V = L;  // other threads relink roots concurrently (atomicMin in uf_unite)
+  int p = V[x];
+  while (p != x) {
+    x = p;
+    p = V[x];
+  }
+  return x;
+}
+__device__ __forceinline__ int uf_find_compress(int *L, int x) {
+  int root = uf_find(L, x);
+  // point the whole path at the root (plain stores: every value written is an ancestor)
+  int p = L[x];
+  while (p != root) {
+    L[x] = root;
+    x = p;
+    p = L[x];
+  }
+  return root;
+}
+__device__ __forceinline__ void uf_unite(int *L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(L + b, a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(L + a, b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// range-angle criterion (:255-270): atan2(d2*sin(alpha), d1 - d2*cos(alpha)) > seg_theta
+__device__ __forceinline__ bool seg_join(float ra, float rb, bool horizontal, const IpDev &P) {
+  const float d1f = fmaxf(ra, rb), d2f = fminf(ra, rb);
+  const float sf = horizontal ? (float)P.sin_x : (float)P.sin_y, cf = horizontal ? (float)P.cos_x : (float)P.cos_y;
+  const float af = atan2f(d2f * sf, d1f - d2f * cf);
+  if (fabsf(af - (float)P.seg_theta) > 1e-4f) return af > (float)P.seg_theta;
+  const double d1 = d1f, d2 = d2f;
+  const double angle = atan2(d2 * (horizontal ? P.sin_x : P.sin_y), d1 - d2 * (horizontal ? P.cos_x : P.cos_y));
+  return angle > P.seg_theta;
+}
+
+__global__ void __launch_bounds__(256) ccl_init_kernel(const float *__restrict__ range, const uint8_t *__restrict__ ground,
+                                                       int *__restrict__ parent, int2 *__restrict__ comp_stat, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
+    const bool valid = ground[base + cell] == 0 && range[base + cell] != ALEGO_EMPTY_RANGE;  // (:134-143)
+    parent[base + cell] = valid ? cell : -1;
+    comp_stat[base + cell] = make_int2(0, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const float *__restrict__ range, int *parent, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  int *L = parent + base;
+  const float *rg = range + base;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
+    if (L[cell] < 0) continue;
+    const int row = cell / P.C, col = cell - row * P.C;
+    const float r0 = rg[cell];
+    // right neighbour, column index wraps (:241-248)
+    if (P.C > 1) {
+      const int nb = (col == P.C - 1) ? cell - col : cell + 1;
+      if (L[nb] >= 0 && seg_join(r0, rg[nb], true, P)) uf_unite(L, cell, nb);
+    }
+    // lower neighbour (next ring), rows do not wrap (:237)
+    if (row + 1 < P.R) {
+      const int nb = cell + P.C;
+      if (L[nb] >= 0 && seg_join(r0, rg[nb], false, P)) uf_unite(L, cell, nb);
+    }
+  }
+}
+
+// flatten + per-component size and highest row (rows of a 4-connected component are contiguous, so the
+// number of distinct rows (:289-296) is max_row - row(root) + 1)
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(int *parent, int2 *comp_stat, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  int *L = parent + base;
+  const int start = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int cell0 = start - threadIdx.x; cell0 < P.RC; cell0 += gridDim.x * blockDim.x) {
+    const int cell = cell0 + threadIdx.x;
+    int root = -1;
+    if (cell < P.RC && L[cell] >= 0) root = uf_find_compress(L, cell);
+    const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
+    if (root >= 0) {
+      const unsigned peers = __match_any_sync(active, root);
+      const int row = cell / P.C;
+      const int mx = __reduce_max_sync(peers, row);
+      if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+        atomicAdd(&comp_stat[base + root].x, __popc(peers));
+        atomicMax(&comp_stat[base + root].y, mx);
+      }
+    }
+  }
+}
+
+struct CellClass {
+  bool keep, outl, rootflag, valid, feasible;
+};
+__device__ __forceinline__ CellClass classify(int cell, int row, int col, const int *L, const int2 *stat, const uint8_t *gr,
+                                              const IpDev &P) {
+  CellClass c;
+  const int root = L[cell];
+  c.valid = root >= 0;
+  c.feasible = false;
+  if (c.valid) {
+    const int2 s = stat[root];
+    const int rows = s.y - root / P.C + 1;
+    c.feasible = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && rows >= P.seg_valid_line_num);  // (:282-301)
+  }
+  const bool g = gr[cell] == 1;
+  // (:164-181) kept: feasible cluster cells, and ground cells on every 5th column or the 5-column borders
+  c.keep = (c.valid && c.feasible) || (g && (col % 5 == 0 || col <= 4 || col >= P.C - 5));
+  c.outl = c.valid && !c.feasible && row > P.ground_scan_id && col % 5 == 0;  // (:167-173)
+  c.rootflag = c.valid && c.feasible && root == cell;
+  return c;
+}
+
+__global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat,
+                                                          const uint8_t *__restrict__ ground, int4 *__restrict__ rowcnt,
+                                                          const float4 *__restrict__ raw, const int *first_valid,
+                                                          const int *last_valid, float *orient, int Nmax, IpDev P) {
+  const int b = blockIdx.y, row = blockIdx.x;
+  const size_t base = (size_t)b * P.RC;
+  int nk = 0, no = 0, nr = 0;
+  for (int col = threadIdx.x; col < P.C; col += blockDim.x) {
+    const CellClass c = classify(row * P.C + col, row, col, parent + base, comp_stat + base, ground + base, P);
+    nk += c.keep;
+    no += c.outl;
+    nr += c.rootflag;
+  }
+  __shared__ int s[3][8];
+  nk = warp_sum_i(nk); no = warp_sum_i(no); nr = warp_sum_i(nr);
+  if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = nk; s[1][threadIdx.x >> 5] = no; s[2][threadIdx.x >> 5] = nr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, o = 0, r = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s[0][w]; o += s[1][w]; r += s[2][w]; }
+    rowcnt[b * P.R + row] = make_int4(a, o, r, 0);
+    if (row == 0) {  // start/end orientation (:62-72): float atan2, float32 message fields
+      float so = 0.f, eo = 0.f;
+      const int fv = first_valid[b], lv = last_valid[b];
+      if (lv >= 0 && fv <= lv) {
+        const float4 p0 = raw[(size_t)b * Nmax + fv], p1 = raw[(size_t)b * Nmax + lv];
+        so = -(float)atan2((double)p0.y, (double)p0.x);
+        eo = (float)((double)(-(float)atan2((double)p1.y, (double)p1.x)) + 2 * CUDART_PI);
+        if ((double)(eo - so) > 3 * CUDART_PI) eo = (float)((double)eo - 2 * CUDART_PI);
+        else if ((double)(eo - so) < CUDART_PI) eo = (float)((double)eo + 2 * CUDART_PI);
+      }
+      orient[b * 4 + 0] = so;
+      orient[b * 4 + 1] = eo;
+      orient[b * 4 + 2] = eo - so;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ip_compact_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat, const uint8_t *__restrict__ ground,
+                  const int4 *__restrict__ rowcnt, const float4 *__restrict__ cloud, const float *__restrict__ range,
+                  int *__restrict__ comp_id, float4 *__restrict__ seg_cloud, uint8_t *__restrict__ seg_ground,
+                  int *__restrict__ seg_col, float *__restrict__ seg_range, int *__restrict__ start_ring,
+                  int *__restrict__ end_ring, int *__restrict__ Mout, float4 *__restrict__ outlier, int *__restrict__ n_outlier,
+                  int out_cap, IpDev P) {
+  const int b = blockIdx.y, row = blockIdx.x;
+  const size_t base = (size_t)b * P.RC;
+  __shared__ int s_base[3];
+  __shared__ int s_scan[34];
+  if (threadIdx.x < 32) {
+    int a = 0, o = 0, r = 0;
+    for (int t = threadIdx.x; t < row; t += 32) {
+      const int4 c = rowcnt[b * P.R + t];
+      a += c.x; o += c.y; r += c.z;
+    }
+    a = warp_sum_i(a); o = warp_sum_i(o); r = warp_sum_i(r);
+    if (threadIdx.x == 0) {
+      s_base[0] = a; s_base[1] = o; s_base[2] = r;
+      const int4 mine = rowcnt[b * P.R + row];
+      start_ring[b * P.R + row] = a + 5;             // (:161)
+      end_ring[b * P.R + row] = a + mine.x - 1 - 5;  // (:190)
+      if (row == P.R - 1) {
+        Mout[b] = a + mine.x;
+        n_outlier[b] = min(o + mine.y, out_cap);
+      }
+    }
+  }
+  __syncthreads();
+  int run_k = s_base[0], run_o = s_base[1], run_r = s_base[2];
+  for (int c0 = 0; c0 < P.C; c0 += blockDim.x) {
+    const int col = c0 + threadIdx.x;
+    CellClass c{false, false, false, false, false};
+    const int cell = row * P.C + col;
+    if (col < P.C) c = classify(cell, row, col, parent + base, comp_stat + base, ground + base, P);
+    const int packed = (int)c.keep | ((int)c.outl << 10) | ((int)c.rootflag << 20);
+    int total;
+    const int ex = block_excl_scan(packed, s_scan, &total);
+    if (c.keep) {
+      const int dst = run_k + (ex & 1023);
+      seg_cloud[base + dst] = cloud[base + cell];
+      seg_ground[base + dst] = ground[base + cell] == 1;  // (:183)
+      seg_col[base + dst] = col;                          // (:184)
+      seg_range[base + dst] = range[base + cell];         // (:185)
+    }
+    if (c.outl) {
+      const int dst = run_o + ((ex >> 10) & 1023);
+      if (dst < out_cap) outlier[(size_t)b * out_cap + dst] = cloud[base + cell];
+    }
+    if (c.rootflag) comp_id[base + cell] = run_r + ((ex >> 20) & 1023) + 1;  // label_cnt_ in raster-seed order (:303-306)
+    run_k += total & 1023;
+    run_o += (total >> 10) & 1023;
+    run_r += (total >> 20) & 1023;
+  }
+}
+
+__global__ void __launch_bounds__(256) ip_label_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat,
+                                                       const int *__restrict__ comp_id, int *__restrict__ label, IpDev P) {
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * P.RC;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
+    const int root = parent[base + cell];
+    int lab = -1;
+    if (root >= 0) {
+      const int2 s = comp_stat[base + root];
+      const int rows = s.y - root / P.C + 1;
+      const bool feas = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && rows >= P.seg_valid_line_num);
+      lab = feas ? comp_id[base + root] : ALEGO_LABEL_INVALID;
+    }
+    label[base + cell] = lab;
+  }
+}
+
+}  // namespace
+
+IpDev make_ip_dev(const AlegoHandle *h) {
+  IpDev d;
+  d.R = h->R; d.C = h->C; d.RC = h->RC;
+  d.ground_scan_id = h->P.ground_scan_id;
+  d.seg_valid_point_num = h->P.seg_valid_point_num;
+  d.seg_valid_line_num = h->P.seg_valid_line_num;
+  d.seg_min_cluster = h->P.seg_min_cluster;
+  d.ang_res_x = h->P.ang_res_x; d.ang_res_y = h->P.ang_res_y; d.ang_bottom = h->P.ang_bottom;
+  d.sensor_mount_ang = h->P.sensor_mount_ang;
+  d.seg_theta = h->P.seg_theta;
+  d.sin_x = h->seg_sin_x; d.cos_x = h->seg_cos_x; d.sin_y = h->seg_sin_y; d.cos_y = h->seg_cos_y;
+  return d;
+}
+
+int ip_run_device(AlegoHandle *h, bool want_labels) {
+  const IpDev P = make_ip_dev(h);
+  const int B = h->B;
+  cudaStream_t s = h->stream;
+  const int pt_blocks = min(div_up(h->Nmax, 256), 4096);
+  const int cell_blocks = min(div_up(h->RC, 256), 4096);
+  { LAUNCH(h, "ip_reset"); ip_reset_kernel<<<div_up(B, 128), 128, 0, s>>>(h->first_valid, h->last_valid, B); }
+  { LAUNCH(h, "ip_project");
+    ip_project_kernel<<<dim3(pt_blocks, B), 256, 0, s>>>(h->raw, h->n_pts, h->winner, h->first_valid, h->last_valid, h->Nmax, P); }
+  { LAUNCH(h, "ip_gather");
+    ip_gather_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->raw, h->winner, h->cloud, h->range, h->ground, h->Nmax, P); }
+  const int gpairs = min(P.ground_scan_id, P.R - 1) * P.C;
+  if (gpairs > 0) {
+    LAUNCH(h, "ip_ground");
+    ip_ground_kernel<<<dim3(min(div_up(gpairs, 256), 4096), B), 256, 0, s>>>(h->cloud, h->ground, P);
+  }
+  { LAUNCH(h, "ccl_init"); ccl_init_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->ground, h->parent, h->comp_stat, P); }
+  { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->parent, P); }
+  { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
+  { LAUNCH(h, "ip_rowcount");
+    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->raw, h->first_valid,
+                                                   h->last_valid, h->orient, h->Nmax, P); }
+  { LAUNCH(h, "ip_compact");
+    ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,
+                                                  h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring,
+                                                  h->end_ring, h->M, h->outlier, h->n_outlier, h->out_cap, P); }
+  if (want_labels) {
+    LAUNCH(h, "ip_label");
+    ip_label_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, h->comp_id, h->label, P);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}

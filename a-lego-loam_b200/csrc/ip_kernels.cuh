@@ -1,0 +1,12 @@
+// ip_kernels.cuh — device-side parameter block and host entry of the ImageProjection stage.
+#pragma once
+#include "common.cuh"
+
+struct IpDev {
+  int R, C, RC, ground_scan_id, seg_valid_point_num, seg_valid_line_num, seg_min_cluster;
+  double ang_res_x, ang_res_y, ang_bottom, sensor_mount_ang, seg_theta;
+  double sin_x, cos_x, sin_y, cos_y;  // sin/cos of seg_alpha_x / seg_alpha_y (utility.h:60-61), host libm
+};
+
+IpDev make_ip_dev(const AlegoHandle *h);
+int ip_run_device(AlegoHandle *h, bool want_labels);

@@ -1,0 +1,541 @@
+// lm_kernels.cu — LaserMapping scan-to-map on the device: replaces src/laserMapping.cpp:188-192, 325-489 and
+// pointAssociateToMap (include/alego/laserMapping.h:187-194).
+//
+//       lm_prepare   : transformAssociateToMap (:188-192)
+// K9    lm_voxel     : downsampleCurrentScan — four VoxelGrid filters (:325-346), one CTA per cloud
+// K13   grid_build   : (grid.cu) index of the local map, replaces the kd-tree builds (:356-357)
+// K14   lm_assoc<EDGE>  : per corner query — pointAssociateToMap, exact 5-NN, mean + 3x3 scatter, symmetric
+//                         eigen-solve, lambda2 > 3*lambda1 test, line end points (:371-417)
+// K15   lm_assoc<PLANE> : per surf query — 5-NN, 5x3 least squares A n = -1, normalise, 0.2 m test (:419-462)
+// K16/K17 lm_solve   : one CTA per sequence — LidarEdge/LidarPlane residuals, Huber, 6x6 reduction, LM
+//                      (solver.cuh), lm_outer_iters fresh solves (:360-478), transformUpdate (:481-489)
+#include "common.cuh"
+#include "grid.cuh"
+#include "lm_kernels.cuh"
+#include "solver.cuh"
+#include "sort_voxel.cuh"
+
+namespace {
+
+struct LmInputs {  // where the three input clouds of every sequence live
+  const float4 *ext_corner, *ext_surf, *ext_outlier;
+  int ext_cap_c, ext_cap_s, ext_cap_o;
+  const int *ext_n;  // [B][4]
+  const int *use_ext;  // [B]
+  const float4 *lo_corner, *lo_surf, *lo_outlier;  // less_sharp, less_flat, outlier of the current sweep
+  int lo_cap_c, lo_cap_s, lo_cap_o;
+  const int *lo_n_corner, *lo_n_surf;  // ring_off arrays, entry [b*(R+1)+R]
+  const int *lo_n_outlier;             // [B]
+  int R;
+};
+__device__ __forceinline__ const float4 *lm_input(const LmInputs &in, int b, int kind, int *n) {
+  if (in.use_ext[b]) {
+    *n = in.ext_n[b * 4 + kind];
+    if (kind == 0) { *n = min(*n, in.ext_cap_c); return in.ext_corner + (size_t)b * in.ext_cap_c; }
+    if (kind == 1) { *n = min(*n, in.ext_cap_s); return in.ext_surf + (size_t)b * in.ext_cap_s; }
+    *n = min(*n, in.ext_cap_o);
+    return in.ext_outlier + (size_t)b * in.ext_cap_o;
+  }
+  if (kind == 0) { *n = in.lo_n_corner[b * (in.R + 1) + in.R]; return in.lo_corner + (size_t)b * in.lo_cap_c; }
+  if (kind == 1) { *n = in.lo_n_surf[b * (in.R + 1) + in.R]; return in.lo_surf + (size_t)b * in.lo_cap_s; }
+  *n = in.lo_n_outlier[b];
+  return in.lo_outlier + (size_t)b * in.lo_cap_o;
+}
+
+__device__ __forceinline__ void mat3_mul_d(const double *A, const double *Bm, double *C) {
+  double t[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) t[r * 3 + c] = A[r * 3] * Bm[c] + A[r * 3 + 1] * Bm[3 + c] + A[r * 3 + 2] * Bm[6 + c];
+  for (int q = 0; q < 9; ++q) C[q] = t[q];
+}
+
+// transformAssociateToMap (:188-192); in pipeline mode odom2laser is LaserOdometry's (t_w_cur_, r_w_cur_)
+__global__ void lm_prepare_kernel(const int *use_ext, const double *t_w, const double *r_w, Pose *o2l, const Pose *m2o, Pose *m2l, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (!use_ext[b]) {
+    for (int q = 0; q < 3; ++q) o2l[b].t[q] = t_w[b * 3 + q];
+    for (int q = 0; q < 9; ++q) o2l[b].R[q] = r_w[b * 9 + q];
+  }
+  const Pose &mo = m2o[b];
+  const Pose &ol = o2l[b];
+  for (int r = 0; r < 3; ++r) m2l[b].t[r] = mo.R[r * 3] * ol.t[0] + mo.R[r * 3 + 1] * ol.t[1] + mo.R[r * 3 + 2] * ol.t[2] + mo.t[r];
+  mat3_mul_d(mo.R, ol.R, m2l[b].R);
+}
+
+#define LMV_THREADS 1024
+#define LMV_STAGE 8192  // keys of shared-memory staging (64 KB)
+// kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launch)
+__global__ void __launch_bounds__(LMV_THREADS)
+lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s, float4 *ds_o,
+                float4 *total, float4 *ds_total, int cap_c, int cap_s, int cap_o, int *lm_n, u64 *sort_c, u64 *sort_s, u64 *sort_o,
+                int sort_cap_c, int sort_cap_s, int sort_cap_o) {
+  extern __shared__ __align__(16) uint8_t lmv_smem[];
+  u64 *stage = reinterpret_cast<u64 *>(lmv_smem);
+  __shared__ float redf[6 * 32 + 8];
+  __shared__ int redi[48];
+  __shared__ VoxFrame frame;
+  const int b = blockIdx.x, kind = first_kind + blockIdx.y;
+  const float4 *src;
+  int n;
+  float leaf;
+  float4 *dst;
+  u64 *keys;
+  int sort_cap;
+  if (kind == 3) {
+    // laser_surf_total_ = laser_surf_ds_ + laser_outlier_ds_ (:337-340)
+    const int ns = lm_n[b * 8 + 1], no = lm_n[b * 8 + 2];
+    float4 *tot = total + (size_t)b * (cap_s + cap_o);
+    for (int t = threadIdx.x; t < ns; t += blockDim.x) tot[t] = ds_s[(size_t)b * cap_s + t];
+    for (int t = threadIdx.x; t < no; t += blockDim.x) tot[ns + t] = ds_o[(size_t)b * cap_o + t];
+    __syncthreads();
+    src = tot; n = ns + no; leaf = leaf_s;
+    dst = ds_total + (size_t)b * (cap_s + cap_o);
+    keys = sort_s + (size_t)b * sort_cap_s; sort_cap = sort_cap_s;
+    if (threadIdx.x == 0) lm_n[b * 8 + 3] = n;
+  } else {
+    src = lm_input(in, b, kind, &n);
+    if (kind == 0) { leaf = leaf_c; dst = ds_c + (size_t)b * cap_c; keys = sort_c + (size_t)b * sort_cap_c; sort_cap = sort_cap_c; n = min(n, cap_c); }
+    else if (kind == 1) { leaf = leaf_s; dst = ds_s + (size_t)b * cap_s; keys = sort_s + (size_t)b * sort_cap_s; sort_cap = sort_cap_s; n = min(n, cap_s); }
+    else { leaf = leaf_o; dst = ds_o + (size_t)b * cap_o; keys = sort_o + (size_t)b * sort_cap_o; sort_cap = sort_cap_o; n = min(n, cap_o); }
+  }
+  n = min(n, sort_cap);
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  const int n_out = block_voxel_grid(src, n, leaf, keys, npad, false, stage, LMV_STAGE, dst, redf, redi, &frame);
+  if (threadIdx.x == 0) lm_n[b * 8 + (kind == 3 ? 4 : kind)] = n_out;
+}
+
+// stand-alone VoxelGrid of one device cloud (alego_voxel_grid)
+__global__ void __launch_bounds__(LMV_THREADS)
+voxel_single_kernel(const float4 *src, int n, float leaf, float4 *dst, u64 *keys, int npad, int *n_out) {
+  extern __shared__ __align__(16) uint8_t lmv_smem[];
+  u64 *stage = reinterpret_cast<u64 *>(lmv_smem);
+  __shared__ float redf[6 * 32 + 8];
+  __shared__ int redi[48];
+  __shared__ VoxFrame frame;
+  const int m = block_voxel_grid(src, n, leaf, keys, npad, false, stage, LMV_STAGE, dst, redf, redi, &frame);
+  if (threadIdx.x == 0) *n_out = m;
+}
+
+// ---- small dense helpers (same algorithms as the oracle, so results agree to rounding) -------------
+// symmetric 3x3 eigen-decomposition by cyclic Jacobi; eigenvalues ascending (Eigen::SelfAdjointEigenSolver
+// convention, laserMapping.cpp:397-403); V columns = eigenvectors
+__device__ void eig3_sym_dev(const double A[9], double w[3], double V[9]) {
+  double a[3][3] = {{A[0], A[1], A[2]}, {A[3], A[4], A[5]}, {A[6], A[7], A[8]}};
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const double dsum = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-40 * dsum || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - s * vkq;
+          v[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int o0 = 0, o1 = 1, o2 = 2;  // stable ascending order of the diagonal
+  if (a[o1][o1] < a[o0][o0]) { int t = o0; o0 = o1; o1 = t; }
+  if (a[o2][o2] < a[o1][o1]) { int t = o1; o1 = o2; o2 = t; }
+  if (a[o1][o1] < a[o0][o0]) { int t = o0; o0 = o1; o1 = t; }
+  const int ord[3] = {o0, o1, o2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    w[k] = a[ord[k]][ord[k]];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) V[r * 3 + k] = v[r][ord[k]];
+  }
+}
+
+// least squares of the 5x3 system A n = b by column-pivoted Householder QR (colPivHouseholderQr().solve, :435)
+__device__ void lstsq_5x3_dev(double A[5][3], double b[5], double n[3]) {
+  int perm[3] = {0, 1, 2};
+  int rank = 3;
+  for (int c = 0; c < 3; ++c) {
+    int best = c;
+    double bn = -1;
+    for (int c2 = c; c2 < 3; ++c2) {
+      double q = 0;
+      for (int i = c; i < 5; ++i) q += A[i][c2] * A[i][c2];
+      if (q > bn) { bn = q; best = c2; }
+    }
+    if (best != c) {
+      for (int i = 0; i < 5; ++i) { const double t = A[i][c]; A[i][c] = A[i][best]; A[i][best] = t; }
+      const int t = perm[c]; perm[c] = perm[best]; perm[best] = t;
+    }
+    const double nrm = sqrt(bn);
+    if (nrm < 1e-300) { rank = c; break; }
+    const double alpha = A[c][c] > 0 ? -nrm : nrm;
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int i = c; i < 5; ++i) v[i] = A[i][c];
+    v[c] -= alpha;
+    double vn = 0;
+    for (int i = c; i < 5; ++i) vn += v[i] * v[i];
+    if (vn > 0) {
+      for (int c2 = c; c2 < 3; ++c2) {
+        double dot = 0;
+        for (int i = c; i < 5; ++i) dot += v[i] * A[i][c2];
+        const double f = 2.0 * dot / vn;
+        for (int i = c; i < 5; ++i) A[i][c2] -= f * v[i];
+      }
+      double dot = 0;
+      for (int i = c; i < 5; ++i) dot += v[i] * b[i];
+      const double f = 2.0 * dot / vn;
+      for (int i = c; i < 5; ++i) b[i] -= f * v[i];
+    }
+  }
+  double y[3] = {0, 0, 0};
+  for (int c = rank - 1; c >= 0; --c) {
+    double acc = b[c];
+    for (int c2 = c + 1; c2 < rank; ++c2) acc -= A[c][c2] * y[c2];
+    y[c] = acc / A[c][c];
+  }
+  for (int c = 0; c < 3; ++c) n[perm[c]] = y[c];
+}
+
+// exact 5 nearest neighbours within squared distance < 1.0 (float), ascending (distance, index).
+// A cell edge >= 1 m makes the 27 surrounding cells sufficient for every neighbour that can pass the gate.
+__device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, float qy, float qz, float *bd, int *bi) {
+  const int T = g.table_size;
+  const int *cs = g.cell_start + (size_t)b * (T + 1);
+  const float4 *sp = g.sorted + (size_t)b * g.cap;
+  const float inv = 1.0f / g.cell;
+  const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);
+#pragma unroll
+  for (int t = 0; t < 5; ++t) { bd[t] = 3.402823466e+38f; bi[t] = 0x7fffffff; }
+  int found = 0;
+  int seen[27];
+  int nseen = 0;
+  for (int c = 0; c < 27; ++c) {
+    const int hsh = grid_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, T);
+    bool dup = false;  // two of the 27 cells can share a bucket: visit it once
+    for (int u = 0; u < nseen; ++u) dup |= (seen[u] == hsh);
+    if (dup) continue;
+    seen[nseen++] = hsh;
+    const int e = cs[hsh + 1];
+    for (int t = cs[hsh]; t < e; ++t) {
+      const float4 p = sp[t];
+      const float d = l2_simple(qx, qy, qz, p);
+      if (!(d < 1.0f)) continue;
+      const int idx = __float_as_int(p.w);
+      if (d < bd[4] || (d == bd[4] && idx < bi[4])) {
+        int pos = 4;
+        while (pos > 0 && (d < bd[pos - 1] || (d == bd[pos - 1] && idx < bi[pos - 1]))) {
+          bd[pos] = bd[pos - 1];
+          bi[pos] = bi[pos - 1];
+          --pos;
+        }
+        bd[pos] = d;
+        bi[pos] = idx;
+        ++found;
+      }
+    }
+  }
+  return found < 5 ? found : 5;
+}
+
+template <bool EDGE>
+__global__ void __launch_bounds__(128)
+lm_assoc_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, const float4 *__restrict__ map,
+                int map_cap, const int *__restrict__ n_map, GridIndex g, const Pose *__restrict__ m2l, const int *__restrict__ guard,
+                double *__restrict__ out, int out_w) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = min(lm_n[b * 8 + n_slot], qcap);
+  if (i >= nq) return;
+  double *o = out + ((size_t)b * qcap + i) * out_w;
+  o[0] = 0.0;
+  if (!guard[b]) return;
+  const float4 cp = query[(size_t)b * qcap + i];
+  const Pose &P = m2l[b];
+  // pointAssociateToMap (laserMapping.h:187-194): double transform, float result
+  const float sx = (float)(P.R[0] * cp.x + P.R[1] * cp.y + P.R[2] * cp.z + P.t[0]);
+  const float sy = (float)(P.R[3] * cp.x + P.R[4] * cp.y + P.R[5] * cp.z + P.t[1]);
+  const float sz = (float)(P.R[6] * cp.x + P.R[7] * cp.y + P.R[8] * cp.z + P.t[2]);
+  float bd[5];
+  int bi[5];
+  if (knn5_gate(g, b, sx, sy, sz, bd, bi) < 5) return;  // point_dist_[4] < 1.0 (:376, :426)
+  const float4 *M = map + (size_t)b * map_cap;
+  double nb[5][3];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float4 p = M[bi[j]];
+    nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
+  }
+  if (EDGE) {
+    double center[3] = {0, 0, 0};
+    for (int j = 0; j < 5; ++j)
+      for (int c = 0; c < 3; ++c) center[c] = center[c] + nb[j][c];
+    for (int c = 0; c < 3; ++c) center[c] = center[c] / 5.0;
+    double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 5; ++j) {
+      const double zm[3] = {nb[j][0] - center[0], nb[j][1] - center[1], nb[j][2] - center[2]};
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) cov[r * 3 + c] = cov[r * 3 + c] + zm[r] * zm[c];
+    }
+    double w[3], V[9];
+    eig3_sym_dev(cov, w, V);
+    if (!(w[2] > 3 * w[1])) return;  // (:403)
+    o[1] = cp.x; o[2] = cp.y; o[3] = cp.z;
+    for (int c = 0; c < 3; ++c) {
+      const double u = V[c * 3 + 2];
+      o[4 + c] = 0.1 * u + center[c];   // lpj (:406)
+      o[7 + c] = -0.1 * u + center[c];  // lpl (:407)
+    }
+    o[0] = 1.0;
+  } else {
+    double A[5][3], rhs[5] = {-1, -1, -1, -1, -1}, nrm[3];
+    for (int j = 0; j < 5; ++j)
+      for (int c = 0; c < 3; ++c) A[j][c] = nb[j][c];
+    lstsq_5x3_dev(A, rhs, nrm);
+    const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    const double d = 1 / nn;
+    for (int c = 0; c < 3; ++c) nrm[c] /= nn;
+    for (int j = 0; j < 5; ++j)
+      if (fabs(nrm[0] * nb[j][0] + nrm[1] * nb[j][1] + nrm[2] * nb[j][2] + d) > 0.2) return;  // (:441-452)
+    o[1] = cp.x; o[2] = cp.y; o[3] = cp.z;
+    o[4] = nrm[0]; o[5] = nrm[1]; o[6] = nrm[2];
+    o[7] = d;
+    o[0] = 1.0;
+  }
+}
+
+// guard of scan2MapOptimization (:350-354)
+__global__ void lm_guard_kernel(const int *lm_n, const int *n_map_corner, int *guard, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  guard[b] = !(lm_n[b * 8 + 0] < 10 || lm_n[b * 8 + 3] < 100 || n_map_corner[b] < 10);
+}
+
+struct LmResidSet {
+  const double *edge;
+  int n_edge_slots;
+  const double *plane;
+  int n_plane_slots;
+  __device__ int slots() const { return n_edge_slots + n_plane_slots; }
+  __device__ bool load(int i, int &kind, double cp[3], double a[3], double b[3], double c[3], double &d) const {
+    if (i < n_edge_slots) {
+      const double *e = edge + (size_t)i * 10;
+      if (e[0] == 0.0) return false;
+      kind = 2;
+      for (int q = 0; q < 3; ++q) { cp[q] = e[1 + q]; a[q] = e[4 + q]; b[q] = e[7 + q]; c[q] = 0; }
+      d = 0;
+      return true;
+    }
+    const double *p = plane + (size_t)(i - n_edge_slots) * 8;
+    if (p[0] == 0.0) return false;
+    kind = 3;
+    for (int q = 0; q < 3; ++q) { cp[q] = p[1 + q]; a[q] = p[4 + q]; b[q] = 0; c[q] = 0; }
+    d = p[7];
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restrict__ plane, int pcap, const int *__restrict__ lm_n,
+                const int *__restrict__ guard, double *lm_params, Pose *m2o, const Pose *o2l, Pose *m2l, AlegoSolveReport *report,
+                double *trace, int *trace_n, int trace_cap, int outer_iters, int max_iters, double huber_a, double *pose_out,
+                const double *t_w) {
+  const int b = blockIdx.x;
+  __shared__ LmShared sh;
+  __shared__ int s_red[34];
+  __shared__ int s_cnt[2];
+  AlegoSolveReport *rep = report + b;
+  double *x = lm_params + b * 6;
+  LmResidSet rs;
+  rs.edge = edge + (size_t)b * ecap * 10;
+  rs.n_edge_slots = min(lm_n[b * 8 + 0], ecap);
+  rs.plane = plane + (size_t)b * pcap * 8;
+  rs.n_plane_slots = min(lm_n[b * 8 + 4], pcap);
+  if (threadIdx.x == 0) trace_n[b] = 0;
+  const bool ok = guard[b] != 0;
+  int ne = 0, np = 0;
+  if (ok) {
+    for (int i = threadIdx.x; i < rs.n_edge_slots; i += blockDim.x) ne += rs.edge[(size_t)i * 10] != 0.0;
+    for (int i = threadIdx.x; i < rs.n_plane_slots; i += blockDim.x) np += rs.plane[(size_t)i * 8] != 0.0;
+  }
+  int tot;
+  block_excl_scan(ne, s_red, &tot);
+  if (threadIdx.x == 0) s_cnt[0] = tot;
+  block_excl_scan(np, s_red, &tot);
+  if (threadIdx.x == 0) s_cnt[1] = tot;
+  __syncthreads();
+  ne = s_cnt[0];
+  np = s_cnt[1];
+  if (threadIdx.x == 0) {
+    rep->status = ok ? ALEGO_OK : ALEGO_FEW_FEATURES;
+    rep->n_corner = ne; rep->n_surf = np; rep->iterations = 0; rep->initial_cost = 0; rep->final_cost = 0;
+  }
+  __syncthreads();
+  if (ok && ne + np > 0) {
+    double *tr = trace ? trace + (size_t)b * trace_cap * 7 : nullptr;
+    for (int outer = 0; outer < outer_iters; ++outer) {  // (:360) the association pose is frozen, so both outer
+      // iterations see the same correspondences; the second Solve continues from the first
+      const LmResult r = block_lm_solve(rs, x, max_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
+      if (threadIdx.x == 0) {
+        if (outer == 0) rep->initial_cost = r.initial_cost;
+        rep->iterations += r.iterations;
+        rep->final_cost = r.final_cost;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {  // transformUpdate (:481-489)
+    const PoseTrig T(x);
+    Pose &ml = m2l[b];
+    for (int q = 0; q < 9; ++q) ml.R[q] = T.R[q];
+    for (int q = 0; q < 3; ++q) ml.t[q] = x[q];
+    const Pose &ol = o2l[b];
+    const double inv[9] = {ol.R[0], ol.R[3], ol.R[6], ol.R[1], ol.R[4], ol.R[7], ol.R[2], ol.R[5], ol.R[8]};
+    Pose &mo = m2o[b];
+    mat3_mul_d(ml.R, inv, mo.R);
+    for (int r = 0; r < 3; ++r) mo.t[r] = ml.t[r] - (mo.R[r * 3] * ol.t[0] + mo.R[r * 3 + 1] * ol.t[1] + mo.R[r * 3 + 2] * ol.t[2]);
+    if (pose_out) {
+      double *po = pose_out + b * 12;
+      for (int q = 0; q < 3; ++q) po[q] = ml.t[q];
+      for (int q = 0; q < 6; ++q) po[3 + q] = x[q];
+      for (int q = 0; q < 3; ++q) po[9 + q] = t_w ? t_w[b * 3 + q] : 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need_o);
+
+static LmInputs make_inputs(AlegoHandle *h) {
+  LmInputs in;
+  in.ext_corner = h->lm_in_corner; in.ext_surf = h->lm_in_surf; in.ext_outlier = h->lm_in_outlier;
+  in.ext_cap_c = h->lm_cap_c; in.ext_cap_s = h->lm_cap_s; in.ext_cap_o = h->lm_cap_o;
+  in.ext_n = h->lm_in_n;
+  in.use_ext = h->lm_use_ext;
+  const int buf = 1 - h->cur;  // lo_scan2scan_device flipped the buffers: the sweep just processed is in 1-cur
+  in.lo_corner = h->less_sharp[buf]; in.lo_surf = h->less_flat[buf]; in.lo_outlier = h->outlier;
+  in.lo_cap_c = h->R * 120; in.lo_cap_s = h->RC; in.lo_cap_o = h->out_cap;
+  in.lo_n_corner = h->ls_ring_off[buf]; in.lo_n_surf = h->lf_ring_off[buf]; in.lo_n_outlier = h->n_outlier;
+  in.R = h->R;
+  return in;
+}
+
+int lm_build_map_index(AlegoHandle *h) {
+  int rc = grid_build(h, &h->g_map_corner, h->map_corner, (size_t)h->map_cap_c, h->n_map_corner, 1, "map_corner");
+  if (rc != ALEGO_OK) return rc;
+  rc = grid_build(h, &h->g_map_surf, h->map_surf, (size_t)h->map_cap_s, h->n_map_surf, 1, "map_surf");
+  if (rc != ALEGO_OK) return rc;
+  h->map_index_valid = true;
+  return ALEGO_OK;
+}
+
+int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose) {
+  const int B = h->B;
+  cudaStream_t s = h->stream;
+  if (!h->map_corner || !h->map_surf) { h->err = "alego_lm_scan2map: no local map (call alego_lm_set_map)"; return ALEGO_NOT_READY; }
+  int rc = lm_ensure_ds_buffers(h, 0, 0, 0);
+  if (rc != ALEGO_OK) return rc;
+  const LmInputs in = make_inputs(h);
+  { LAUNCH(h, "lm_prepare"); lm_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_use_ext, h->t_w, h->r_w, h->o2l, h->m2o, h->m2l, B); }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(lm_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LMV_STAGE * 8));
+    attr_set = true;
+  }
+  const int cs = h->ds_cap_s, cc = h->ds_cap_c, co = h->ds_cap_o;
+  u64 *sort_c = h->vox_sort, *sort_s = sort_c + (size_t)B * next_pow2(cc), *sort_o = sort_s + (size_t)B * next_pow2(cs + co);
+  { LAUNCH(h, "lm_voxel_3");
+    lm_voxel_kernel<<<dim3(B, 3), LMV_THREADS, LMV_STAGE * 8, s>>>(in, 0, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
+        (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
+        h->lm_n, sort_c, sort_s, sort_o, next_pow2(cc), next_pow2(cs + co), next_pow2(co)); }
+  { LAUNCH(h, "lm_voxel_total");
+    lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_STAGE * 8, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
+        (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
+        h->lm_n, sort_c, sort_s, sort_o, next_pow2(cc), next_pow2(cs + co), next_pow2(co)); }
+  if (h->rebuild_map_every_step || !h->map_index_valid) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
+    rc = lm_build_map_index(h);
+    if (rc != ALEGO_OK) return rc;
+  }
+  { LAUNCH(h, "lm_guard"); lm_guard_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_n, h->n_map_corner, guard_dev, B); }
+  { LAUNCH(h, "lm_assoc_corner");
+    lm_assoc_kernel<true><<<dim3(div_up(cc, 128), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
+        h->n_map_corner, h->g_map_corner, h->m2l, guard_dev, h->lm_edge, 10); }
+  { LAUNCH(h, "lm_assoc_surf");
+    lm_assoc_kernel<false><<<dim3(div_up(cs + co, 128), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf,
+        h->map_cap_s, h->n_map_surf, h->g_map_surf, h->m2l, guard_dev, h->lm_plane, 8); }
+  { LAUNCH(h, "lm_solve");
+    lm_solve_kernel<<<B, 256, 0, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
+        h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
+        write_pose ? h->d_pose : nullptr, h->t_w); }
+  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}
+
+// downsampled-cloud / residual buffers, sized from the largest possible inputs
+static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need_o) {
+  const int B = h->B;
+  int want_c = std::max(std::max(h->R * 120, h->lm_cap_c), need_c);
+  int want_s = std::max(std::max(h->RC, h->lm_cap_s), need_s);
+  int want_o = std::max(std::max(h->out_cap, h->lm_cap_o), need_o);
+  if (h->lm_corner_ds && want_c <= h->ds_cap_c && want_s <= h->ds_cap_s && want_o <= h->ds_cap_o) return ALEGO_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->lm_corner_ds); cudaFree(h->lm_surf_ds); cudaFree(h->lm_outlier_ds); cudaFree(h->lm_surf_total);
+  cudaFree(h->lm_surf_total_ds); cudaFree(h->lm_edge); cudaFree(h->lm_plane); cudaFree(h->vox_sort);
+  h->ds_cap_c = want_c; h->ds_cap_s = want_s; h->ds_cap_o = want_o;
+  CUDA_TRY(h, cudaMalloc(&h->lm_corner_ds, (size_t)B * want_c * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_surf_ds, (size_t)B * want_s * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_outlier_ds, (size_t)B * want_o * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_surf_total, (size_t)B * (want_s + want_o) * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_surf_total_ds, (size_t)B * (want_s + want_o) * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_edge, (size_t)B * want_c * 10 * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_plane, (size_t)B * (want_s + want_o) * 8 * sizeof(double)));
+  const size_t sort_elems = (size_t)B * ((size_t)next_pow2(want_c) + next_pow2(want_s + want_o) + next_pow2(want_o));
+  CUDA_TRY(h, cudaMalloc(&h->vox_sort, sort_elems * sizeof(u64)));
+  return ALEGO_OK;
+}
+
+int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float *out_xyzi, int *n_out) {
+  cudaStream_t s = h->stream;
+  if (n == 0) { *n_out = 0; return ALEGO_OK; }
+  const int npad = next_pow2(n);
+  float4 *d_in = nullptr, *d_out = nullptr;
+  u64 *d_keys = nullptr;
+  int *d_n = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d_in, (size_t)n * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&d_out, (size_t)n * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)npad * sizeof(u64)));
+  CUDA_TRY(h, cudaMalloc(&d_n, sizeof(int)));
+  CUDA_TRY(h, cudaMemcpyAsync(d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LMV_STAGE * 8));
+  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_STAGE * 8, s>>>(d_in, n, leaf, d_out, d_keys, npad, d_n); }
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(n_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (out_xyzi && *n_out > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(out_xyzi, d_out, (size_t)*n_out * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+  }
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_n);
+  return ALEGO_OK;
+}
+
+int lm_ensure_buffers(AlegoHandle *h, int need_c, int need_s, int need_o) { return lm_ensure_ds_buffers(h, need_c, need_s, need_o); }

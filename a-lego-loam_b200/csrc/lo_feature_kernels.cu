@@ -1,0 +1,351 @@
+// lo_feature_kernels.cu — LaserOdometry feature extraction on the device: replaces steps 2-4 of
+// LaserOdometry::mainLoop (src/laserOdometry.cpp:118-297).
+//
+// K6+K7 lo_curv_occl      : 11-tap float range stencil (:122-129) fused with markOccludedPoints (:131-159);
+//                           the ±6 window of ranges / columns is staged in shared memory
+// K8a   lo_sort_segments  : per ring segment, the exact permutation std::sort would produce (:185)
+// K8b   lo_select         : one warp per ring walks its 6 segments in order (:188-286)
+// K9    lo_less_flat_voxel: per-ring VoxelGrid(0.4) of the less-flat points (:279-293)
+//       lo_finalize       : ring-major concatenation of the per-ring lists / clouds
+#include "common.cuh"
+#include "lo_kernels.cuh"
+#include "sort_voxel.cuh"
+#include "stdsort_clone.cuh"
+
+namespace {
+
+#define CURV_TILE 256
+
+__global__ void __launch_bounds__(CURV_TILE)
+lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__ seg_col, const int *__restrict__ Mdev,
+                    float *__restrict__ curv, uint8_t *__restrict__ picked0, int *__restrict__ flabel,
+                    int *__restrict__ sort_idx, int RC) {
+  const int b = blockIdx.y;
+  const int M = Mdev[b];
+  const int tile_lo = blockIdx.x * CURV_TILE;
+  if (tile_lo >= M) return;
+  const size_t base = (size_t)b * RC;
+  __shared__ float sr[CURV_TILE + 12];
+  __shared__ int sc[CURV_TILE + 12];
+  for (int t = threadIdx.x; t < CURV_TILE + 12; t += CURV_TILE) {
+    const int g = tile_lo - 6 + t;
+    const bool ok = g >= 0 && g < M;
+    sr[t] = ok ? seg_range[base + g] : 0.f;
+    sc[t] = ok ? seg_col[base + g] : 0;
+  }
+  __syncthreads();
+  const int i = tile_lo + threadIdx.x;
+  if (i >= M) return;
+  const int li = threadIdx.x + 6;
+  float c = 0.f;
+  bool pk = false;
+  const int lo = 5, hi = M - 5;  // loop bounds of both reference loops: i in [5, M-5)
+  if (i >= lo && i < hi) {
+    // (:124) float sum, strictly left to right, r[i]*10 is a float product; compiled without FMA contraction
+    const float d = sr[li - 5] + sr[li - 4] + sr[li - 3] + sr[li - 2] + sr[li - 1] - sr[li] * 10 + sr[li + 1] + sr[li + 2] +
+                    sr[li + 3] + sr[li + 4] + sr[li + 5];
+    c = fabsf(d);  // cloud_curvature_ = double(d)*double(d) is recovered exactly as (double)c*(double)c
+  }
+  // markOccludedPoints as a gather: which iterations j of the reference loop mark position i?
+#pragma unroll
+  for (int o = 0; o <= 5; ++o) {  // j = i+o marks j-5..j when depth1 - depth2 > 0.5 (:140-145)
+    const int j = i + o, lj = li + o;
+    if (j >= lo && j < hi && abs(sc[lj] - sc[lj + 1]) < 10 && (double)sr[lj] - (double)sr[lj + 1] > 0.5) pk = true;
+  }
+#pragma unroll
+  for (int o = 1; o <= 5; ++o) {  // j = i-o marks j+1..j+5 when depth2 - depth1 > 0.5 (:146-150)
+    const int j = i - o, lj = li - o;
+    if (j >= lo && j < hi && abs(sc[lj] - sc[lj + 1]) < 10) {
+      const double d1 = sr[lj], d2 = sr[lj + 1];
+      if (!(d1 - d2 > 0.5) && d2 - d1 > 0.5) pk = true;
+    }
+  }
+  if (i >= lo && i < hi) {  // parallel-beam test, skipped by the `continue` of the first branch (:144,152-158)
+    const double d1 = sr[li], d2 = sr[li + 1];
+    const bool first_branch = abs(sc[li] - sc[li + 1]) < 10 && d1 - d2 > 0.5;
+    if (!first_branch) {
+      const double diff1 = fabs((double)sr[li - 1] - d1), diff2 = fabs(d2 - d1), thr = 0.02 * (double)sr[li];
+      if (diff1 > thr && diff2 > thr) pk = true;
+    }
+  }
+  curv[base + i] = c;
+  picked0[base + i] = pk ? 1 : 0;
+  flabel[base + i] = 0;
+  sort_idx[base + i] = i;
+}
+
+// segment bounds (:177-178)
+__device__ __forceinline__ void segment_bounds(int start, int end, int j, int &sp, int &ep) {
+  sp = (start * (6 - j) + end * j) / 6;
+  ep = (start * (5 - j) + end * (j + 1)) / 6 - 1;
+}
+
+// one thread per (sequence, ring, segment): the permutation libstdc++'s std::sort leaves, ties included
+__global__ void __launch_bounds__(64)
+lo_sort_segments_kernel(const float *__restrict__ curv, const int *__restrict__ start_ring, const int *__restrict__ end_ring,
+                        unsigned long long *__restrict__ scratch, int *__restrict__ sort_idx, int B, int R, int RC) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * R * 6) return;
+  const int b = t / (R * 6), rs = t - b * R * 6, ring = rs / 6, j = rs - ring * 6;
+  int sp, ep;
+  segment_bounds(start_ring[b * R + ring], end_ring[b * R + ring], j, sp, ep);
+  if (sp >= ep) return;
+  const size_t base = (size_t)b * RC;
+  unsigned long long *e = scratch + base + sp;
+  const int n = ep - sp + 1;
+  for (int k = 0; k < n; ++k) e[k] = ((unsigned long long)__float_as_uint(curv[base + sp + k]) << 32) | (unsigned)(sp + k);
+  ssc::sort(e, n);
+  for (int k = 0; k < n; ++k) sort_idx[base + sp + k] = (int)(e[k] & 0xffffffffu);
+}
+
+// neighbour suppression (:211-234, 252-275) executed by one lane; pk is the ring's picked window
+__device__ __forceinline__ void suppress(const int *__restrict__ col, uint8_t *pk, int idx, int lo) {
+  for (int l = 1; l <= 5; ++l) {
+    if (abs(col[idx + l] - col[idx + l - 1]) > 10) break;
+    pk[idx + l - lo] = 1;
+  }
+  for (int l = -1; l >= -5; --l) {
+    if (abs(col[idx + l] - col[idx + l + 1]) > 10) break;
+    pk[idx + l - lo] = 1;
+  }
+}
+
+#define SEL_WARPS 4
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ seg_ground, const float *__restrict__ curv,
+                 const int *__restrict__ sort_idx, const int *__restrict__ start_ring, const int *__restrict__ end_ring,
+                 const uint8_t *__restrict__ picked0, uint8_t *__restrict__ picked, int *__restrict__ flabel,
+                 int *__restrict__ ring_feat_cnt, int *__restrict__ ring_sharp, int *__restrict__ ring_less_sharp,
+                 int *__restrict__ ring_flat, int R, int RC, int pkcap) {
+  extern __shared__ uint8_t sel_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ring = blockIdx.x * SEL_WARPS + warp, b = blockIdx.y;
+  if (ring >= R) return;
+  const size_t base = (size_t)b * RC;
+  const int br = b * R + ring;
+  const int start = start_ring[br], end = end_ring[br];
+  const int lo = start - 5, len = end + 5 - lo + 1;  // the ring's kept points are [lo, lo+len)
+  uint8_t *pk = sel_smem + (size_t)warp * pkcap;
+  for (int t = lane; t < len; t += 32) pk[t] = picked0[base + lo + t];
+  __syncwarp();
+  const int *col = seg_col + base;
+  int n_sharp = 0, n_less = 0, n_flat = 0;
+  for (int j = 0; j < 6; ++j) {
+    int sp, ep;
+    segment_bounds(start, end, j, sp, ep);
+    if (sp >= ep) continue;
+    // ---- sharp / less sharp: descending curvature (:188-236)
+    int picked_num = 0;
+    bool stop = false;
+    for (int kk = ep; kk >= sp && !stop; kk -= 32) {
+      const int k = kk - lane;
+      const bool inr = k >= sp;
+      const int idx = inr ? sort_idx[base + k] : sp;
+      const float c = inr ? curv[base + idx] : 0.f;
+      const bool thr = inr && (double)c * (double)c > 0.1;
+      const bool nong = inr && seg_ground[base + idx] == 0;
+      if (__ballot_sync(0xffffffffu, thr) == 0) break;  // sorted: nothing further can exceed the threshold
+      int cursor = 0;
+      while (true) {
+        const bool cand = thr && nong && lane >= cursor && pk[idx - lo] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (!m) break;
+        const int first = __ffs(m) - 1;
+        ++picked_num;
+        if (lane == first) {
+          pk[idx - lo] = 1;
+          if (picked_num <= 2) {
+            flabel[base + idx] = 2;
+            ring_sharp[br * 12 + n_sharp] = idx;
+            ring_less_sharp[br * 120 + n_less] = idx;
+          } else if (picked_num <= 20) {
+            flabel[base + idx] = 1;
+            ring_less_sharp[br * 120 + n_less] = idx;
+          }
+        }
+        if (picked_num <= 2) { ++n_sharp; ++n_less; }
+        else if (picked_num <= 20) ++n_less;
+        else { stop = true; __syncwarp(); break; }  // 21st candidate: marked picked, no label, walk ends (:207-210)
+        if (lane == first) suppress(col, pk, idx, lo);
+        __syncwarp();
+        cursor = first + 1;
+      }
+    }
+    __syncwarp();
+    // ---- flat: ascending curvature (:238-277)
+    picked_num = 0;
+    stop = false;
+    for (int kk = sp; kk <= ep && !stop; kk += 32) {
+      const int k = kk + lane;
+      const bool inr = k <= ep;
+      const int idx = inr ? sort_idx[base + k] : sp;
+      const float c = inr ? curv[base + idx] : 1e30f;
+      const bool thr = inr && (double)c * (double)c < 0.1;
+      const bool gr = inr && seg_ground[base + idx] == 1;
+      if (__ballot_sync(0xffffffffu, thr) == 0) break;
+      int cursor = 0;
+      while (true) {
+        const bool cand = thr && gr && lane >= cursor && pk[idx - lo] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (!m) break;
+        const int first = __ffs(m) - 1;
+        ++picked_num;
+        if (lane == first) {
+          flabel[base + idx] = -1;
+          ring_flat[br * 24 + n_flat] = idx;
+          pk[idx - lo] = 1;
+        }
+        ++n_flat;
+        if (picked_num >= 4) { stop = true; __syncwarp(); break; }  // breaks before the suppression (:248-251)
+        if (lane == first) suppress(col, pk, idx, lo);
+        __syncwarp();
+        cursor = first + 1;
+      }
+    }
+    __syncwarp();
+  }
+  for (int t = lane; t < len; t += 32) picked[base + lo + t] = pk[t];
+  if (lane == 0) {
+    ring_feat_cnt[br * 4 + 0] = n_sharp;
+    ring_feat_cnt[br * 4 + 1] = n_less;
+    ring_feat_cnt[br * 4 + 2] = n_flat;
+  }
+}
+
+// per-ring less_flat_scan (:279-285) + VoxelGrid (:288-293).  Output staged at lf_stage[lo...] of the ring.
+#define LFV_THREADS 256
+__global__ void __launch_bounds__(LFV_THREADS)
+lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ flabel, const int *__restrict__ start_ring,
+                          const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt, int R,
+                          int RC, int pts_cap, int key_cap, float leaf) {
+  extern __shared__ __align__(16) uint8_t lfv_smem[];
+  float4 *pts = reinterpret_cast<float4 *>(lfv_smem);
+  u64 *keys = reinterpret_cast<u64 *>(lfv_smem + (size_t)pts_cap * sizeof(float4));
+  __shared__ float redf[48];
+  __shared__ int redi[48];
+  __shared__ VoxFrame frame;
+  __shared__ int seg_sp[6], seg_ep[6];
+  const int ring = blockIdx.x, b = blockIdx.y, br = b * R + ring;
+  const size_t base = (size_t)b * RC;
+  const int start = start_ring[br], end = end_ring[br];
+  if (threadIdx.x < 6) {
+    int sp, ep;
+    segment_bounds(start, end, threadIdx.x, sp, ep);
+    seg_sp[threadIdx.x] = sp;
+    seg_ep[threadIdx.x] = ep;
+  }
+  __syncthreads();
+  // ordered compaction of {k in a processed segment : cloud_label_[k] <= 0}
+  int n = 0;
+  for (int k0 = start; k0 < end; k0 += LFV_THREADS) {  // the segments tile [start, end-1]
+    const int k = k0 + threadIdx.x;
+    bool member = false;
+    if (k < end) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) member |= (seg_sp[j] < seg_ep[j] && k >= seg_sp[j] && k <= seg_ep[j]);
+      member = member && flabel[base + k] <= 0;
+    }
+    int total;
+    const int ex = block_excl_scan(member ? 1 : 0, redi, &total);
+    if (member && n + ex < pts_cap) pts[n + ex] = seg_cloud[base + k];
+    n += total;
+  }
+  __syncthreads();
+  n = min(n, pts_cap);
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  npad = min(npad, key_cap);
+  const int lo = max(start - 5, 0);
+  const int n_out = block_voxel_grid(pts, n, leaf, keys, npad, true, nullptr, 0, lf_stage + base + lo, redf, redi, &frame);
+  if (threadIdx.x == 0) ring_feat_cnt[br * 4 + 3] = n_out;
+}
+
+// ring-major concatenation: index lists, feature clouds, ring offsets of the clouds that become the next
+// scan's targets (corner_last_ = less_sharp, surf_last_ = less_flat, :531-534)
+__global__ void __launch_bounds__(128)
+lo_finalize_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ ring_feat_cnt, const int *__restrict__ ring_sharp,
+                   const int *__restrict__ ring_less_sharp, const int *__restrict__ ring_flat, const float4 *__restrict__ lf_stage,
+                   const int *__restrict__ start_ring, int *__restrict__ sharp_idx, int *__restrict__ less_sharp_idx,
+                   int *__restrict__ flat_idx, float4 *__restrict__ sharp, float4 *__restrict__ flat,
+                   float4 *__restrict__ less_sharp, float4 *__restrict__ less_flat, int *__restrict__ ls_ring_off,
+                   int *__restrict__ lf_ring_off, int *__restrict__ n_feat, int R, int RC) {
+  const int ring = blockIdx.x, b = blockIdx.y, br = b * R + ring;
+  const size_t base = (size_t)b * RC;
+  __shared__ int off[4], cnt[4];
+  if (threadIdx.x < 32) {
+    int a[4] = {0, 0, 0, 0};
+    for (int t = threadIdx.x; t < ring; t += 32)
+      for (int q = 0; q < 4; ++q) a[q] += ring_feat_cnt[(b * R + t) * 4 + q];
+    for (int q = 0; q < 4; ++q) a[q] = warp_sum_i(a[q]);
+    if (threadIdx.x == 0)
+      for (int q = 0; q < 4; ++q) { off[q] = a[q]; cnt[q] = ring_feat_cnt[br * 4 + q]; }
+  }
+  __syncthreads();
+  const int cS = R * 12, cL = R * 120, cF = R * 24;
+  for (int t = threadIdx.x; t < cnt[0]; t += blockDim.x) {
+    const int idx = ring_sharp[br * 12 + t];
+    sharp_idx[b * cS + off[0] + t] = idx;
+    sharp[(size_t)b * cS + off[0] + t] = seg_cloud[base + idx];
+  }
+  for (int t = threadIdx.x; t < cnt[1]; t += blockDim.x) {
+    const int idx = ring_less_sharp[br * 120 + t];
+    less_sharp_idx[b * cL + off[1] + t] = idx;
+    less_sharp[(size_t)b * cL + off[1] + t] = seg_cloud[base + idx];
+  }
+  for (int t = threadIdx.x; t < cnt[2]; t += blockDim.x) {
+    const int idx = ring_flat[br * 24 + t];
+    flat_idx[b * cF + off[2] + t] = idx;
+    flat[(size_t)b * cF + off[2] + t] = seg_cloud[base + idx];
+  }
+  const int lo = max(start_ring[br] - 5, 0);
+  for (int t = threadIdx.x; t < cnt[3]; t += blockDim.x) less_flat[base + off[3] + t] = lf_stage[base + lo + t];
+  if (threadIdx.x == 0) {
+    ls_ring_off[b * (R + 1) + ring] = off[1];
+    lf_ring_off[b * (R + 1) + ring] = off[3];
+    if (ring == R - 1) {
+      ls_ring_off[b * (R + 1) + R] = off[1] + cnt[1];
+      lf_ring_off[b * (R + 1) + R] = off[3] + cnt[3];
+      n_feat[b * 4 + 0] = off[0] + cnt[0];
+      n_feat[b * 4 + 1] = off[1] + cnt[1];
+      n_feat[b * 4 + 2] = off[2] + cnt[2];
+      n_feat[b * 4 + 3] = off[3] + cnt[3];
+    }
+  }
+}
+
+}  // namespace
+
+int lo_extract_device(AlegoHandle *h) {
+  const int B = h->B, R = h->R, C = h->C, RC = h->RC;
+  cudaStream_t s = h->stream;
+  { LAUNCH(h, "lo_curv_occl");
+    lo_curv_occl_kernel<<<dim3(div_up(RC, CURV_TILE), B), CURV_TILE, 0, s>>>(h->seg_range, h->seg_col, h->M, h->curv, h->picked0,
+                                                                             h->flabel, h->sort_idx, RC); }
+  { LAUNCH(h, "lo_sort_segments");
+    lo_sort_segments_kernel<<<div_up(B * R * 6, 64), 64, 0, s>>>(h->curv, h->start_ring, h->end_ring, h->sort_scratch, h->sort_idx,
+                                                                B, R, RC); }
+  const int pkcap = (C + 32 + 15) & ~15;
+  { LAUNCH(h, "lo_select");
+    lo_select_kernel<<<dim3(div_up(R, SEL_WARPS), B), SEL_WARPS * 32, (size_t)SEL_WARPS * pkcap, s>>>(
+        h->seg_col, h->seg_ground, h->curv, h->sort_idx, h->start_ring, h->end_ring, h->picked0, h->picked, h->flabel,
+        h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, R, RC, pkcap); }
+  const int pts_cap = C, key_cap = next_pow2(C);
+  const size_t lfv_smem = (size_t)pts_cap * sizeof(float4) + (size_t)key_cap * sizeof(u64);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(lo_less_flat_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  { LAUNCH(h, "lo_less_flat_voxel");
+    lo_less_flat_voxel_kernel<<<dim3(R, B), LFV_THREADS, lfv_smem, s>>>(h->seg_cloud, h->flabel, h->start_ring, h->end_ring,
+                                                                       h->lf_stage, h->ring_feat_cnt, R, RC, pts_cap, key_cap,
+                                                                       (float)h->P.less_flat_leaf); }
+  const int cur = h->cur;
+  { LAUNCH(h, "lo_finalize");
+    lo_finalize_kernel<<<dim3(R, B), 128, 0, s>>>(h->seg_cloud, h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat,
+                                                 h->lf_stage, h->start_ring, h->sharp_idx, h->less_sharp_idx, h->flat_idx, h->sharp,
+                                                 h->flat, h->less_sharp[cur], h->less_flat[cur], h->ls_ring_off[cur],
+                                                 h->lf_ring_off[cur], h->n_feat, R, RC); }
+  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}

@@ -1,0 +1,202 @@
+/*
+ * alego_b200.h — C ABI of the B200-native A-LeGO-LOAM per-scan hot path.
+ *
+ * The reference (jyakaranda/A-LeGO-LOAM) has NO library / FFI surface for its numerics: the
+ * hot path is inlined in ROS callbacks (src/imageProjection.cpp:49-316, src/laserOdometry.cpp:79-555,
+ * src/laserMapping.cpp:325-489).  This header therefore DEFINES the boundary a maintainer would bind
+ * from those callbacks; every entry point cites the reference code it replaces.  Plain pointers and
+ * sizes only, no torch / CUDA types in any signature, never throws, every call returns an int status.
+ *
+ * Batch model: one handle owns `n_seq` INDEPENDENT scan sequences that advance in lock-step (one
+ * sweep per sequence per call).  n_seq = 1 is the reference's single-robot case; n_seq > 1 is how a
+ * B200 leaves the launch-latency regime (a 64x1800 sweep is 1.8 MB).  Sequences never exchange data.
+ *
+ * Threading: a handle is not thread-safe; distinct handles are fully independent (own stream).
+ */
+#ifndef ALEGO_B200_H_
+#define ALEGO_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (reference behaviour: log-and-return, laserOdometry.cpp:91-109,424,498;
+ *      laserMapping.cpp:350-354) ---- */
+#define ALEGO_OK            0
+#define ALEGO_FEW_FEATURES  1  /* a solve was skipped (<10 correspondences / LM guard); state still valid */
+#define ALEGO_BAD_ARG      -1
+#define ALEGO_CUDA_ERROR   -2
+#define ALEGO_NOT_READY    -3  /* stage called before its producer stage */
+
+/* ---- presets for alego_default_params ---- */
+#define ALEGO_PRESET_VLP16_1800   0  /* 16 x 1800  (BASELINE cfg1/cfg2)                       */
+#define ALEGO_PRESET_HDL64_1800   1  /* 64 x 1800  (headline metric)                          */
+#define ALEGO_PRESET_HDL64_2048   2  /* 64 x 2048  (BASELINE cfg4/cfg5)                       */
+#define ALEGO_PRESET_REFERENCE    3  /* 16 x 4000, the literal constants of utility.h:50-65   */
+
+/* Runtime form of the compile-time constants in include/alego/utility.h:50-73 and of the literals in
+ * laserOdometry.cpp:290,415,489 / laserMapping.cpp:37-41,360,470. */
+typedef struct AlegoParams {
+  int32_t n_scan;               /* N_SCAN            utility.h:50 */
+  int32_t horizon_scan;         /* Horizon_SCAN      utility.h:55 = int(360/ang_res_x + 0.5) */
+  int32_t ground_scan_id;       /* utility.h:57 */
+  int32_t seg_valid_point_num;  /* utility.h:64 (5)  */
+  int32_t seg_valid_line_num;   /* utility.h:65 (3)  */
+  int32_t seg_min_cluster;      /* imageProjection.cpp:283 (30) */
+  int32_t lo_surf_iters;        /* laserOdometry.cpp:415 (5) */
+  int32_t lo_corner_iters;      /* laserOdometry.cpp:489 (5; README says 10) */
+  int32_t lm_outer_iters;       /* laserMapping.cpp:360 (2) */
+  int32_t lm_max_iters;         /* laserMapping.cpp:470 (20) */
+  int32_t reserved_i[6];
+  double ang_res_x;             /* utility.h:51 (deg) */
+  double ang_res_y;             /* utility.h:52 (deg) */
+  double ang_bottom;            /* utility.h:56 (deg) */
+  double sensor_mount_ang;      /* utility.h:58 (deg) */
+  double seg_theta;             /* utility.h:63 (rad) */
+  double nearest_feature_dist;  /* utility.h:73 (m^2) */
+  double huber_delta;           /* HuberLoss(0.1) laserOdometry.cpp:331, laserMapping.cpp:363 */
+  double less_flat_leaf;        /* laserOdometry.cpp:290 (0.4) */
+  double lm_corner_leaf;        /* laserMapping.cpp:37 (0.4) */
+  double lm_surf_leaf;          /* laserMapping.cpp:38 (0.8) */
+  double lm_outlier_leaf;       /* laserMapping.cpp:39 (1.0) */
+  double reserved_d[5];
+} AlegoParams;
+
+/* Field-for-field mirror of msg/cloud_info.msg:1-12 (Header omitted).  Arrays are caller-owned:
+ * ring arrays hold n_scan entries, the per-point arrays n_scan*horizon_scan entries of which the first
+ * `size` are meaningful (imageProjection.cpp:16-20,183-190). */
+typedef struct AlegoCloudInfo {
+  int32_t *startRingIndex;            /* [n_scan] */
+  int32_t *endRingIndex;              /* [n_scan] */
+  float startOrientation;
+  float endOrientation;
+  float orientationDiff;
+  int32_t size;                       /* M = number of segmented points */
+  uint8_t *segmentedCloudGroundFlag;  /* [M] bool */
+  int32_t *segmentedCloudColInd;      /* [M] */
+  float *segmentedCloudRange;         /* [M] */
+} AlegoCloudInfo;
+
+/* Per-sequence result of one Levenberg-Marquardt solve chain (what summary.BriefReport() and the
+ * correspondence counters log at laserOdometry.cpp:408,420,482,494 and laserMapping.cpp:465,477). */
+typedef struct AlegoSolveReport {
+  int32_t status;          /* ALEGO_OK / ALEGO_FEW_FEATURES */
+  int32_t n_corner;        /* corner / edge correspondences   */
+  int32_t n_surf;          /* surf / plane correspondences    */
+  int32_t iterations;      /* LM iterations over all solves (successful + unsuccessful steps) */
+  double initial_cost;     /* of the first executed solve */
+  double final_cost;       /* of the last executed solve  */
+} AlegoSolveReport;
+
+typedef struct AlegoHandle AlegoHandle;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int alego_default_params(AlegoParams *p, int preset);
+/* Replaces the three onInit() bodies (imageProjection.cpp:6-47, laserOdometry.cpp:6-77,
+ * laserMapping.cpp:5-100): allocates every device buffer for n_seq sequences on `device`. */
+int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per_scan, AlegoHandle **out);
+void alego_destroy(AlegoHandle *h);
+const char *alego_last_error(const AlegoHandle *h);   /* never NULL */
+int alego_synchronize(AlegoHandle *h);
+int alego_get_params(const AlegoHandle *h, AlegoParams *out);
+int alego_n_seq(const AlegoHandle *h);
+
+/* Pinned host memory for the sweep buffers (cudaMallocHost) so that the H2D copies are asynchronous. */
+void *alego_host_alloc(size_t bytes);
+void alego_host_free(void *p);
+
+/* ---- ImageProjection: replaces ImageProjection::pcCB + labelComponents
+ *      (src/imageProjection.cpp:49-208, 210-316) -------------------------------------------------- */
+/* xyzi_host: [n_seq][max_points_per_scan][4] float32 (x,y,z,intensity) — the decoded
+ * sensor_msgs::PointCloud2 of /lslidar_point_cloud; n_points[n_seq].  Copies H2D (async on the
+ * handle's stream; pass pinned memory for true overlap) and runs the IP kernels. */
+int alego_ip_process(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
+/* Same, but only the H2D copy / only the kernels (inputs already resident in HBM). */
+int alego_ip_upload(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
+int alego_ip_run(AlegoHandle *h);
+/* Fetch what pcCB publishes for sequence `seq`: /seg_info, /segmented_cloud, /outlier
+ * (imageProjection.cpp:318-336).  Any output pointer may be NULL.  label_image is the R x C
+ * label_mat_ (-1 ground/empty, 1..K clusters, 999999 rejected), row-major. */
+int alego_ip_get(AlegoHandle *h, int seq, AlegoCloudInfo *info, float *segmented_xyzi, float *outlier_xyzi,
+                 int32_t *n_outlier, int32_t *label_image);
+
+/* ---- LaserOdometry, features: replaces steps 2-4 of LaserOdometry::mainLoop
+ *      (src/laserOdometry.cpp:118-297) ------------------------------------------------------------ */
+int alego_lo_extract(AlegoHandle *h);
+/* Index lists are positions in the segmented cloud, in the reference's push_back order.
+ * less_flat_xyzi is the per-ring VoxelGrid(0.4) output concatenated over rings (:288-293).
+ * cloud_label is cloud_label_[0..M) (2 sharp, 1 less sharp, -1 flat, 0 rest). */
+int alego_lo_get_features(AlegoHandle *h, int seq, int32_t *sharp_idx, int32_t *n_sharp, int32_t *less_sharp_idx,
+                          int32_t *n_less_sharp, int32_t *flat_idx, int32_t *n_flat, float *less_flat_xyzi,
+                          int32_t *n_less_flat, int32_t *cloud_label);
+
+/* ---- LaserOdometry, scan-to-scan: replaces src/laserOdometry.cpp:316-535 + transformToStart
+ *      (:728-740) + CornerCostFunction / SurfCostFunction (utility.h:122-240) ---------------------- */
+/* First call per sequence only initialises the targets (:316-324).  reports may be NULL. */
+int alego_lo_scan2scan(AlegoHandle *h, AlegoSolveReport *reports /*[n_seq]*/);
+/* params_[6] (current->last), t_w_cur_[3], r_w_cur_[9] row-major (laserOdometry.h:76-80). */
+int alego_lo_get_state(AlegoHandle *h, int seq, double params[6], double t_w[3], double r_w[9]);
+int alego_lo_set_params(AlegoHandle *h, int seq, const double params[6]);
+
+/* ---- LaserMapping, scan-to-map: replaces src/laserMapping.cpp:325-489 + pointAssociateToMap
+ *      (laserMapping.h:187-194) + LidarEdge/LidarPlaneCostFunction (utility.h:242-349) ------------- */
+/* Local map of sequence `seq` (corner_from_map_ds_, surf_from_map_ds_): uploads and builds the
+ * device search grid — replaces the two KdTreeFLANN::setInputCloud calls at laserMapping.cpp:356-357.
+ * alego_lm_scan2map rebuilds the grid every call when params rebuild flag is set (reference rebuilds
+ * its kd-trees every mapped frame). */
+int alego_lm_set_map(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t n_corner, const float *surf_xyzi,
+                     int32_t n_surf);
+/* Stand-alone inputs for sequence `seq` (the /corner_last, /surf_last, /outlier clouds of
+ * laserMapping.cpp:133-153) and the odometry prediction odom2laser (:154-164). When not called, the
+ * clouds produced on the device by the LO stage of the same handle are used. */
+int alego_lm_set_scan(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t n_corner, const float *surf_xyzi,
+                      int32_t n_surf, const float *outlier_xyzi, int32_t n_outlier);
+int alego_lm_set_odom(AlegoHandle *h, int seq, const double t_odom2laser[3], const double r_odom2laser[9]);
+/* downsampleCurrentScan + scan2MapOptimization + transformUpdate (:325-346, 348-479, 481-489). */
+int alego_lm_scan2map(AlegoHandle *h, AlegoSolveReport *reports /*[n_seq]*/);
+/* params_[6], map2laser (t[3], R[9] row-major), map2odom (t[3], R[9]) (laserMapping.h:171-177). */
+int alego_lm_get_state(AlegoHandle *h, int seq, double params[6], double t_map2laser[3], double r_map2laser[9],
+                       double t_map2odom[3], double r_map2odom[9]);
+int alego_lm_set_params(AlegoHandle *h, int seq, const double params[6]);
+/* The four VoxelGrid outputs of downsampleCurrentScan (laser_corner_ds_, laser_surf_ds_,
+ * laser_outlier_ds_, laser_surf_total_ds_). Any pointer may be NULL. */
+int alego_lm_get_downsampled(AlegoHandle *h, int seq, float *corner_ds, int32_t *n_corner_ds, float *surf_ds,
+                             int32_t *n_surf_ds, float *outlier_ds, int32_t *n_outlier_ds, float *surf_total_ds,
+                             int32_t *n_surf_total_ds);
+
+/* ---- whole path: one sweep per sequence through IP -> LO -> LM ------------------------------------ */
+/* poses_out: [n_seq][12] doubles: t_map2laser[3], then params_ of LM [6] (x,y,z,roll,pitch,yaw),
+ * then t_w_cur_ of LO [3].  Host buffers in, host buffers out (H2D + D2H inside the call).
+ * xyzi_host == NULL means "inputs already uploaded with alego_ip_upload". poses_out may be NULL. */
+int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out);
+/* lm_every: run LM on every k-th sweep (reference: 2, laserMapping.cpp:112); 0 disables LM. */
+int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_every_step, int use_cuda_graph);
+
+/* ---- stand-alone operators (used by LO/LM internally, exposed for tests and callers) ------------- */
+/* pcl::VoxelGrid<PointXYZI> equivalent on host data (setLeafSize(leaf,leaf,leaf); filter()).
+ * out_xyzi needs room for n points. */
+int alego_voxel_grid(AlegoHandle *h, const float *xyzi, int32_t n, float leaf, float *out_xyzi, int32_t *n_out);
+
+/* ---- measurement hooks ----------------------------------------------------------------------------
+ * CUDA-event timing on the handle's own stream (torch.cuda.Event only sees torch's current stream). */
+int alego_timer_mark(AlegoHandle *h, int slot);                         /* cudaEventRecord(slot)  */
+int alego_timer_elapsed_ms(AlegoHandle *h, int slot_a, int slot_b, float *ms);
+/* Per-kernel accumulation: when enabled every kernel launch is bracketed by events. */
+int alego_profile_enable(AlegoHandle *h, int on);
+int alego_profile_reset(AlegoHandle *h);
+int alego_profile_count(const AlegoHandle *h);
+/* name_out: at least 64 bytes. total_ms summed over `launches` launches since the last reset. */
+int alego_profile_get(AlegoHandle *h, int i, char *name_out, int64_t *launches, double *total_ms);
+int64_t alego_launch_count(const AlegoHandle *h);                       /* kernels launched since create */
+
+/* ---- test hook: copy a named device array of sequence `seq` to host ---------------------------------
+ * Returns bytes written (>=0) or a negative status.  Names are listed in DESIGN.md ("debug arrays"). */
+int64_t alego_debug_get(AlegoHandle *h, const char *name, int seq, void *dst, size_t capacity_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALEGO_B200_H_ */

@@ -1,0 +1,55 @@
+"""The C-ABI library loads and exports every symbol include/alego_b200.h declares (no GPU work)."""
+import ctypes
+import os
+import re
+
+
+def test_library_exports_every_declared_symbol(alego):
+    hdr = open(os.path.join(os.path.dirname(alego.CSRC_DIR), "..", "include", "alego_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(alego_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 34
+    L = ctypes.CDLL(alego.LIB_PATH)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    for s in alego.EXPORTED_SYMBOLS:
+        assert s in declared
+
+
+def test_struct_layout_matches_header(alego):
+    # 16 int32 + 16 doubles
+    assert ctypes.sizeof(alego.AlegoParams) == 16 * 4 + 16 * 8
+    assert ctypes.sizeof(alego.AlegoSolveReport) == 4 * 4 + 2 * 8
+    L = ctypes.CDLL(alego.LIB_PATH)
+    L.alego_default_params.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    for preset in range(4):
+        p = alego.AlegoParams()
+        assert L.alego_default_params(ctypes.byref(p), preset) == 0
+        q = alego.default_params(preset)
+        assert bytes(p) == bytes(q)
+    assert L.alego_default_params(ctypes.byref(p), 99) == alego.BAD_ARG
+
+
+def test_reference_preset_matches_utility_h(alego):
+    p = alego.default_params(alego.PRESET_REFERENCE)  # include/alego/utility.h:50-65
+    assert (p.n_scan, p.horizon_scan, p.ground_scan_id) == (16, 4000, 10)
+    assert (p.ang_res_x, p.ang_res_y, p.ang_bottom) == (0.09, 2.0, 15.0)
+    assert (p.seg_theta, p.seg_valid_point_num, p.seg_valid_line_num, p.nearest_feature_dist) == (1.047, 5, 3, 25.0)
+
+
+def test_null_and_bad_arguments_do_not_crash(alego):
+    L = ctypes.CDLL(alego.LIB_PATH)
+    L.alego_last_error.restype = ctypes.c_char_p
+    L.alego_last_error.argtypes = [ctypes.c_void_p]
+    assert L.alego_last_error(None) == b"null handle"
+    L.alego_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    h = ctypes.c_void_p()
+    assert L.alego_create(None, 0, 1, 10, ctypes.byref(h)) == alego.BAD_ARG
+    p = alego.default_params(0)
+    assert L.alego_create(ctypes.byref(p), 0, 0, 10, ctypes.byref(h)) == alego.BAD_ARG
+    p.n_scan = 100000
+    assert L.alego_create(ctypes.byref(p), 0, 1, 10, ctypes.byref(h)) == alego.BAD_ARG
+    L.alego_ip_run.argtypes = [ctypes.c_void_p]
+    assert L.alego_ip_run(None) == alego.BAD_ARG
+    L.alego_destroy.argtypes = [ctypes.c_void_p]
+    L.alego_destroy(None)

@@ -1,0 +1,376 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): segmentation labels and feature indices bit-exact; poses within
+1e-4 m / 1e-4 rad after the same iteration count.  Integer / index / byte outputs are compared with
+array_equal, float32 pass-through data (ranges, clouds) bit-exact, double-precision solver state with the
+tolerance written at each assert.
+"""
+import numpy as np
+import pytest
+
+from conftest import first_diff
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-4  # metres / radians, north_star
+
+
+def make_scans(alego, P, seeds, t=0, **kw):
+    scans = []
+    for s in seeds:
+        w = alego.SynthWorld(seed=s)
+        scans.append(w.render(P, alego.trajectory_pose(t, seed=s), noise_seed=1000 * s + t, **kw))
+    return scans
+
+
+def check_ip(g, o, seq, tag=""):
+    R, Cc = g.R, g.Cc
+    rm = o.get("range_mat")
+    rm32 = np.where(rm == np.finfo(np.float64).max, np.finfo(np.float32).max, rm).astype(np.float32)
+    assert np.array_equal(g.debug("range_mat", seq), rm32), tag + " range_mat: " + first_diff(g.debug("range_mat", seq), rm32)
+    assert np.array_equal(g.debug("full_cloud", seq), o.get("full_cloud")), tag + " full_cloud"
+    assert np.array_equal(g.debug("ground_mat", seq), o.get("ground_mat")), tag + " ground_mat: " + first_diff(g.debug("ground_mat", seq), o.get("ground_mat"))
+    assert np.array_equal(g.debug("label_mat", seq), o.get("label_mat")), tag + " label_mat: " + first_diff(g.debug("label_mat", seq), o.get("label_mat"))
+    out = g.ip_get(seq)
+    for k in ("startRingIndex", "endRingIndex", "segmentedCloudGroundFlag", "segmentedCloudColInd", "segmentedCloudRange",
+              "segmented_cloud", "outlier_cloud"):
+        assert np.array_equal(out[k], o.get(k)), tag + " " + k + ": " + first_diff(out[k], o.get(k))
+    assert np.array_equal(out["label_mat"].reshape(-1), o.get("label_mat"))
+    # orientation: float atan2 of the device vs glibc may differ by 1 ulp (unused downstream: adjustDistortion is dead code)
+    for k in ("startOrientation", "endOrientation", "orientationDiff"):
+        assert abs(out[k] - float(o.get(k))) < 1e-5, (k, out[k], o.get(k))
+    return out
+
+
+def check_features(g, o, seq, tag=""):
+    M = len(o.get("segmentedCloudColInd"))
+    ca = g.debug("cloud_curvature_abs", seq).astype(np.float64)
+    if M > 10:
+        assert np.array_equal((ca * ca)[5:M - 5], o.get("cloud_curvature")[5:M - 5]), tag + " curvature"
+        assert np.array_equal(g.debug("cloud_neighbor_picked", seq)[5:M - 5], o.get("cloud_neighbor_picked")[5:M - 5]), \
+            tag + " picked: " + first_diff(g.debug("cloud_neighbor_picked", seq)[5:M - 5], o.get("cloud_neighbor_picked")[5:M - 5])
+        assert np.array_equal(g.debug("cloud_label", seq)[5:M - 5], o.get("cloud_label")[5:M - 5]), tag + " cloud_label"
+    for k in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+        assert np.array_equal(g.debug(k, seq), o.get(k)), tag + " " + k + ": " + first_diff(g.debug(k, seq), o.get(k))
+    for k in ("sharp", "less_sharp", "flat"):
+        assert np.array_equal(g.debug(k, seq), o.get(k)), tag + " " + k
+    # per-ring VoxelGrid: bit-exact against the (voxel, input order) summation; 1e-5 against PCL's std::sort order
+    lf = g.debug("less_flat", seq)
+    assert np.array_equal(lf, o.get("less_flat_stable")), tag + " less_flat: " + first_diff(lf, o.get("less_flat_stable"))
+    assert lf.shape == o.get("less_flat").shape and np.allclose(lf, o.get("less_flat"), rtol=0, atol=2e-5), tag + " less_flat vs PCL order"
+
+
+@pytest.mark.parametrize("preset", [0, 1, 2, 3])
+def test_ip_and_features_bit_exact(alego, ob, preset):
+    P = alego.default_params(preset)
+    seeds = [0, 1, 2] if preset != 1 else [0, 1, 2, 3, 4]
+    scans = make_scans(alego, P, seeds)
+    g = alego.Alego(P, n_seq=len(seeds))
+    buf, n = g.pack_scans(scans)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for b, s in enumerate(scans):
+        o = ob.Oracle(P)
+        assert o.ip(s) == 0
+        assert o.get("min_margin_row") > 0.2 and o.get("min_margin_col") > 0.2  # audit: rays sit at cell centres
+        o.lo_features()
+        check_ip(g, o, b, "preset%d seq%d" % (preset, b))
+        check_features(g, o, b, "preset%d seq%d" % (preset, b))
+    g.close()
+
+
+def test_ip_edge_cases(alego, ob):
+    """empty / ragged / NaN / duplicate-cell / out-of-range inputs (the reference's removeNaN + skip rules)."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    w = alego.SynthWorld(seed=7)
+    full = w.render(P, (0, 0, 0, 0), noise_seed=1)
+    rng = np.random.default_rng(0)
+    with_nan = full.copy()
+    with_nan[rng.choice(len(full), 500, replace=False), rng.integers(0, 3, 500)] = np.nan
+    with_nan[0, 0] = np.nan     # first / last valid point shift (orientation)
+    with_nan[-1, 2] = np.inf
+    dup = np.concatenate([full, full[::7] * np.float32(1.01)])  # second return in the same cell: the later point wins
+    out_of_fov = full.copy()
+    out_of_fov[::11, 2] += 40.0  # vertical angle beyond the top ring -> "error row_id", skipped
+    half = full[: len(full) // 2]
+    tiny = full[:3]
+    cases = [full, with_nan, dup, out_of_fov, half, tiny]
+    g = alego.Alego(P, n_seq=len(cases), max_points=len(dup))
+    buf, n = g.pack_scans(cases)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for b, s in enumerate(cases):
+        o = ob.Oracle(P)
+        assert o.ip(s) == 0
+        o.lo_features()
+        check_ip(g, o, b, "case%d" % b)
+        check_features(g, o, b, "case%d" % b)
+    assert ob.Oracle(P).get("n_dup_cells") == 0
+    g.close()
+
+
+def test_ip_zero_points_is_not_an_error(alego):
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    g = alego.Alego(P, n_seq=2)
+    w = alego.SynthWorld(seed=1)
+    buf, n = g.pack_scans([np.zeros((0, 4), np.float32), w.render(P)])
+    g.ip_process(buf, n)
+    g.lo_extract()
+    out = g.ip_get(0)
+    assert out["size"] == 0 and len(out["outlier_cloud"]) == 0 and (out["label_mat"] == -1).all()
+    assert g.ip_get(1)["size"] > 1000
+    g.close()
+
+
+def test_ip_sub_cell_jitter(alego, ob):
+    """Rays jittered by +-0.3 cell still sit > 0.1 cell from every binning boundary: labels stay bit-exact."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    scans = make_scans(alego, P, [11, 12], jitter_cells=0.3)
+    g = alego.Alego(P, n_seq=2)
+    buf, n = g.pack_scans(scans)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for b, s in enumerate(scans):
+        o = ob.Oracle(P)
+        o.ip(s)
+        assert o.get("min_margin_row") > 0.1 and o.get("min_margin_col") > 0.1
+        o.lo_features()
+        check_ip(g, o, b)
+        check_features(g, o, b)
+    g.close()
+
+
+def test_idempotent_and_batch_independent(alego):
+    """Size-independent properties at the headline size: re-running a sweep reproduces every output bit for bit,
+    and a sequence's result does not depend on its batch neighbours."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    scans = make_scans(alego, P, [0, 1, 2, 3])
+    g = alego.Alego(P, n_seq=4)
+    buf, n = g.pack_scans(scans)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    names = ["label_mat", "segmentedCloudColInd", "segmentedCloudRange", "sharp_idx", "less_sharp_idx", "flat_idx", "less_flat"]
+    first = {(k, b): g.debug(k, b).copy() for k in names for b in range(4)}
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for (k, b), v in first.items():
+        assert np.array_equal(g.debug(k, b), v), (k, b)
+    buf2, n2 = g.pack_scans(scans[::-1])
+    g.ip_process(buf2, n2)
+    g.lo_extract()
+    for (k, b), v in first.items():
+        assert np.array_equal(g.debug(k, 3 - b), v), (k, b)
+    # labels: every feasible label 1..K appears, raster order of first appearance is increasing
+    lab = first[("label_mat", 0)]
+    feas = lab[(lab > 0) & (lab < alego.LABEL_INVALID)]
+    K = feas.max()
+    firsts = [np.argmax(lab == k) for k in range(1, K + 1)]
+    assert all(lab[f] == k + 1 for k, f in enumerate(firsts)) and np.all(np.diff(firsts) > 0)
+    g.close()
+
+
+@pytest.mark.parametrize("n,leaf", [(1, 0.4), (17, 0.4), (5000, 0.4), (5000, 0.8), (40000, 0.8), (70000, 1.0)])
+def test_voxel_grid(alego, ob, n, leaf):
+    rng = np.random.default_rng(n)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, :2] = rng.uniform(-60, 60, (n, 2))
+    pts[:, 2] = rng.uniform(-2, 6, n)
+    pts[:, 3] = rng.uniform(0, 64, n)
+    P = alego.default_params(0)
+    g = alego.Alego(P, n_seq=1)
+    out = g.voxel_grid(pts, leaf)
+    ref_stable, _ = ob.voxel_grid(pts, leaf, stable=True)
+    ref_pcl, _ = ob.voxel_grid(pts, leaf, stable=False)
+    assert np.array_equal(out, ref_stable), first_diff(out, ref_stable)
+    assert out.shape == ref_pcl.shape and np.allclose(out, ref_pcl, rtol=0, atol=2e-5)
+    # tiny leaf on a wide cloud: PCL's overflow guard returns the input unchanged
+    if n == 5000 and leaf == 0.4:
+        wide = pts.copy()
+        wide[:, :3] *= 100.0
+        out = g.voxel_grid(wide, 0.001)
+        assert np.array_equal(out, wide)
+    g.close()
+
+
+def run_sequence(alego, ob, P, seed, n_sweeps, with_lm, lm_every=1, map_sizes=(6000, 30000)):
+    w = alego.SynthWorld(seed=seed)
+    g = alego.Alego(P, n_seq=1)
+    o = ob.Oracle(P, lm_every=lm_every if with_lm else 0, stable_voxel=True)
+    if with_lm:
+        corner, surf = w.make_map(map_sizes[0], map_sizes[1], seed=seed, radius=70.0)
+        g.lm_set_map(0, corner, surf)
+        o.lm_set_map(corner, surf)
+    g.pipeline_config(lm_every=lm_every if with_lm else 0)
+    return w, g, o
+
+
+@pytest.mark.parametrize("preset,seed", [(0, 0), (0, 1), (1, 2)])
+def test_scan_to_scan_parity(alego, ob, preset, seed):
+    """BASELINE config 2: LaserOdometry 2-step scan-to-scan on consecutive synthetic sweeps."""
+    P = alego.default_params(preset)
+    w, g, o = run_sequence(alego, ob, P, seed, 4, with_lm=False)
+    for t in range(4):
+        scan = w.render(P, alego.trajectory_pose(t, speed=0.25, yaw_rate=0.02, seed=seed), noise_seed=50 + t)
+        buf, n = g.pack_scans([scan])
+        g.ip_process(buf, n)
+        g.lo_extract()
+        rc, rep = g.lo_scan2scan()
+        o.ip(scan)
+        o.lo_features()
+        o.lo_scan2scan()
+        orep = o.report("lo")
+        assert rep[0]["n_surf"] == orep["n_surf"] and rep[0]["n_corner"] == orep["n_corner"], (t, rep[0], orep)
+        if t > 0:
+            gs = g.debug("lo_surf_corr")
+            gs = gs[gs[:, 1] >= 0]
+            assert np.array_equal(gs, o.get("lo_surf_corr")), "surf correspondences: " + first_diff(gs, o.get("lo_surf_corr"))
+            gc = g.debug("lo_corner_corr")
+            gc = gc[gc[:, 1] >= 0]
+            assert np.array_equal(gc, o.get("lo_corner_corr")), "corner correspondences: " + first_diff(gc, o.get("lo_corner_corr"))
+            assert rep[0]["iterations"] == orep["iterations"], (rep[0], orep)
+            tg, to = g.debug("lo_trace"), o.get("lo_trace")
+            assert tg.shape == to.shape and np.allclose(tg, to, rtol=1e-7, atol=1e-9), "per-iteration cost/pose trace"
+            assert orep["n_surf"] >= 10 and orep["n_corner"] >= 10
+        p, tw, rw = g.lo_get_state(0)
+        assert np.abs(p - o.get("lo_params")).max() < POSE_TOL
+        assert np.abs(tw - o.get("t_w_cur")).max() < POSE_TOL and np.abs(rw.reshape(-1) - o.get("r_w_cur")).max() < POSE_TOL
+        assert np.array_equal(g.debug("surf_last"), o.get("surf_last")) and np.array_equal(g.debug("corner_last"), o.get("corner_last"))
+    # the odometry actually follows the motion (sanity, not parity): translation of the last step ~ speed
+    assert 0.1 < np.linalg.norm(p[:2]) < 0.5
+    g.close()
+
+
+def lm_standalone_case(alego, P, seed, n_corner, n_surf, offset):
+    w = alego.SynthWorld(seed=seed)
+    corner_map, surf_map = w.make_map(n_corner, n_surf, seed=seed, radius=80.0)
+    scan = w.render(P, (0.0, 0.0, 0.0, 0.0), noise_seed=seed)
+    return w, corner_map, surf_map, scan
+
+
+@pytest.mark.parametrize("n_corner,n_surf", [(6000, 30000), (50000, 200000)])
+def test_scan_to_map_parity(alego, ob, n_corner, n_surf):
+    """BASELINE config 3: LaserMapping scan-to-map against a 50k corner + 200k surf local map (and a small one)."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    w, cm, sm, scan = lm_standalone_case(alego, P, 5, n_corner, n_surf, None)
+    # features of the sweep from the oracle front end, fed to both LaserMapping implementations
+    o = ob.Oracle(P, stable_voxel=True)
+    o.ip(scan)
+    o.lo_features()
+    corner, surf, outl = o.get("less_sharp"), o.get("less_flat_stable"), o.get("outlier_cloud")
+    o.lm_set_map(cm, sm)
+    o.lm_set_scan(corner, surf, outl)
+    # odometry prediction off by (0.2 m, 1 deg) from the truth (identity)
+    yaw = np.deg2rad(1.0)
+    R0 = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+    t0 = np.array([0.15, -0.12, 0.05])
+    x0 = np.array([0.15, -0.12, 0.05, 0.0, 0.0, yaw])
+    o.lm_set_odom(t0, R0)
+    o.lm_set_params(x0)
+    o.lm_scan2map()
+    g = alego.Alego(P, n_seq=2)
+    for b in range(2):
+        g.lm_set_map(b, cm, sm)
+        g.lm_set_scan(b, corner, surf, outl)
+        g.lm_set_odom(b, t0, R0)
+        g.lm_set_params(b, x0)
+    rc, rep = g.lm_scan2map()
+    orep = o.report("lm")
+    for b in range(2):
+        for k in ("lm_corner_ds", "lm_surf_ds", "lm_outlier_ds", "lm_surf_total_ds"):
+            assert np.array_equal(g.debug(k, b), o.get(k)), k + ": " + first_diff(g.debug(k, b), o.get(k))
+        e = g.debug("lm_edge", b)
+        p = g.debug("lm_plane", b)
+        assert np.array_equal(np.nonzero(e[:, 0])[0], o.get("lm_corner_sel")), "edge correspondences"
+        assert np.array_equal(np.nonzero(p[:, 0])[0], o.get("lm_surf_sel")), "plane correspondences"
+        res = o.get("lm_resids")
+        oe, op = res[res[:, 0] == 2], res[res[:, 0] == 3]
+        ge, gp = e[e[:, 0] != 0], p[p[:, 0] != 0]
+        # line end points: the eigenvector sign is arbitrary -> compare the unordered pair {lpj, lpl}
+        mid_g, mid_o = 0.5 * (ge[:, 4:7] + ge[:, 7:10]), 0.5 * (oe[:, 4:7] + oe[:, 7:10])
+        dir_g, dir_o = ge[:, 4:7] - ge[:, 7:10], oe[:, 4:7] - oe[:, 7:10]
+        assert np.allclose(mid_g, mid_o, atol=1e-9) and np.allclose(np.abs(np.sum(dir_g * dir_o, 1)), 0.04, atol=1e-9)
+        assert np.allclose(gp[:, 4:8], np.c_[op[:, 4:7], op[:, 13]], atol=1e-9), "plane parameters"
+        assert rep[b]["n_corner"] == orep["n_corner"] and rep[b]["n_surf"] == orep["n_surf"], (rep[b], orep)
+        assert rep[b]["iterations"] == orep["iterations"], (rep[b], orep)
+        tg, to = g.debug("lm_trace", b), o.get("lm_trace")
+        assert tg.shape == to.shape and np.allclose(tg, to, rtol=1e-6, atol=1e-8), "per-iteration cost/pose trace"
+        st = g.lm_get_state(b)
+        assert np.abs(st["params"] - o.get("lm_params")).max() < POSE_TOL
+        assert np.abs(st["t_map2odom"] - o.get("t_map2odom")).max() < POSE_TOL
+        assert np.abs(st["r_map2odom"].reshape(-1) - o.get("r_map2odom")).max() < POSE_TOL
+    # sanity: scan-to-map pulled the pose towards the truth (identity)
+    assert orep["n_surf"] > 100 and np.linalg.norm(o.get("lm_params")[:3]) < 0.08
+    g.close()
+
+
+def test_lm_guard_few_features(alego, ob):
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    w = alego.SynthWorld(seed=2)
+    cm, sm = w.make_map(3000, 10000, seed=2, radius=50.0)
+    g = alego.Alego(P, n_seq=1)
+    g.lm_set_map(0, cm, sm)
+    few = np.zeros((5, 4), np.float32)
+    g.lm_set_scan(0, few, few, few)
+    rc, rep = g.lm_scan2map()
+    assert rc == alego.FEW_FEATURES and rep[0]["status"] == alego.FEW_FEATURES and rep[0]["iterations"] == 0
+    g.close()
+
+
+@pytest.mark.parametrize("preset,lm_every", [(0, 1), (1, 2)])
+def test_full_pipeline_sequence(alego, ob, preset, lm_every):
+    """IP -> LO -> LM over consecutive sweeps, every stage fed by the previous one on the device."""
+    P = alego.default_params(preset)
+    seed = 4 + preset
+    w, g, o = run_sequence(alego, ob, P, seed, 6, with_lm=True, lm_every=lm_every)
+    for t in range(6):
+        scan = w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=70 + t)
+        buf, n = g.pack_scans([scan])
+        poses = g.pipeline_step(buf, n)
+        o.pipeline_step(scan)
+        assert np.array_equal(g.debug("label_mat"), o.get("label_mat")), "sweep %d label_mat" % t
+        for k in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+            assert np.array_equal(g.debug(k), o.get(k)), "sweep %d %s" % (t, k)
+        assert np.abs(g.debug("lo_params") - o.get("lo_params")).max() < POSE_TOL, "sweep %d LO" % t
+        assert np.abs(poses[0, 3:9] - o.get("lm_params")).max() < POSE_TOL, "sweep %d LM params" % t
+        assert np.abs(poses[0, 0:3] - o.get("t_map2laser")).max() < POSE_TOL
+        assert np.abs(poses[0, 9:12] - o.get("t_w_cur")).max() < POSE_TOL
+    true_pose = alego.trajectory_pose(5, seed=seed)
+    assert np.linalg.norm(poses[0, 3:5] - np.array(true_pose[:2])) < 0.3  # sanity: tracks the trajectory
+    g.close()
+
+
+def test_batched_sequences_match_single(alego, ob):
+    """n_seq independent sequences in one handle == each sequence alone (no cross-talk), 3 sweeps."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seeds = [0, 1, 2, 3, 4]
+    worlds = [alego.SynthWorld(seed=s) for s in seeds]
+    g = alego.Alego(P, n_seq=len(seeds))
+    oracles = [ob.Oracle(P, lm_every=1, stable_voxel=True) for _ in seeds]
+    for b, w in enumerate(worlds):
+        cm, sm = w.make_map(4000 + 500 * b, 20000 + 1000 * b, seed=b, radius=60.0)
+        g.lm_set_map(b, cm, sm)
+        oracles[b].lm_set_map(cm, sm)
+    g.pipeline_config(lm_every=1)
+    for t in range(3):
+        scans = [w.render(P, alego.trajectory_pose(t, seed=s), noise_seed=10 * s + t) for w, s in zip(worlds, seeds)]
+        buf, n = g.pack_scans(scans)
+        poses = g.pipeline_step(buf, n)
+        for b, s in enumerate(scans):
+            oracles[b].pipeline_step(s)
+            assert np.array_equal(g.debug("less_sharp_idx", b), oracles[b].get("less_sharp_idx"))
+            assert np.abs(poses[b, 3:9] - oracles[b].get("lm_params")).max() < POSE_TOL, (t, b)
+    g.close()
+
+
+def test_stage_order_errors(alego):
+    P = alego.default_params(0)
+    g = alego.Alego(P, n_seq=1)
+    with pytest.raises(alego.AlegoError):
+        g.lo_extract()          # before ip_process
+    with pytest.raises(alego.AlegoError):
+        g.lo_scan2scan()        # before lo_extract
+    with pytest.raises(alego.AlegoError):
+        g.lm_scan2map()         # no map
+    with pytest.raises(alego.AlegoError):
+        g.debug("label_mat", seq=5)
+    g.close()
