@@ -121,6 +121,8 @@ def lib():
         "alego_ip_process": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "alego_ip_upload": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "alego_ip_run": (C.c_int, [H]),
+        "alego_stage_upload": (C.c_int, [H, C.c_int, C.c_void_p, C.c_void_p]),
+        "alego_stage_select": (C.c_int, [H, C.c_int]),
         "alego_ip_get": (C.c_int, [H, C.c_int, C.POINTER(AlegoCloudInfo), C.c_void_p, C.c_void_p, PI, C.c_void_p]),
         "alego_lo_extract": (C.c_int, [H]),
         "alego_lo_get_features": (C.c_int, [H, C.c_int, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p]),
@@ -156,7 +158,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "alego_default_params", "alego_create", "alego_destroy", "alego_last_error", "alego_synchronize", "alego_get_params",
-    "alego_n_seq", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
+    "alego_n_seq", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
     "alego_lo_get_features", "alego_lo_scan2scan", "alego_lo_get_state", "alego_lo_set_params", "alego_lm_set_map",
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
     "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_voxel_grid", "alego_timer_mark",
@@ -243,6 +245,12 @@ class Alego:
 
     def ip_run(self):
         return self._chk(self.L.alego_ip_run(self.h))
+
+    def stage_upload(self, slot, buf, n):
+        return self._chk(self.L.alego_stage_upload(self.h, slot, _ptr(buf), _ptr(n)))
+
+    def stage_select(self, slot):
+        return self._chk(self.L.alego_stage_select(self.h, slot))
 
     def ip_get(self, seq=0, labels=True):
         R, RC = self.R, self.R * self.Cc

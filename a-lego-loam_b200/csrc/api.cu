@@ -135,8 +135,10 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto &e : h->timer) CUDA_TRY(h, cudaEventCreate(&e));
   const size_t B = n_seq, RC = h->RC, R = h->R;
-  DMALLOC(h, h->raw, B * h->Nmax);
-  DMALLOC(h, h->n_pts, B);
+  DMALLOC(h, h->raw_own, B * h->Nmax);
+  DMALLOC(h, h->n_pts_own, B);
+  h->raw = h->raw_own;
+  h->n_pts = h->n_pts_own;
   DMALLOC(h, h->first_valid, B);
   DMALLOC(h, h->last_valid, B);
   DMALLOC(h, h->winner, B * RC);
@@ -246,7 +248,9 @@ void alego_destroy(AlegoHandle *h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void *ptrs[] = {h->raw, h->n_pts, h->first_valid, h->last_valid, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
+  for (auto p : h->stage_raw) cudaFree(p);
+  for (auto p : h->stage_n) cudaFree(p);
+  void *ptrs[] = {h->raw_own, h->n_pts_own, h->first_valid, h->last_valid, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
                   h->comp_id, h->label, h->rowcnt, h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring, h->end_ring,
                   h->M, h->outlier, h->n_outlier, h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,
@@ -296,21 +300,54 @@ void alego_host_free(void *p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points);
+
 int alego_ip_upload(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points) {
   if (!h || !xyzi_host || !n_points) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  h->raw = h->raw_own;
+  h->n_pts = h->n_pts_own;
+  return upload_into(h, h->raw, h->n_pts, xyzi_host, n_points);
+}
+
+// Pre-stage sweeps in HBM: slot k holds one sweep per sequence; alego_stage_select makes it the input of the
+// next alego_ip_run / alego_pipeline_step(NULL, ...) without any copy.
+int alego_stage_upload(AlegoHandle *h, int slot, const float *xyzi_host, const int32_t *n_points) {
+  if (!h || slot < 0 || slot > 4096 || !xyzi_host || !n_points) return ALEGO_BAD_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  while ((int)h->stage_raw.size() <= slot) {
+    float4 *r = nullptr;
+    int *n = nullptr;
+    CUDA_TRY(h, cudaMalloc(&r, (size_t)h->B * h->Nmax * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc(&n, (size_t)h->B * sizeof(int)));
+    h->stage_raw.push_back(r);
+    h->stage_n.push_back(n);
+  }
+  int rc = upload_into(h, h->stage_raw[slot], h->stage_n[slot], xyzi_host, n_points);
+  if (rc != ALEGO_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return ALEGO_OK;
+}
+int alego_stage_select(AlegoHandle *h, int slot) {
+  if (!h || slot < 0 || slot >= (int)h->stage_raw.size()) return ALEGO_BAD_ARG;
+  h->raw = h->stage_raw[slot];
+  h->n_pts = h->stage_n[slot];
+  return ALEGO_OK;
+}
+
+static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points) {
   size_t total = 0;
   for (int b = 0; b < h->B; ++b) {
     if (n_points[b] < 0 || n_points[b] > h->Nmax) { h->err = "n_points out of range"; return ALEGO_BAD_ARG; }
     total += n_points[b];
   }
-  CUDA_TRY(h, cudaMemcpyAsync(h->n_pts, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(n_dev, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (total * 10 >= (size_t)h->B * h->Nmax * 9) {  // nearly full rows: one DMA
-    CUDA_TRY(h, cudaMemcpyAsync(h->raw, xyzi_host, (size_t)h->B * h->Nmax * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(raw, xyzi_host, (size_t)h->B * h->Nmax * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
   } else {
     for (int b = 0; b < h->B; ++b)
       if (n_points[b] > 0)
-        CUDA_TRY(h, cudaMemcpyAsync(h->raw + (size_t)b * h->Nmax, xyzi_host + (size_t)b * h->Nmax * 4, (size_t)n_points[b] * sizeof(float4),
+        CUDA_TRY(h, cudaMemcpyAsync(raw + (size_t)b * h->Nmax, xyzi_host + (size_t)b * h->Nmax * 4, (size_t)n_points[b] * sizeof(float4),
                                     cudaMemcpyHostToDevice, h->stream));
   }
   return ALEGO_OK;

@@ -59,8 +59,12 @@ struct AlegoHandle {
   double seg_sin_x, seg_cos_x, seg_sin_y, seg_cos_y;
 
   // ---------------- ImageProjection ----------------
-  float4 *raw = nullptr;       // [B][Nmax]
+  float4 *raw = nullptr;       // [B][Nmax]  (points at raw_own or at a staged sweep)
   int *n_pts = nullptr;        // [B]
+  float4 *raw_own = nullptr;
+  int *n_pts_own = nullptr;
+  std::vector<float4 *> stage_raw;  // sweeps pre-staged in HBM (alego_stage_*)
+  std::vector<int *> stage_n;
   int *first_valid = nullptr;  // [B]
   int *last_valid = nullptr;   // [B]
   int *winner = nullptr;       // [B][RC]  index of the last input point that fell in the cell (-1 none)

@@ -95,7 +95,9 @@ int synth_render(void *wv, const AlegoParams *P, const double *pose4, uint64_t n
   const int R = P->n_scan, C = P->horizon_scan;
   const double ox = pose4[0], oy = pose4[1], oz = pose4[2], yaw = pose4[3];
   const double cyw = std::cos(yaw), syw = std::sin(yaw);
-  int n = 0;
+  std::vector<float> cellbuf((size_t)R * C * 4);
+  std::vector<unsigned char> hitbuf((size_t)R * C, 0);
+#pragma omp parallel for schedule(dynamic, 8)
   for (int c = 0; c < C; ++c) {
     for (int r = 0; r < R; ++r) {
       Rng rng(mix(mix(noise_seed, (uint64_t)r), (uint64_t)c));
@@ -150,13 +152,20 @@ int synth_render(void *wv, const AlegoParams *P, const double *pose4, uint64_t n
       if (noise < -3 * range_sigma) noise = -3 * range_sigma;
       if (best >= max_range || drop) continue;
       const double t = best + noise;
-      xyzi_out[4 * n + 0] = (float)(dsx * t);
-      xyzi_out[4 * n + 1] = (float)(dsy * t);
-      xyzi_out[4 * n + 2] = (float)(dsz * t);
-      xyzi_out[4 * n + 3] = (float)(10.0 + 5.0 * rng.uni());
-      ++n;
+      float *o = &cellbuf[((size_t)c * R + r) * 4];
+      o[0] = (float)(dsx * t);
+      o[1] = (float)(dsy * t);
+      o[2] = (float)(dsz * t);
+      o[3] = (float)(10.0 + 5.0 * rng.uni());
+      hitbuf[(size_t)c * R + r] = 1;
     }
   }
+  int n = 0;
+  for (size_t k = 0; k < (size_t)R * C; ++k)
+    if (hitbuf[k]) {
+      std::memcpy(xyzi_out + 4 * (size_t)n, &cellbuf[k * 4], 16);
+      ++n;
+    }
   return n;
 }
 

@@ -117,6 +117,11 @@ int alego_ip_process(AlegoHandle *h, const float *xyzi_host, const int32_t *n_po
 /* Same, but only the H2D copy / only the kernels (inputs already resident in HBM). */
 int alego_ip_upload(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
 int alego_ip_run(AlegoHandle *h);
+/* Pre-stage sweeps in HBM (slot k = one sweep per sequence) and select a slot as the input of the next
+ * alego_ip_run / alego_pipeline_step(h, NULL, NULL, ...) — no copy at selection time.  Used to measure the
+ * path with inputs already resident in device memory. */
+int alego_stage_upload(AlegoHandle *h, int slot, const float *xyzi_host, const int32_t *n_points);
+int alego_stage_select(AlegoHandle *h, int slot);
 /* Fetch what pcCB publishes for sequence `seq`: /seg_info, /segmented_cloud, /outlier
  * (imageProjection.cpp:318-336).  Any output pointer may be NULL.  label_image is the R x C
  * label_mat_ (-1 ground/empty, 1..K clusters, 999999 rejected), row-major. */
