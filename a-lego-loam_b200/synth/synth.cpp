@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/alego_b200.h"
@@ -97,8 +98,10 @@ int synth_render(void *wv, const AlegoParams *P, const double *pose4, uint64_t n
   const double cyw = std::cos(yaw), syw = std::sin(yaw);
   std::vector<float> cellbuf((size_t)R * C * 4);
   std::vector<unsigned char> hitbuf((size_t)R * C, 0);
-#pragma omp parallel for schedule(dynamic, 8)
-  for (int c = 0; c < C; ++c) {
+  // columns are independent (per-cell seeded noise): split them over host threads (std::thread, not OpenMP —
+  // the image's default CXX has no libgomp)
+  auto render_cols = [&](int c_begin, int c_end) {
+  for (int c = c_begin; c < c_end; ++c) {
     for (int r = 0; r < R; ++r) {
       Rng rng(mix(mix(noise_seed, (uint64_t)r), (uint64_t)c));
       const double jr = jitter_cells > 0 ? rng.uni(-jitter_cells, jitter_cells) : 0.0;
@@ -159,6 +162,19 @@ int synth_render(void *wv, const AlegoParams *P, const double *pose4, uint64_t n
       o[3] = (float)(10.0 + 5.0 * rng.uni());
       hitbuf[(size_t)c * R + r] = 1;
     }
+  }
+  };
+  {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 16) nt = 16;
+    std::vector<std::thread> pool;
+    const int chunk = (C + (int)nt - 1) / (int)nt;
+    for (unsigned k = 0; k < nt; ++k) {
+      const int b = (int)k * chunk, e = b + chunk < C ? b + chunk : C;
+      if (b < e) pool.emplace_back(render_cols, b, e);
+    }
+    for (auto &t : pool) t.join();
   }
   int n = 0;
   for (size_t k = 0; k < (size_t)R * C; ++k)
