@@ -1,0 +1,117 @@
+// alego_host.cpp — see alego_host.h.  Thin: argument marshalling only, every numeric step is a C-ABI call.
+#include "alego_host.h"
+
+#include <cstring>
+
+namespace alego {
+
+AlegoContext::~AlegoContext() {
+  if (h_) alego_destroy(h_);
+}
+
+int AlegoContext::init(const AlegoParams &p, int device, int n_seq, int max_points_per_scan) {
+  if (h_) return ALEGO_BAD_ARG;
+  p_ = p;
+  n_seq_ = n_seq;
+  max_pts_ = max_points_per_scan > 0 ? max_points_per_scan : p.n_scan * p.horizon_scan;
+  return alego_create(&p_, device, n_seq_, max_pts_, &h_);
+}
+
+std::string AlegoContext::last_error() const { return alego_last_error(h_); }
+
+ImageProjection::~ImageProjection() {
+  if (pinned_) alego_host_free(pinned_);
+}
+
+int ImageProjection::onInit() {
+  if (!ctx_.handle()) return ALEGO_NOT_READY;
+  if (pinned_) return ALEGO_OK;
+  pinned_ = static_cast<float *>(alego_host_alloc(sizeof(float) * 4 * (size_t)ctx_.n_seq() * ctx_.max_points()));
+  n_points_.assign(ctx_.n_seq(), 0);
+  return pinned_ ? ALEGO_OK : ALEGO_CUDA_ERROR;
+}
+
+int ImageProjection::process(const std::vector<PointCloud> &clouds) {
+  if (!pinned_ || (int)clouds.size() != ctx_.n_seq()) return ALEGO_BAD_ARG;
+  for (int b = 0; b < ctx_.n_seq(); ++b) {
+    const size_t n = clouds[b].size();
+    if (n > (size_t)ctx_.max_points()) return ALEGO_BAD_ARG;
+    n_points_[b] = (int32_t)n;
+    if (n) std::memcpy(pinned_ + (size_t)b * ctx_.max_points() * 4, clouds[b].data(), n * sizeof(PointXYZI));
+  }
+  return alego_ip_process(ctx_.handle(), pinned_, n_points_.data());
+}
+
+int ImageProjection::results(int seq, CloudInfo *info, PointCloud *segmented, PointCloud *outlier) {
+  const AlegoParams &p = ctx_.params();
+  const size_t rc = (size_t)p.n_scan * p.horizon_scan;
+  CloudInfo tmp;
+  CloudInfo *ci = info ? info : &tmp;
+  ci->startRingIndex.assign(p.n_scan, 0);
+  ci->endRingIndex.assign(p.n_scan, 0);
+  ci->segmentedCloudGroundFlag.assign(rc, 0);
+  ci->segmentedCloudColInd.assign(rc, 0);
+  ci->segmentedCloudRange.assign(rc, 0.f);
+  AlegoCloudInfo raw{};
+  raw.startRingIndex = ci->startRingIndex.data();
+  raw.endRingIndex = ci->endRingIndex.data();
+  raw.segmentedCloudGroundFlag = ci->segmentedCloudGroundFlag.data();
+  raw.segmentedCloudColInd = ci->segmentedCloudColInd.data();
+  raw.segmentedCloudRange = ci->segmentedCloudRange.data();
+  if (segmented) segmented->assign(rc, PointXYZI{0, 0, 0, 0});
+  if (outlier) outlier->assign(rc, PointXYZI{0, 0, 0, 0});
+  int32_t n_out = 0;
+  const int rcode = alego_ip_get(ctx_.handle(), seq, &raw, segmented ? &(*segmented)[0].x : nullptr,
+                                 outlier ? &(*outlier)[0].x : nullptr, &n_out, nullptr);
+  if (rcode != ALEGO_OK) return rcode;
+  ci->size = raw.size;
+  ci->startOrientation = raw.startOrientation;
+  ci->endOrientation = raw.endOrientation;
+  ci->orientationDiff = raw.orientationDiff;
+  if (segmented) segmented->resize(raw.size);
+  if (outlier) outlier->resize(n_out);
+  return ALEGO_OK;
+}
+
+int LaserOdometry::process(AlegoSolveReport *reports) {
+  const int rc = alego_lo_extract(ctx_.handle());
+  if (rc != ALEGO_OK) return rc;
+  return alego_lo_scan2scan(ctx_.handle(), reports);
+}
+
+int LaserOdometry::odometry(int seq, double params[6], double t_w_cur[3], double r_w_cur[9]) {
+  return alego_lo_get_state(ctx_.handle(), seq, params, t_w_cur, r_w_cur);
+}
+
+int LaserOdometry::features(int seq, std::vector<int32_t> *sharp_idx, std::vector<int32_t> *less_sharp_idx,
+                            std::vector<int32_t> *flat_idx, PointCloud *less_flat) {
+  const AlegoParams &p = ctx_.params();
+  const int R = p.n_scan;
+  const size_t rc = (size_t)R * p.horizon_scan;
+  std::vector<int32_t> s(R * 12), ls(R * 120), f(R * 24);
+  PointCloud lf(less_flat ? rc : 0);
+  int32_t ns = 0, nls = 0, nf = 0, nlf = 0;
+  const int rcode = alego_lo_get_features(ctx_.handle(), seq, s.data(), &ns, ls.data(), &nls, f.data(), &nf,
+                                          less_flat ? &lf[0].x : nullptr, &nlf, nullptr);
+  if (rcode != ALEGO_OK) return rcode;
+  s.resize(ns); ls.resize(nls); f.resize(nf);
+  if (sharp_idx) sharp_idx->swap(s);
+  if (less_sharp_idx) less_sharp_idx->swap(ls);
+  if (flat_idx) flat_idx->swap(f);
+  if (less_flat) { lf.resize(nlf); less_flat->swap(lf); }
+  return ALEGO_OK;
+}
+
+int LaserMapping::setLocalMap(int seq, const PointCloud &corner, const PointCloud &surf) {
+  return alego_lm_set_map(ctx_.handle(), seq, corner.empty() ? nullptr : &corner[0].x, (int32_t)corner.size(),
+                          surf.empty() ? nullptr : &surf[0].x, (int32_t)surf.size());
+}
+
+int LaserMapping::process(AlegoSolveReport *reports) { return alego_lm_scan2map(ctx_.handle(), reports); }
+
+int LaserMapping::pose(int seq, double params[6], double t_map2laser[3], double r_map2laser[9], double t_map2odom[3],
+                       double r_map2odom[9]) {
+  return alego_lm_get_state(ctx_.handle(), seq, params, t_map2laser, r_map2laser, t_map2odom, r_map2odom);
+}
+
+}  // namespace alego
