@@ -25,8 +25,7 @@ struct GridIndex {
   int table_size = 0;  // power of two
   int cap = 0;         // points per sequence
   float cell = 1.0f;
-  int *cell_start = nullptr;  // [B][table_size+1]
-  int *cursor = nullptr;      // [B][table_size]  scratch (counts, then fill cursors)
+  int *cell_start = nullptr;  // [B][table_size+4]  entry h = first slot of bucket h, entry table_size = #points (+3 pad)
   float4 *sorted = nullptr;   // [B][cap]  xyz + original index (int bits in .w)
 };
 

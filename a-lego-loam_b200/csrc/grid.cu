@@ -1,7 +1,7 @@
 // grid.cu — hashed uniform cell grid over a point cloud, one per sequence: the device replacement for
 // pcl::KdTreeFLANN::setInputCloud (laserOdometry.cpp:321-322,533-534; laserMapping.cpp:356-357).
 // Build = counting sort of the points by hashed cell: count (atomics on a per-sequence table), exclusive
-// scan of the table, fill.  Points are copied next to each other per bucket (xyz + original index), so a
+// scan of the table, fill (the table is count, fill cursor and final bucket index in turn, see grid_scan_kernel).  Points are copied next to each other per bucket (xyz + original index), so a
 // query reads whole buckets with coalesced 16-byte loads.  Bucket order is arbitrary; every consumer ranks
 // candidates by (distance, original index), so results do not depend on it.
 #include "common.cuh"
@@ -14,34 +14,31 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float4 *__restric
   const int b = blockIdx.y;
   const int n = min(n_ptr[(size_t)b * n_stride], cap);
   const float4 *src = pts + (size_t)b * pts_stride;
-  int *cnt = counts + (size_t)b * T;
+  int *cnt = counts + (size_t)b * (T + 4);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = ldg_f4(src + i);
     if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
-    atomicAdd(cnt + grid_hash(grid_coord(p.x, inv_cell), grid_coord(p.y, inv_cell), grid_coord(p.z, inv_cell), T), 1);
+    atomicAdd(cnt + 1 + grid_hash(grid_coord(p.x, inv_cell), grid_coord(p.y, inv_cell), grid_coord(p.z, inv_cell), T), 1);
   }
 }
 
-// one CTA per sequence: exclusive scan of T counters (T a multiple of blockDim); leaves the bucket starts in
-// cell_start[0..T] and in `counts` (which becomes the fill cursor)
-__global__ void __launch_bounds__(1024) grid_scan_kernel(int *__restrict__ counts, int *__restrict__ cell_start, int T) {
-  const int b = blockIdx.x;
-  int *cnt = counts + (size_t)b * T;
-  int *cs = cell_start + (size_t)b * (T + 1);
+// one CTA per sequence: in-place exclusive scan of the T+1 entries of the bucket table (entry 0 is always 0, entry
+// 1+h holds the count of bucket h), 4096 entries per iteration with coalesced 16-byte accesses.  Afterwards entry
+// 1+h = start of bucket h = the fill cursor; the fill kernel advances it to the END of bucket h = start of bucket
+// h+1, so that after the fill entry h = start(h) and entry T = number of points: one array is count, cursor and index.
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int *__restrict__ table, int T) {
+  int *arr = table + (size_t)blockIdx.x * (T + 4);
   __shared__ int s_scan[34];
-  const int per = T / blockDim.x;  // consecutive counters per thread
-  const int lo = threadIdx.x * per;
-  int sum = 0;
-  for (int k = 0; k < per; ++k) sum += cnt[lo + k];
-  int total;
-  int run = block_excl_scan(sum, s_scan, &total);
-  for (int k = 0; k < per; ++k) {
-    const int c = cnt[lo + k];
-    cs[lo + k] = run;
-    cnt[lo + k] = run;
-    run += c;
+  int carry = 0;
+  for (int c0 = 0; c0 < T + 4; c0 += 4096) {
+    const int i = c0 + threadIdx.x * 4;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (i < T + 4) v = *reinterpret_cast<const int4 *>(arr + i);
+    int total;
+    const int ex = block_excl_scan(v.x + v.y + v.z + v.w, s_scan, &total) + carry;
+    if (i < T + 4) *reinterpret_cast<int4 *>(arr + i) = make_int4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    carry += total;
   }
-  if (threadIdx.x == 0) cs[T] = total;
 }
 
 __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict__ pts, size_t pts_stride, const int *__restrict__ n_ptr,
@@ -50,7 +47,7 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict
   const int b = blockIdx.y;
   const int n = min(n_ptr[(size_t)b * n_stride], cap);
   const float4 *src = pts + (size_t)b * pts_stride;
-  int *cur = cursor + (size_t)b * T;
+  int *cur = cursor + (size_t)b * (T + 4) + 1;
   float4 *dst = sorted + (size_t)b * cap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = ldg_f4(src + i);
@@ -69,18 +66,16 @@ int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell) {
   int T = next_pow2(cap > 2048 ? cap / 2 : 1024);
   if (T < 1024) T = 1024;
   g->table_size = T;
-  CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)h->B * (T + 1) * sizeof(int)));
-  CUDA_TRY(h, cudaMalloc(&g->cursor, (size_t)h->B * T * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)h->B * (T + 4) * sizeof(int)));
   CUDA_TRY(h, cudaMalloc(&g->sorted, (size_t)h->B * cap * sizeof(float4)));
-  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)h->B * (T + 1) * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)h->B * (T + 4) * sizeof(int), h->stream));
   return ALEGO_OK;
 }
 
 void grid_free(GridIndex *g) {
   if (g->cell_start) cudaFree(g->cell_start);
-  if (g->cursor) cudaFree(g->cursor);
   if (g->sorted) cudaFree(g->sorted);
-  g->cell_start = g->cursor = nullptr;
+  g->cell_start = nullptr;
   g->sorted = nullptr;
   g->cap = g->table_size = 0;
 }
@@ -91,12 +86,12 @@ int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_strid
   const float inv = 1.0f / g->cell;
   const int blocks = min(div_up(g->cap, 256), 1024);
   std::string t0 = std::string("grid_count_") + tag, t1 = std::string("grid_scan_") + tag, t2 = std::string("grid_fill_") + tag;
-  CUDA_TRY(h, cudaMemsetAsync(g->cursor, 0, (size_t)B * T * sizeof(int), s));
+  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)B * (T + 4) * sizeof(int), s));
   { LAUNCH(h, t0.c_str());
-    grid_count_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cursor, T, inv, g->cap); }
-  { LAUNCH(h, t1.c_str()); grid_scan_kernel<<<B, 1024, 0, s>>>(g->cursor, g->cell_start, T); }
+    grid_count_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cell_start, T, inv, g->cap); }
+  { LAUNCH(h, t1.c_str()); grid_scan_kernel<<<B, 1024, 0, s>>>(g->cell_start, T); }
   { LAUNCH(h, t2.c_str());
-    grid_fill_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cursor, g->sorted, T, inv, g->cap); }
+    grid_fill_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cell_start, g->sorted, T, inv, g->cap); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

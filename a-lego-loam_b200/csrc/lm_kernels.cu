@@ -219,7 +219,7 @@ __device__ void lstsq_5x3_dev(double A[5][3], double b[5], double n[3]) {
 // A cell edge >= 1 m makes the 27 surrounding cells sufficient for every neighbour that can pass the gate.
 __device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, float qy, float qz, float *bd, int *bi) {
   const int T = g.table_size;
-  const int *cs = g.cell_start + (size_t)b * (T + 1);
+  const int *cs = g.cell_start + (size_t)b * (T + 4);
   const float4 *sp = g.sorted + (size_t)b * g.cap;
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);

@@ -80,22 +80,130 @@ __device__ __forceinline__ void segment_bounds(int start, int end, int j, int &s
   ep = (start * (5 - j) + end * (j + 1)) / 6 - 1;
 }
 
-// one thread per (sequence, ring, segment): the permutation libstdc++'s std::sort leaves, ties included
-__global__ void __launch_bounds__(64)
+// ---------------------------------------------------------------------------------------------------
+// K8a: one WARP per (sequence, ring, segment) reproduces the permutation libstdc++'s std::sort leaves with the
+// reference's curvature-only comparator (:185), ties included — as a data-parallel algorithm:
+//  * introsort's partition loop keeps its exact structure (explicit stack, median-of-3 by lane 0), but each
+//    __unguarded_partition is evaluated with prefix counts instead of two walking pointers.  With pivot p,
+//    "left stoppers" L = positions (ascending) whose key >= p, "right stoppers" R = positions (descending) whose
+//    key <= p: the sequential loop swaps L[k] <-> R[k] while L[k] < R[k] and returns min(L[K], R[K-1]) (K = number
+//    of swaps).  An L element at t swaps iff #R after t > #L before t; an R element swaps iff #L before t > #R after
+//    t; its partner is the stopper of equal rank.  Three ballot sweeps over the range, no divergence.
+//  * __final_insertion_sort is a stable sort of what the partitions leave; ranges <= 16 are mutually ordered, so
+//    it reduces to a stable rank sort inside every leaf, done for all elements at once.
+//  * depth-limit heapsort (never reached on non-adversarial data) runs on lane 0 with the sequential clone.
+// tools/proto_parallel_introsort.py checks this formulation against the real std::sort; tests/test_gpu_parity.py
+// checks the kernel's cloud_sort_idx_ against the oracle's on tie-heavy sweeps.
+#define SORT_WARPS 8
+__device__ __forceinline__ unsigned ss_key(unsigned long long e) { return (unsigned)(e >> 32); }
+__device__ __forceinline__ unsigned ss_pack(int f, int l, int depth) { return (unsigned)f | ((unsigned)l << 11) | ((unsigned)depth << 22); }
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
 lo_sort_segments_kernel(const float *__restrict__ curv, const int *__restrict__ start_ring, const int *__restrict__ end_ring,
-                        unsigned long long *__restrict__ scratch, int *__restrict__ sort_idx, int B, int R, int RC) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * R * 6) return;
-  const int b = t / (R * 6), rs = t - b * R * 6, ring = rs / 6, j = rs - ring * 6;
+                        unsigned long long *__restrict__ scratch, int *__restrict__ sort_idx, int B, int R, int RC, int cap) {
+  extern __shared__ __align__(16) unsigned char ss_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * SORT_WARPS + warp;
+  if (seg >= B * R * 6) return;
+  const int b = seg / (R * 6), rs = seg - b * R * 6, ring = rs / 6, j = rs - ring * 6;
   int sp, ep;
   segment_bounds(start_ring[b * R + ring], end_ring[b * R + ring], j, sp, ep);
   if (sp >= ep) return;
   const size_t base = (size_t)b * RC;
-  unsigned long long *e = scratch + base + sp;
   const int n = ep - sp + 1;
-  for (int k = 0; k < n; ++k) e[k] = ((unsigned long long)__float_as_uint(curv[base + sp + k]) << 32) | (unsigned)(sp + k);
-  ssc::sort(e, n);
-  for (int k = 0; k < n; ++k) sort_idx[base + sp + k] = (int)(e[k] & 0xffffffffu);
+  if (n > cap) {  // cannot happen for cap = C/6 + 8 (a ring holds <= C points); kept as a correct slow path
+    if (lane == 0) {
+      unsigned long long *e = scratch + base + sp;
+      for (int k = 0; k < n; ++k) e[k] = ((unsigned long long)__float_as_uint(curv[base + sp + k]) << 32) | (unsigned)(sp + k);
+      ssc::sort(e, n);
+      for (int k = 0; k < n; ++k) sort_idx[base + sp + k] = (int)(e[k] & 0xffffffffu);
+    }
+    return;
+  }
+  const size_t per_warp = (size_t)cap * 14 + 16;
+  unsigned long long *e = reinterpret_cast<unsigned long long *>(ss_smem + warp * per_warp);
+  unsigned *bounds = reinterpret_cast<unsigned *>(e + cap);
+  unsigned short *posL = reinterpret_cast<unsigned short *>(bounds + cap);
+  unsigned short *posR = posL + cap / 2 + 4;
+  const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+  for (int k = lane; k < n; k += 32) e[k] = ((unsigned long long)__float_as_uint(curv[base + sp + k]) << 32) | (unsigned)k;
+  __syncwarp();
+  unsigned stack[24];
+  int spn = 0;
+  stack[spn++] = ss_pack(0, n, 2 * (31 - __clz(n)));
+  while (spn > 0) {
+    const unsigned fr = stack[--spn];
+    const int f = (int)(fr & 2047u);
+    int l = (int)((fr >> 11) & 2047u), depth = (int)(fr >> 22);
+    bool heap = false;
+    while (l - f > 16) {
+      if (depth == 0) {
+        if (lane == 0) ssc::heap_sort(e + f, (long)(l - f));
+        __syncwarp();
+        heap = true;
+        break;
+      }
+      --depth;
+      if (lane == 0) ssc::median_to_first(e + f, e + f + 1, e + f + (l - f) / 2, e + l - 1);
+      __syncwarp();
+      const unsigned p = ss_key(e[f]);
+      const int lo = f + 1;
+      int totR = 0;
+      for (int c = lo; c < l; c += 32) {
+        const int t = c + lane;
+        totR += __popc(__ballot_sync(full, t < l && ss_key(e[t]) <= p));
+      }
+      int runL = 0, runR = 0, K = 0, first_keep_L = 0x7fffffff, min_swap_R = l;
+      for (int c = lo; c < l; c += 32) {
+        const int t = c + lane;
+        const bool v = t < l;
+        const unsigned kt = v ? ss_key(e[t]) : 0u;
+        const bool isL = v && kt >= p, isR = v && kt <= p;
+        const unsigned mL = __ballot_sync(full, isL), mR = __ballot_sync(full, isR);
+        const int cL = runL + __popc(mL & lt_mask);           // left stoppers before t
+        const int cR = totR - (runR + __popc(mR & le_mask));  // right stoppers after t
+        const bool sL = isL && cR > cL, sR = isR && cL > cR;
+        if (sL) posL[cL] = (unsigned short)t;
+        if (sR) posR[cR] = (unsigned short)t;
+        if (isL && !sL) first_keep_L = min(first_keep_L, t);
+        if (sR) min_swap_R = min(min_swap_R, t);
+        K += __popc(__ballot_sync(full, sL));
+        runL += __popc(mL);
+        runR += __popc(mR);
+      }
+      first_keep_L = __reduce_min_sync(full, first_keep_L);
+      min_swap_R = __reduce_min_sync(full, min_swap_R);
+      __syncwarp();
+      for (int k = lane; k < K; k += 32) {
+        const int a = posL[k], c2 = posR[k];
+        const unsigned long long ea = e[a];
+        e[a] = e[c2];
+        e[c2] = ea;
+      }
+      __syncwarp();
+      const int cut = min(first_keep_L, min_swap_R);
+      if (spn < 24) stack[spn++] = ss_pack(cut, l, depth);
+      l = cut;
+    }
+    if (heap) {
+      for (int t = f + lane; t < l; t += 32) bounds[t] = (unsigned)t | ((unsigned)(t + 1) << 16);
+    } else {
+      for (int t = f + lane; t < l; t += 32) bounds[t] = (unsigned)f | ((unsigned)l << 16);
+    }
+  }
+  __syncwarp();
+  for (int t = lane; t < n; t += 32) {
+    const unsigned bd = bounds[t];
+    const int a = (int)(bd & 0xffffu), c2 = (int)(bd >> 16);
+    const unsigned long long my = e[t];
+    const unsigned mk = ss_key(my);
+    int rank = a;
+    for (int u = a; u < c2; ++u) {
+      const unsigned ku = ss_key(e[u]);
+      rank += (ku < mk) || (ku == mk && u < t);
+    }
+    sort_idx[base + sp + rank] = sp + (int)(my & 0xffffu);
+  }
 }
 
 // neighbour suppression (:211-234, 252-275) executed by one lane; pk is the ring's picked window
@@ -321,9 +429,16 @@ int lo_extract_device(AlegoHandle *h) {
   { LAUNCH(h, "lo_curv_occl");
     lo_curv_occl_kernel<<<dim3(div_up(RC, CURV_TILE), B), CURV_TILE, 0, s>>>(h->seg_range, h->seg_col, h->M, h->curv, h->picked0,
                                                                              h->flabel, h->sort_idx, RC); }
+  const int sort_cap = ((C / 6 + 8) + 3) & ~3;
+  const size_t sort_smem = (size_t)SORT_WARPS * ((size_t)sort_cap * 14 + 16);
+  static bool sort_attr_set = false;
+  if (!sort_attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(lo_sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    sort_attr_set = true;
+  }
   { LAUNCH(h, "lo_sort_segments");
-    lo_sort_segments_kernel<<<div_up(B * R * 6, 64), 64, 0, s>>>(h->curv, h->start_ring, h->end_ring, h->sort_scratch, h->sort_idx,
-                                                                B, R, RC); }
+    lo_sort_segments_kernel<<<div_up(B * R * 6, SORT_WARPS), SORT_WARPS * 32, sort_smem, s>>>(h->curv, h->start_ring, h->end_ring,
+                                                                                          h->sort_scratch, h->sort_idx, B, R, RC, sort_cap); }
   const int pkcap = (C + 32 + 15) & ~15;
   { LAUNCH(h, "lo_select");
     lo_select_kernel<<<dim3(div_up(R, SEL_WARPS), B), SEL_WARPS * 32, (size_t)SEL_WARPS * pkcap, s>>>(

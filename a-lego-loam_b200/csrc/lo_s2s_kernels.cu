@@ -35,7 +35,7 @@ __device__ __forceinline__ Best warp_min_best(Best v) {
 __device__ Best warp_nearest(const GridIndex &g, int b, float qx, float qy, float qz, int max_shell) {
   const int lane = threadIdx.x & 31;
   const int T = g.table_size;
-  const int *cs = g.cell_start + (size_t)b * (T + 1);
+  const int *cs = g.cell_start + (size_t)b * (T + 4);
   const float4 *sp = g.sorted + (size_t)b * g.cap;
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);

@@ -50,6 +50,9 @@ def check_features(g, o, seq, tag=""):
         assert np.array_equal(g.debug("cloud_neighbor_picked", seq)[5:M - 5], o.get("cloud_neighbor_picked")[5:M - 5]), \
             tag + " picked: " + first_diff(g.debug("cloud_neighbor_picked", seq)[5:M - 5], o.get("cloud_neighbor_picked")[5:M - 5])
         assert np.array_equal(g.debug("cloud_label", seq)[5:M - 5], o.get("cloud_label")[5:M - 5]), tag + " cloud_label"
+        # the permutation std::sort leaves in every processed segment, ties included (laserOdometry.cpp:185)
+        assert np.array_equal(g.debug("cloud_sort_idx", seq)[5:M - 5], o.get("cloud_sort_idx")[5:M - 5]), \
+            tag + " cloud_sort_idx: " + first_diff(g.debug("cloud_sort_idx", seq)[5:M - 5], o.get("cloud_sort_idx")[5:M - 5])
     for k in ("sharp_idx", "less_sharp_idx", "flat_idx"):
         assert np.array_equal(g.debug(k, seq), o.get(k)), tag + " " + k + ": " + first_diff(g.debug(k, seq), o.get(k))
     for k in ("sharp", "less_sharp", "flat"):
@@ -137,6 +140,29 @@ def test_ip_sub_cell_jitter(alego, ob):
         o.lo_features()
         check_ip(g, o, b)
         check_features(g, o, b)
+    g.close()
+
+
+@pytest.mark.parametrize("preset", [0, 1, 3])
+def test_feature_sort_tie_heavy(alego, ob, preset):
+    """Noise-free sweeps: whole stretches of a ring share one curvature value, so the feature picks depend on the order
+    std::sort leaves between equal keys — the device must reproduce libstdc++'s introsort permutation exactly."""
+    P = alego.default_params(preset)
+    scans = make_scans(alego, P, [21, 22, 23], range_sigma=0.0, dropout=0.0)
+    g = alego.Alego(P, n_seq=len(scans))
+    buf, n = g.pack_scans(scans)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    ties = sens = 0
+    for b, s in enumerate(scans):
+        o = ob.Oracle(P)
+        o.ip(s)
+        o.lo_features()
+        ties += int(o.get("n_tie_segments"))
+        sens += int(o.get("tie_sensitive"))
+        check_features(g, o, b, "tie-heavy preset%d seq%d" % (preset, b))
+    assert ties > 20, ties      # the case does exercise tie handling ...
+    assert sens >= 1, sens      # ... and an (index-ordered) stable sort would pick different features
     g.close()
 
 
