@@ -138,6 +138,8 @@ def lib():
         "alego_lm_get_downsampled": (C.c_int, [H, C.c_int, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI]),
         "alego_pipeline_step": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p]),
         "alego_pipeline_config": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
+        "alego_pipeline_submit": (C.c_int, [H, C.c_void_p, C.c_void_p]),
+        "alego_pipeline_collect": (C.c_int, [H, C.c_void_p]),
         "alego_voxel_grid": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, PI]),
         "alego_timer_mark": (C.c_int, [H, C.c_int]),
         "alego_timer_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, PF]),
@@ -161,7 +163,7 @@ EXPORTED_SYMBOLS = [
     "alego_n_seq", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
     "alego_lo_get_features", "alego_lo_scan2scan", "alego_lo_get_state", "alego_lo_set_params", "alego_lm_set_map",
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
-    "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_voxel_grid", "alego_timer_mark",
+    "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
     "alego_timer_elapsed_ms", "alego_profile_enable", "alego_profile_reset", "alego_profile_count", "alego_profile_get",
     "alego_launch_count", "alego_debug_get",
 ]
@@ -339,8 +341,17 @@ class Alego:
         return {"params": p, "t_map2laser": t1, "r_map2laser": r1.reshape(3, 3), "t_map2odom": t2, "r_map2odom": r2.reshape(3, 3)}
 
     # ---- whole path
-    def pipeline_config(self, lm_every=1, rebuild_map_index_every_step=True, use_cuda_graph=False):
-        return self._chk(self.L.alego_pipeline_config(self.h, lm_every, int(rebuild_map_index_every_step), int(use_cuda_graph)))
+    def pipeline_config(self, lm_every=1, rebuild_map_index_every_step=True, overlap_map_build=True):
+        return self._chk(self.L.alego_pipeline_config(self.h, lm_every, int(rebuild_map_index_every_step), 0 if overlap_map_build else -1))
+
+    def pipeline_submit(self, buf, n):
+        """Asynchronous pipeline_step: buf must be pinned (pinned_empty) and untouched until collected; <= 2 in flight."""
+        return self._chk(self.L.alego_pipeline_submit(self.h, _ptr(buf), _ptr(n)))
+
+    def pipeline_collect(self, want_poses=True):
+        poses = np.zeros((self.n_seq, 12), np.float64) if want_poses else None
+        self._chk(self.L.alego_pipeline_collect(self.h, _ptr(poses)))
+        return poses
 
     def pipeline_step(self, buf=None, n=None, want_poses=True):
         poses = np.zeros((self.n_seq, 12), np.float64) if want_poses else None

@@ -133,12 +133,23 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   h->seg_sin_y = std::sin(ay); h->seg_cos_y = std::cos(ay);
   CUDA_TRY(h, cudaSetDevice(device));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto &e : h->timer) CUDA_TRY(h, cudaEventCreate(&e));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_consumed[k], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pose[k], cudaEventDisableTiming));
+  }
   const size_t B = n_seq, RC = h->RC, R = h->R;
   DMALLOC(h, h->raw_own, B * h->Nmax);
   DMALLOC(h, h->n_pts_own, B);
   h->raw = h->raw_own;
   h->n_pts = h->n_pts_own;
+  h->raw_slot[0] = h->raw_own;
+  h->n_pts_slot[0] = h->n_pts_own;
   DMALLOC(h, h->first_valid, B);
   DMALLOC(h, h->last_valid, B);
   DMALLOC(h, h->winner, B * RC);
@@ -248,6 +259,21 @@ void alego_destroy(AlegoHandle *h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->side_stream) cudaStreamSynchronize(h->side_stream);
+  if (h->raw_slot[1]) cudaFree(h->raw_slot[1]);
+  if (h->n_pts_slot[1]) cudaFree(h->n_pts_slot[1]);
+  for (int k = 0; k < 2; ++k) {
+    if (h->h_n_pts_slot[k]) cudaFreeHost(h->h_n_pts_slot[k]);
+    if (h->h_pose_slot[k]) cudaFreeHost(h->h_pose_slot[k]);
+    if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
+    if (h->ev_consumed[k]) cudaEventDestroy(h->ev_consumed[k]);
+    if (h->ev_pose[k]) cudaEventDestroy(h->ev_pose[k]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto p : h->stage_raw) cudaFree(p);
   for (auto p : h->stage_n) cudaFree(p);
   void *ptrs[] = {h->raw_own, h->n_pts_own, h->first_valid, h->last_valid, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
@@ -300,7 +326,7 @@ void alego_host_free(void *p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points);
+static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points, cudaStream_t st = nullptr);
 
 int alego_ip_upload(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points) {
   if (!h || !xyzi_host || !n_points) return ALEGO_BAD_ARG;
@@ -335,20 +361,21 @@ int alego_stage_select(AlegoHandle *h, int slot) {
   return ALEGO_OK;
 }
 
-static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points) {
+static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyzi_host, const int32_t *n_points, cudaStream_t st) {
+  if (!st) st = h->stream;
   size_t total = 0;
   for (int b = 0; b < h->B; ++b) {
     if (n_points[b] < 0 || n_points[b] > h->Nmax) { h->err = "n_points out of range"; return ALEGO_BAD_ARG; }
     total += n_points[b];
   }
-  CUDA_TRY(h, cudaMemcpyAsync(n_dev, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(n_dev, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, st));
   if (total * 10 >= (size_t)h->B * h->Nmax * 9) {  // nearly full rows: one DMA
-    CUDA_TRY(h, cudaMemcpyAsync(raw, xyzi_host, (size_t)h->B * h->Nmax * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(raw, xyzi_host, (size_t)h->B * h->Nmax * sizeof(float4), cudaMemcpyHostToDevice, st));
   } else {
     for (int b = 0; b < h->B; ++b)
       if (n_points[b] > 0)
         CUDA_TRY(h, cudaMemcpyAsync(raw + (size_t)b * h->Nmax, xyzi_host + (size_t)b * h->Nmax * 4, (size_t)n_points[b] * sizeof(float4),
-                                    cudaMemcpyHostToDevice, h->stream));
+                                    cudaMemcpyHostToDevice, st));
   }
   return ALEGO_OK;
 }
@@ -600,42 +627,108 @@ int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_ev
   if (!h || lm_every < 0) return ALEGO_BAD_ARG;
   h->lm_every = lm_every;
   h->rebuild_map_every_step = rebuild_map_index_every_step != 0;
-  (void)use_cuda_graph;  // reserved
+  h->overlap_map_build = use_cuda_graph >= 0;  // third argument: < 0 disables the side-stream map-index build (debugging); graphs reserved
   return ALEGO_OK;
 }
 
-int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out) {
-  if (!h) return ALEGO_BAD_ARG;
-  CUDA_TRY(h, cudaSetDevice(h->dev));
+// IP -> LO -> LM on whatever h->raw / h->n_pts point at; everything is enqueued, nothing waits.
+static int pipeline_enqueue(AlegoHandle *h) {
   int rc;
-  if (xyzi_host) {
-    if ((rc = alego_ip_upload(h, xyzi_host, n_points)) != ALEGO_OK) return rc;
-  }
   bool any_ext = false;
   for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
   if (any_ext) {  // the pipeline feeds LaserMapping from LaserOdometry's device clouds
     CUDA_TRY(h, cudaMemsetAsync(h->lm_use_ext, 0, h->B * sizeof(int), h->stream));
     std::fill(h->lm_scan_is_external.begin(), h->lm_scan_is_external.end(), 0);
   }
+  const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
+  // The local-map index does not depend on the sweep: rebuild it (the reference rebuilds its kd-trees every mapped
+  // frame, laserMapping.cpp:356-357) on the side stream while ImageProjection / LaserOdometry run on the main one.
+  cudaEvent_t map_ev = nullptr;
+  if (run_lm && h->overlap_map_build && !h->profiling && (h->rebuild_map_every_step || !h->map_index_valid)) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));  // after the previous pass's associations (the index is rebuilt in place)
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    h->launch_stream = h->side_stream;
+    rc = lm_build_map_index(h);
+    h->launch_stream = nullptr;
+    if (rc != ALEGO_OK) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    map_ev = h->ev_join;
+  }
   if ((rc = alego_ip_run(h)) != ALEGO_OK) return rc;
   if ((rc = alego_lo_extract(h)) != ALEGO_OK) return rc;
   if ((rc = lo_scan2scan_device(h)) != ALEGO_OK) return rc;
   h->stage_feat_done = false;
-  const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
   if (run_lm) {
     if ((rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
-    if ((rc = lm_scan2map_device(h, h->lm_guard, true)) != ALEGO_OK) return rc;
+    if ((rc = lm_scan2map_device(h, h->lm_guard, true, map_ev)) != ALEGO_OK) return rc;
   } else {
+    if (map_ev) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, map_ev, 0));
     LAUNCH(h, "pose_pack");
     pose_pack_kernel<<<div_up(h->B, 128), 128, 0, h->stream>>>(h->m2l, h->lm_params, h->t_w, h->d_pose, h->B);
   }
   ++h->scan_count;
+  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}
+
+int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out) {
+  if (!h) return ALEGO_BAD_ARG;
+  if (h->n_submitted != h->n_collected) { h->err = "alego_pipeline_step while submitted steps are in flight"; return ALEGO_NOT_READY; }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  int rc;
+  if (xyzi_host) {
+    if ((rc = alego_ip_upload(h, xyzi_host, n_points)) != ALEGO_OK) return rc;
+  }
+  if ((rc = pipeline_enqueue(h)) != ALEGO_OK) return rc;
   if (poses_out) {
     CUDA_TRY(h, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     std::memcpy(poses_out, h->h_pose, (size_t)h->B * 12 * sizeof(double));
   }
-  CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}
+
+// Asynchronous form: the H2D copy of sweep t+1 (copy stream, second device staging buffer) overlaps the pass over
+// sweep t.  At most two steps in flight; alego_pipeline_collect returns them in submission order.
+int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points) {
+  if (!h || !xyzi_host || !n_points) return ALEGO_BAD_ARG;
+  if (h->n_submitted - h->n_collected >= 2) { h->err = "alego_pipeline_submit: two steps already in flight (collect first)"; return ALEGO_NOT_READY; }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  const int slot = (int)(h->n_submitted & 1);
+  if (!h->raw_slot[slot]) {
+    CUDA_TRY(h, cudaMalloc(&h->raw_slot[slot], (size_t)h->B * h->Nmax * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc(&h->n_pts_slot[slot], (size_t)h->B * sizeof(int)));
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (!h->h_n_pts_slot[k]) CUDA_TRY(h, cudaMallocHost((void **)&h->h_n_pts_slot[k], (size_t)h->B * sizeof(int32_t)));
+    if (!h->h_pose_slot[k]) CUDA_TRY(h, cudaMallocHost((void **)&h->h_pose_slot[k], (size_t)h->B * 12 * sizeof(double)));
+  }
+  std::memcpy(h->h_n_pts_slot[slot], n_points, (size_t)h->B * sizeof(int32_t));
+  // the staging buffer may still be read by the pass submitted two steps ago
+  if (h->consumed_valid[slot]) CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+  int rc = upload_into(h, h->raw_slot[slot], h->n_pts_slot[slot], xyzi_host, h->h_n_pts_slot[slot], h->copy_stream);
+  if (rc != ALEGO_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+  h->raw = h->raw_slot[slot];
+  h->n_pts = h->n_pts_slot[slot];
+  if ((rc = pipeline_enqueue(h)) != ALEGO_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
+  h->consumed_valid[slot] = true;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_pose_slot[slot], h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev_pose[slot], h->stream));
+  ++h->n_submitted;
+  return ALEGO_OK;
+}
+
+int alego_pipeline_collect(AlegoHandle *h, double *poses_out) {
+  if (!h) return ALEGO_BAD_ARG;
+  if (h->n_submitted == h->n_collected) { h->err = "alego_pipeline_collect: nothing in flight"; return ALEGO_NOT_READY; }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  const int slot = (int)(h->n_collected & 1);
+  CUDA_TRY(h, cudaEventSynchronize(h->ev_pose[slot]));
+  if (poses_out) std::memcpy(poses_out, h->h_pose_slot[slot], (size_t)h->B * 12 * sizeof(double));
+  ++h->n_collected;
   return ALEGO_OK;
 }
 

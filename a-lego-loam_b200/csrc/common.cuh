@@ -40,6 +40,14 @@ struct AlegoHandle {
   AlegoParams P;
   int dev = 0, B = 0, Nmax = 0, R = 0, C = 0, RC = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;    // map-index build overlapped with IP + LO (alego_pipeline_step)
+  cudaStream_t copy_stream = nullptr;    // H2D of the next sweep overlapped with the current pass (alego_pipeline_submit)
+  cudaStream_t launch_stream = nullptr;  // when set, LAUNCH() / grid_build() target this stream instead of `stream`
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_pose[2] = {nullptr, nullptr};
+  bool consumed_valid[2] = {false, false};
+  bool overlap_map_build = true;
+  long long n_submitted = 0, n_collected = 0;
   std::string err;
   int64_t launches = 0;
   bool profiling = false;
@@ -62,6 +70,9 @@ struct AlegoHandle {
   int *n_pts = nullptr;        // [B]
   float4 *raw_own = nullptr;
   int *n_pts_own = nullptr;
+  float4 *raw_slot[2] = {nullptr, nullptr};  // device staging of alego_pipeline_submit (slot 0 aliases raw_own)
+  int *n_pts_slot[2] = {nullptr, nullptr};
+  int32_t *h_n_pts_slot[2] = {nullptr, nullptr};  // pinned copies of the caller's n_points
   std::vector<float4 *> stage_raw;  // sweeps pre-staged in HBM (alego_stage_*)
   std::vector<int *> stage_n;
   int *first_valid = nullptr;  // [B]
@@ -151,6 +162,7 @@ struct AlegoHandle {
 
   // host staging for small D2H results
   double *h_pose = nullptr;  // pinned [B][12]
+  double *h_pose_slot[2] = {nullptr, nullptr};  // pinned, per in-flight step
   double *d_pose = nullptr;  // [B][12]
 };
 
@@ -186,11 +198,11 @@ struct LaunchScope {
       return e;
     };
     e0 = get(); e1 = get();
-    cudaEventRecord(e0, h->stream);
+    cudaEventRecord(e0, h->launch_stream ? h->launch_stream : h->stream);
   }
   ~LaunchScope() {
     if (id < 0) return;
-    cudaEventRecord(e1, h->stream);
+    cudaEventRecord(e1, h->launch_stream ? h->launch_stream : h->stream);
     h->prof[id].pending.emplace_back(e0, e1);
   }
 };

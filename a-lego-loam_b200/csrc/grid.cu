@@ -82,7 +82,7 @@ void grid_free(GridIndex *g) {
 
 int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag) {
   const int B = h->B, T = g->table_size;
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->launch_stream ? h->launch_stream : h->stream;
   const float inv = 1.0f / g->cell;
   const int blocks = min(div_up(g->cap, 256), 1024);
   std::string t0 = std::string("grid_count_") + tag, t1 = std::string("grid_scan_") + tag, t2 = std::string("grid_fill_") + tag;

@@ -448,7 +448,7 @@ int lm_build_map_index(AlegoHandle *h) {
   return ALEGO_OK;
 }
 
-int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose) {
+int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEvent_t map_index_event) {
   const int B = h->B;
   cudaStream_t s = h->stream;
   if (!h->map_corner || !h->map_surf) { h->err = "alego_lm_scan2map: no local map (call alego_lm_set_map)"; return ALEGO_NOT_READY; }
@@ -471,7 +471,9 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose) {
     lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_STAGE * 8, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
         (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
         h->lm_n, sort_c, sort_s, sort_o, next_pow2(cc), next_pow2(cs + co), next_pow2(co)); }
-  if (h->rebuild_map_every_step || !h->map_index_valid) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
+  if (map_index_event) {  // built concurrently on the side stream (alego_pipeline_step)
+    CUDA_TRY(h, cudaStreamWaitEvent(s, map_index_event, 0));
+  } else if (h->rebuild_map_every_step || !h->map_index_valid) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
     rc = lm_build_map_index(h);
     if (rc != ALEGO_OK) return rc;
   }

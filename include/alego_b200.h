@@ -177,8 +177,19 @@ int alego_lm_get_downsampled(AlegoHandle *h, int seq, float *corner_ds, int32_t 
  * then t_w_cur_ of LO [3].  Host buffers in, host buffers out (H2D + D2H inside the call).
  * xyzi_host == NULL means "inputs already uploaded with alego_ip_upload". poses_out may be NULL. */
 int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out);
-/* lm_every: run LM on every k-th sweep (reference: 2, laserMapping.cpp:112); 0 disables LM. */
-int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_every_step, int use_cuda_graph);
+/* Asynchronous form of alego_pipeline_step for streaming ingestion (a rosbag / sensor thread feeding the nodelets,
+ * imageProjection.cpp:45 subscriber queue): submit enqueues the H2D copy of the sweeps on a copy stream into one of
+ * two device staging buffers and the whole IP -> LO -> LM pass behind it, and returns without waiting, so the copy
+ * of sweep t+1 overlaps the pass over sweep t.  xyzi_host must be pinned (alego_host_alloc) and stay untouched until
+ * the step is collected.  At most two steps may be in flight; collect waits for the OLDEST one and returns its
+ * poses (layout as alego_pipeline_step; poses_out may be NULL). */
+int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
+int alego_pipeline_collect(AlegoHandle *h, double *poses_out);
+/* lm_every: run LM on every k-th sweep (reference: 2, laserMapping.cpp:112); 0 disables LM.
+ * rebuild_map_index_every_step: rebuild the local-map search index on every mapped sweep, like the reference's kd-tree
+ * builds (laserMapping.cpp:356-357), instead of only after alego_lm_set_map.  options: 0 default; a negative value
+ * disables the side-stream overlap of that rebuild (debugging). */
+int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_every_step, int options);
 
 /* ---- stand-alone operators (used by LO/LM internally, exposed for tests and callers) ------------- */
 /* pcl::VoxelGrid<PointXYZI> equivalent on host data (setLeafSize(leaf,leaf,leaf); filter()).

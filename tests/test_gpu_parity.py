@@ -400,3 +400,50 @@ def test_stage_order_errors(alego):
     with pytest.raises(alego.AlegoError):
         g.debug("label_mat", seq=5)
     g.close()
+
+
+def test_async_submit_collect_matches_sync(alego):
+    """alego_pipeline_submit / _collect (H2D of sweep t+1 overlapped with the pass over sweep t, map index built on the side
+    stream) returns bit-identical poses to the synchronous alego_pipeline_step, with and without the side-stream overlap."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seeds, T = [0, 1, 2], 6
+    worlds = [alego.SynthWorld(seed=s) for s in seeds]
+    maps = [w.make_map(4000, 20000, seed=s, radius=60.0) for w, s in zip(worlds, seeds)]
+    sweeps = [[w.render(P, alego.trajectory_pose(t, seed=s), noise_seed=10 * s + t) for w, s in zip(worlds, seeds)] for t in range(T)]
+
+    def fresh(overlap):
+        g = alego.Alego(P, n_seq=len(seeds))
+        for b, (cm, sm) in enumerate(maps):
+            g.lm_set_map(b, cm, sm)
+        g.pipeline_config(lm_every=2, overlap_map_build=overlap)
+        return g
+
+    g = fresh(False)
+    ref = []
+    for t in range(T):
+        buf, n = g.pack_scans(sweeps[t])
+        ref.append(g.pipeline_step(buf, n))
+    g.close()
+    g = fresh(True)
+    bufs = [alego.pinned_empty((len(seeds), g.max_points, 4), np.float32) for _ in range(2)]
+    ns = [np.zeros(len(seeds), np.int32) for _ in range(2)]
+    got = []
+    for t in range(T):
+        if t >= 2:
+            got.append(g.pipeline_collect())     # frees the pinned buffer of step t-2
+        b_, n_ = g.pack_scans(sweeps[t])
+        bufs[t % 2][:] = b_
+        ns[t % 2][:] = n_
+        g.pipeline_submit(bufs[t % 2], ns[t % 2])
+    with pytest.raises(alego.AlegoError):
+        g.pipeline_submit(bufs[0], ns[0])        # two steps already in flight
+    got.append(g.pipeline_collect())
+    got.append(g.pipeline_collect())
+    with pytest.raises(alego.AlegoError):
+        g.pipeline_collect()                     # nothing in flight
+    for t in range(T):
+        assert np.array_equal(got[t], ref[t]), "sweep %d" % t
+    # and the synchronous call still works afterwards on the same handle
+    buf, n = g.pack_scans(sweeps[0])
+    assert g.pipeline_step(buf, n).shape == (len(seeds), 12)
+    g.close()
