@@ -286,7 +286,7 @@ void alego_destroy(AlegoHandle *h) {
                   h->lo_trace_n, h->map_corner, h->map_surf, h->n_map_corner, h->n_map_surf, h->lm_in_corner, h->lm_in_surf,
                   h->lm_in_outlier, h->lm_in_n, h->lm_use_ext, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total,
                   h->lm_surf_total_ds, h->lm_n, h->lm_params, h->m2o, h->o2l, h->m2l, h->lm_edge, h->lm_plane, h->lm_report,
-                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose};
+                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose, h->lm_nn_c, h->lm_nn_s};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   grid_free(&h->g_surf_last);

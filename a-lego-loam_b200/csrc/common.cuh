@@ -154,6 +154,7 @@ struct AlegoHandle {
   Pose *m2o = nullptr, *o2l = nullptr, *m2l = nullptr;  // [B]
   double *lm_edge = nullptr;   // [B][ds_cap_c][10]: valid, cp3, lpj3, lpl3
   double *lm_plane = nullptr;  // [B][ds_cap_s+o][8]: valid, cp3, n3, d
+  int *lm_nn_c = nullptr, *lm_nn_s = nullptr;  // [B][cap][5] map indices of the gated 5-NN (first = -1: none)
   AlegoSolveReport *lm_report = nullptr;
   int *lm_guard = nullptr;     // [B] scan2MapOptimization guard (laserMapping.cpp:350)
   double *lm_trace = nullptr;  // [B][outer*(iters+1)][7]

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(int *__restrict__ table
 
 __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict__ pts, size_t pts_stride, const int *__restrict__ n_ptr,
                                                         int n_stride, int *__restrict__ cursor, float4 *__restrict__ sorted, int T,
-                                                        float inv_cell, int cap) {
+                                                        float inv_cell, int cap, int pack_ring) {
   const int b = blockIdx.y;
   const int n = min(n_ptr[(size_t)b * n_stride], cap);
   const float4 *src = pts + (size_t)b * pts_stride;
@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict
     const float4 p = ldg_f4(src + i);
     if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
     const int slot = atomicAdd(cur + grid_hash(grid_coord(p.x, inv_cell), grid_coord(p.y, inv_cell), grid_coord(p.z, inv_cell), T), 1);
-    dst[slot] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    // pack_ring: the ring id int(intensity) (laserOdometry.cpp:347,436) rides in bits 24..30 next to the index
+    const int tag = pack_ring ? (i | ((int)p.w << GRID_RING_SHIFT)) : i;
+    dst[slot] = make_float4(p.x, p.y, p.z, __int_as_float(tag));
   }
 }
 
@@ -80,7 +82,8 @@ void grid_free(GridIndex *g) {
   g->cap = g->table_size = 0;
 }
 
-int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag) {
+int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag,
+               bool pack_ring) {
   const int B = h->B, T = g->table_size;
   cudaStream_t s = h->launch_stream ? h->launch_stream : h->stream;
   const float inv = 1.0f / g->cell;
@@ -91,7 +94,7 @@ int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_strid
     grid_count_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cell_start, T, inv, g->cap); }
   { LAUNCH(h, t1.c_str()); grid_scan_kernel<<<B, 1024, 0, s>>>(g->cell_start, T); }
   { LAUNCH(h, t2.c_str());
-    grid_fill_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cell_start, g->sorted, T, inv, g->cap); }
+    grid_fill_kernel<<<dim3(blocks, B), 256, 0, s>>>(pts, pts_stride, n_ptr, n_stride, g->cell_start, g->sorted, T, inv, g->cap, pack_ring ? 1 : 0); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

@@ -216,7 +216,30 @@ __device__ void lstsq_5x3_dev(double A[5][3], double b[5], double n[3]) {
 }
 
 // exact 5 nearest neighbours within squared distance < 1.0 (float), ascending (distance, index).
-// A cell edge >= 1 m makes the 27 surrounding cells sufficient for every neighbour that can pass the gate.
+// A cell edge >= 1 m makes the 27 surrounding cells sufficient for every neighbour that can pass the gate.  The
+// x-runs of 3 cells are contiguous in the blocked hash layout (grid.cuh), so a query reads 9 columns x (1 or 2)
+// ranges; the range bounds of all columns are independent loads issued before any point is touched.
+__device__ __forceinline__ void knn5_offer(float d, int idx, float *bd, int *bi, int &found) {
+  if (d < bd[4] || (d == bd[4] && idx < bi[4])) {
+    // two hash-colliding blocks can present the same bucket twice: a point already held is not offered again (a point
+    // that was evicted can never re-enter: everything held is strictly better)
+    if (idx == bi[0] || idx == bi[1] || idx == bi[2] || idx == bi[3] || idx == bi[4]) return;
+    int pos = 4;
+#pragma unroll
+    for (int t = 4; t > 0; --t) {
+      if (pos == t && (d < bd[t - 1] || (d == bd[t - 1] && idx < bi[t - 1]))) {
+        bd[t] = bd[t - 1];
+        bi[t] = bi[t - 1];
+        pos = t - 1;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+      if (pos == t) { bd[t] = d; bi[t] = idx; }
+    ++found;
+  }
+}
+
 __device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, float qy, float qz, float *bd, int *bi) {
   const int T = g.table_size;
   const int *cs = g.cell_start + (size_t)b * (T + 4);
@@ -226,48 +249,50 @@ __device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, fl
 #pragma unroll
   for (int t = 0; t < 5; ++t) { bd[t] = 3.402823466e+38f; bi[t] = 0x7fffffff; }
   int found = 0;
-  int seen[27];
-  int nseen = 0;
-  for (int c = 0; c < 27; ++c) {
-    const int hsh = grid_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, T);
-    bool dup = false;  // two of the 27 cells can share a bucket: visit it once
-    for (int u = 0; u < nseen; ++u) dup |= (seen[u] == hsh);
-    if (dup) continue;
-    seen[nseen++] = hsh;
-    const int e = cs[hsh + 1];
-    for (int t = cs[hsh]; t < e; ++t) {
+  int r1s[9], r1e[9], r2s[9], r2e[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const int iy = cy + c % 3 - 1, iz = cz + c / 3 - 1;
+    const int h0 = grid_hash(cx - 1, iy, iz, T), h1 = grid_hash(cx, iy, iz, T), h2 = grid_hash(cx + 1, iy, iz, T);
+    r1s[c] = cs[h0];
+    r2e[c] = cs[h2 + 1];
+    if (h2 == h0 + 2) {          // one block: [h0, h2] contiguous
+      r1e[c] = r2e[c];
+      r2s[c] = r2e[c];
+    } else if (h1 == h0 + 1) {   // {cx-1, cx} | {cx+1}
+      r1e[c] = cs[h1 + 1];
+      r2s[c] = cs[h2];
+    } else {                     // {cx-1} | {cx, cx+1}
+      r1e[c] = cs[h0 + 1];
+      r2s[c] = cs[h1];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    for (int t = r1s[c]; t < r1e[c]; ++t) {
       const float4 p = sp[t];
       const float d = l2_simple(qx, qy, qz, p);
-      if (!(d < 1.0f)) continue;
-      const int idx = __float_as_int(p.w);
-      if (d < bd[4] || (d == bd[4] && idx < bi[4])) {
-        int pos = 4;
-        while (pos > 0 && (d < bd[pos - 1] || (d == bd[pos - 1] && idx < bi[pos - 1]))) {
-          bd[pos] = bd[pos - 1];
-          bi[pos] = bi[pos - 1];
-          --pos;
-        }
-        bd[pos] = d;
-        bi[pos] = idx;
-        ++found;
-      }
+      if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
+    }
+    for (int t = r2s[c]; t < r2e[c]; ++t) {
+      const float4 p = sp[t];
+      const float d = l2_simple(qx, qy, qz, p);
+      if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
     }
   }
   return found < 5 ? found : 5;
 }
 
-template <bool EDGE>
-__global__ void __launch_bounds__(128)
-lm_assoc_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, const float4 *__restrict__ map,
-                int map_cap, const int *__restrict__ n_map, GridIndex g, const Pose *__restrict__ m2l, const int *__restrict__ guard,
-                double *__restrict__ out, int out_w) {
+// K14a/K15a: per query — pointAssociateToMap, exact gated 5-NN; writes the 5 map indices (nn[0] = -1: no residual)
+__global__ void __launch_bounds__(256)
+lm_knn_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, GridIndex g,
+              const Pose *__restrict__ m2l, const int *__restrict__ guard, int *__restrict__ nn) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(lm_n[b * 8 + n_slot], qcap);
   if (i >= nq) return;
-  double *o = out + ((size_t)b * qcap + i) * out_w;
-  o[0] = 0.0;
-  if (!guard[b]) return;
+  int *o = nn + ((size_t)b * qcap + i) * 5;
+  if (!guard[b]) { o[0] = -1; return; }
   const float4 cp = query[(size_t)b * qcap + i];
   const Pose &P = m2l[b];
   // pointAssociateToMap (laserMapping.h:187-194): double transform, float result
@@ -276,7 +301,25 @@ lm_assoc_kernel(const float4 *__restrict__ query, int qcap, const int *__restric
   const float sz = (float)(P.R[6] * cp.x + P.R[7] * cp.y + P.R[8] * cp.z + P.t[2]);
   float bd[5];
   int bi[5];
-  if (knn5_gate(g, b, sx, sy, sz, bd, bi) < 5) return;  // point_dist_[4] < 1.0 (:376, :426)
+  if (knn5_gate(g, b, sx, sy, sz, bd, bi) < 5) { o[0] = -1; return; }  // point_dist_[4] < 1.0 (:376, :426)
+#pragma unroll
+  for (int t = 0; t < 5; ++t) o[t] = bi[t];
+}
+
+// K14b/K15b: per query with 5 neighbours — line test (PCA) or plane fit in double; writes the residual block
+template <bool EDGE>
+__global__ void __launch_bounds__(128)
+lm_fit_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, const float4 *__restrict__ map,
+              int map_cap, const int *__restrict__ nn, double *__restrict__ out, int out_w) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = min(lm_n[b * 8 + n_slot], qcap);
+  if (i >= nq) return;
+  double *o = out + ((size_t)b * qcap + i) * out_w;
+  o[0] = 0.0;
+  const int *bi = nn + ((size_t)b * qcap + i) * 5;
+  if (bi[0] < 0) return;
+  const float4 cp = query[(size_t)b * qcap + i];
   const float4 *M = map + (size_t)b * map_cap;
   double nb[5][3];
 #pragma unroll
@@ -310,9 +353,9 @@ lm_assoc_kernel(const float4 *__restrict__ query, int qcap, const int *__restric
     for (int j = 0; j < 5; ++j)
       for (int c = 0; c < 3; ++c) A[j][c] = nb[j][c];
     lstsq_5x3_dev(A, rhs, nrm);
-    const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-    const double d = 1 / nn;
-    for (int c = 0; c < 3; ++c) nrm[c] /= nn;
+    const double nn2 = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    const double d = 1 / nn2;
+    for (int c = 0; c < 3; ++c) nrm[c] /= nn2;
     for (int j = 0; j < 5; ++j)
       if (fabs(nrm[0] * nb[j][0] + nrm[1] * nb[j][1] + nrm[2] * nb[j][2] + d) > 0.2) return;  // (:441-452)
     o[1] = cp.x; o[2] = cp.y; o[3] = cp.z;
@@ -478,12 +521,18 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEven
     if (rc != ALEGO_OK) return rc;
   }
   { LAUNCH(h, "lm_guard"); lm_guard_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_n, h->n_map_corner, guard_dev, B); }
-  { LAUNCH(h, "lm_assoc_corner");
-    lm_assoc_kernel<true><<<dim3(div_up(cc, 128), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
-        h->n_map_corner, h->g_map_corner, h->m2l, guard_dev, h->lm_edge, 10); }
-  { LAUNCH(h, "lm_assoc_surf");
-    lm_assoc_kernel<false><<<dim3(div_up(cs + co, 128), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf,
-        h->map_cap_s, h->n_map_surf, h->g_map_surf, h->m2l, guard_dev, h->lm_plane, 8); }
+  // query slots actually populated are far fewer than the capacities: size the grids from the LO feature capacities
+  { LAUNCH(h, "lm_knn_corner");
+    lm_knn_kernel<<<dim3(div_up(cc, 256), B), 256, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->g_map_corner, h->m2l, guard_dev, h->lm_nn_c); }
+  { LAUNCH(h, "lm_fit_corner");
+    lm_fit_kernel<true><<<dim3(div_up(cc, 128), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
+                                                                  h->lm_nn_c, h->lm_edge, 10); }
+  { LAUNCH(h, "lm_knn_surf");
+    lm_knn_kernel<<<dim3(div_up(cs + co, 256), B), 256, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->g_map_surf, h->m2l, guard_dev,
+                                                                h->lm_nn_s); }
+  { LAUNCH(h, "lm_fit_surf");
+    lm_fit_kernel<false><<<dim3(div_up(cs + co, 128), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
+                                                                       h->lm_nn_s, h->lm_plane, 8); }
   { LAUNCH(h, "lm_solve");
     lm_solve_kernel<<<B, 256, 0, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
         h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
@@ -502,6 +551,7 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(h->lm_corner_ds); cudaFree(h->lm_surf_ds); cudaFree(h->lm_outlier_ds); cudaFree(h->lm_surf_total);
   cudaFree(h->lm_surf_total_ds); cudaFree(h->lm_edge); cudaFree(h->lm_plane); cudaFree(h->vox_sort);
+  cudaFree(h->lm_nn_c); cudaFree(h->lm_nn_s);
   h->ds_cap_c = want_c; h->ds_cap_s = want_s; h->ds_cap_o = want_o;
   CUDA_TRY(h, cudaMalloc(&h->lm_corner_ds, (size_t)B * want_c * sizeof(float4)));
   CUDA_TRY(h, cudaMalloc(&h->lm_surf_ds, (size_t)B * want_s * sizeof(float4)));
@@ -510,6 +560,8 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
   CUDA_TRY(h, cudaMalloc(&h->lm_surf_total_ds, (size_t)B * (want_s + want_o) * sizeof(float4)));
   CUDA_TRY(h, cudaMalloc(&h->lm_edge, (size_t)B * want_c * 10 * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->lm_plane, (size_t)B * (want_s + want_o) * 8 * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_nn_c, (size_t)B * want_c * 5 * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&h->lm_nn_s, (size_t)B * (want_s + want_o) * 5 * sizeof(int)));
   const size_t sort_elems = (size_t)B * ((size_t)next_pow2(want_c) + next_pow2(want_s + want_o) + next_pow2(want_o));
   CUDA_TRY(h, cudaMalloc(&h->vox_sort, sort_elems * sizeof(u64)));
   return ALEGO_OK;
