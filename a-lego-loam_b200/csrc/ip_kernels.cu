@@ -5,7 +5,7 @@
 // K1a ip_project   : per input point row/col binning (:76-104), deterministic "last writer wins" by atomicMax
 // K1b ip_gather    : per cell — organised cloud, range image, resets of the per-scan images (:24-33,:197-205)
 // K2  ip_ground    : vertical-neighbour slope test (:106-132)
-// K3  ccl_*        : connected components by lock-free union-find (:134-156, 210-280)
+// K3  ccl_*        : connected components: per-ring runs by scan, vertical joins by lock-free union-find (:134-156, 210-280)
 // K4/K5 ip_rowcount + ip_compact : feasibility (:282-315), raster-order label numbering, ring-major stream
 //                    compaction into the cloud_info arrays (:158-191)
 #include <math_constants.h>
@@ -185,36 +185,83 @@ __device__ __forceinline__ bool seg_join(float ra, float rb, bool horizontal, co
   return angle > P.seg_theta;
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const float *__restrict__ range, const uint8_t *__restrict__ ground,
+// inclusive block-wide max scan of one int per thread (smem: >= 33 ints); all threads must call
+__device__ __forceinline__ int block_incl_max_scan(int v, int *smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, t);
+  }
+  __syncthreads();
+  if (lane == 31) smem[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? smem[lane] : -0x7fffffff;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w = max(w, t);
+    }
+    smem[lane] = w;
+  }
+  __syncthreads();
+  return wid > 0 ? max(v, smem[wid - 1]) : v;
+}
+
+// Horizontal pass, one CTA per (ring, sequence): candidate mask (:134-143) and the horizontal joins of the ring.  A
+// ring decomposes into runs of cells each joined to its left neighbour; every cell is pointed at the first cell of its
+// run by a max-scan of the run-start columns — no atomics.  The column wrap (:241-248) links the last run to the first.
+__global__ void __launch_bounds__(256) ccl_rows_kernel(const float *__restrict__ range, const uint8_t *__restrict__ ground,
                                                        int *__restrict__ parent, int2 *__restrict__ comp_stat, IpDev P) {
-  const int b = blockIdx.y;
-  const size_t base = (size_t)b * P.RC;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
-    const bool valid = ground[base + cell] == 0 && range[base + cell] != ALEGO_EMPTY_RANGE;  // (:134-143)
-    parent[base + cell] = valid ? cell : -1;
-    comp_stat[base + cell] = make_int2(0, 0);
+  const int b = blockIdx.y, row = blockIdx.x;
+  const size_t base = (size_t)b * P.RC + (size_t)row * P.C;
+  const float *rg = range + base;
+  const uint8_t *gr = ground + base;
+  __shared__ int s_scan[34];
+  int carry = -1;  // run-start column inherited from the columns left of this chunk
+  for (int c0 = 0; c0 < P.C; c0 += blockDim.x) {
+    const int col = c0 + threadIdx.x;
+    bool valid = false, join_left = false;
+    if (col < P.C) {
+      const float r0 = rg[col];
+      valid = gr[col] == 0 && r0 != ALEGO_EMPTY_RANGE;
+      if (valid && col > 0) {
+        const float rl = rg[col - 1];
+        join_left = gr[col - 1] == 0 && rl != ALEGO_EMPTY_RANGE && seg_join(rl, r0, true, P);
+      }
+      comp_stat[base + col] = make_int2(0, 0);
+    }
+    const int start = (valid && !join_left) ? col : -1;
+    const int run = max(block_incl_max_scan(start, s_scan), carry);
+    if (col < P.C) parent[base + col] = valid ? row * P.C + run : -1;
+    // the last thread of the chunk holds the max over the whole chunk
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_scan[33] = run;
+    __syncthreads();
+    carry = s_scan[33];
+  }
+  if (threadIdx.x == 0 && P.C > 1) {
+    const float rf = rg[0], rl = rg[P.C - 1];
+    const bool vf = gr[0] == 0 && rf != ALEGO_EMPTY_RANGE, vl = gr[P.C - 1] == 0 && rl != ALEGO_EMPTY_RANGE;
+    if (vf && vl && seg_join(rl, rf, true, P)) {
+      const int last_root = parent[base + P.C - 1];  // written by this CTA (same thread block: visible after the barrier)
+      if (last_root != row * P.C) parent[(size_t)b * P.RC + last_root] = row * P.C;
+    }
   }
 }
 
+// Vertical pass: joins between a cell and the cell below it (rows do not wrap, :237) on the union-find forest
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const float *__restrict__ range, int *parent, IpDev P) {
   const int b = blockIdx.y;
   const size_t base = (size_t)b * P.RC;
   int *L = parent + base;
   const float *rg = range + base;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
-    if (L[cell] < 0) continue;
-    const int row = cell / P.C, col = cell - row * P.C;
-    const float r0 = rg[cell];
-    // right neighbour, column index wraps (:241-248)
-    if (P.C > 1) {
-      const int nb = (col == P.C - 1) ? cell - col : cell + 1;
-      if (L[nb] >= 0 && seg_join(r0, rg[nb], true, P)) uf_unite(L, cell, nb);
-    }
-    // lower neighbour (next ring), rows do not wrap (:237)
-    if (row + 1 < P.R) {
-      const int nb = cell + P.C;
-      if (L[nb] >= 0 && seg_join(r0, rg[nb], false, P)) uf_unite(L, cell, nb);
-    }
+  const int n = P.RC - P.C;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x) {
+    const int nb = cell + P.C;
+    if (L[cell] < 0 || L[nb] < 0) continue;
+    if (seg_join(rg[cell], rg[nb], false, P)) uf_unite(L, cell, nb);
   }
 }
 
@@ -408,7 +455,7 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
     LAUNCH(h, "ip_ground");
     ip_ground_kernel<<<dim3(min(div_up(gpairs, 256), 4096), B), 256, 0, s>>>(h->cloud, h->ground, P);
   }
-  { LAUNCH(h, "ccl_init"); ccl_init_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->ground, h->parent, h->comp_stat, P); }
+  { LAUNCH(h, "ccl_rows"); ccl_rows_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->range, h->ground, h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->parent, P); }
   { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ip_rowcount");

@@ -64,14 +64,13 @@ __global__ void lm_prepare_kernel(const int *use_ext, const double *t_w, const d
 }
 
 #define LMV_THREADS 1024
-#define LMV_STAGE 8192  // keys of shared-memory staging (64 KB)
+#define LMV_SMEM (radix_scratch_bytes<int>(LMV_THREADS))  // radix-sort scratch (64 KB of digit counters)
 // kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launch)
 __global__ void __launch_bounds__(LMV_THREADS)
 lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s, float4 *ds_o,
                 float4 *total, float4 *ds_total, int cap_c, int cap_s, int cap_o, int *lm_n, u64 *sort_c, u64 *sort_s, u64 *sort_o,
                 int sort_cap_c, int sort_cap_s, int sort_cap_o) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
-  u64 *stage = reinterpret_cast<u64 *>(lmv_smem);
   __shared__ float redf[6 * 32 + 8];
   __shared__ int redi[48];
   __shared__ VoxFrame frame;
@@ -91,30 +90,28 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
     __syncthreads();
     src = tot; n = ns + no; leaf = leaf_s;
     dst = ds_total + (size_t)b * (cap_s + cap_o);
-    keys = sort_s + (size_t)b * sort_cap_s; sort_cap = sort_cap_s;
+    keys = sort_s + (size_t)b * 2 * sort_cap_s; sort_cap = sort_cap_s;
     if (threadIdx.x == 0) lm_n[b * 8 + 3] = n;
   } else {
     src = lm_input(in, b, kind, &n);
-    if (kind == 0) { leaf = leaf_c; dst = ds_c + (size_t)b * cap_c; keys = sort_c + (size_t)b * sort_cap_c; sort_cap = sort_cap_c; n = min(n, cap_c); }
-    else if (kind == 1) { leaf = leaf_s; dst = ds_s + (size_t)b * cap_s; keys = sort_s + (size_t)b * sort_cap_s; sort_cap = sort_cap_s; n = min(n, cap_s); }
-    else { leaf = leaf_o; dst = ds_o + (size_t)b * cap_o; keys = sort_o + (size_t)b * sort_cap_o; sort_cap = sort_cap_o; n = min(n, cap_o); }
+    if (kind == 0) { leaf = leaf_c; dst = ds_c + (size_t)b * cap_c; keys = sort_c + (size_t)b * 2 * sort_cap_c; sort_cap = sort_cap_c; n = min(n, cap_c); }
+    else if (kind == 1) { leaf = leaf_s; dst = ds_s + (size_t)b * cap_s; keys = sort_s + (size_t)b * 2 * sort_cap_s; sort_cap = sort_cap_s; n = min(n, cap_s); }
+    else { leaf = leaf_o; dst = ds_o + (size_t)b * cap_o; keys = sort_o + (size_t)b * 2 * sort_cap_o; sort_cap = sort_cap_o; n = min(n, cap_o); }
   }
   n = min(n, sort_cap);
-  int npad = 1;
-  while (npad < n) npad <<= 1;
-  const int n_out = block_voxel_grid(src, n, leaf, keys, npad, false, stage, LMV_STAGE, dst, redf, redi, &frame);
+  // ping-pong key buffers [2][sort_cap] in global memory (L2 resident), digit counters in shared memory
+  const int n_out = block_voxel_grid<int>(src, n, leaf, keys, keys + sort_cap, lmv_smem, dst, redf, redi, &frame);
   if (threadIdx.x == 0) lm_n[b * 8 + (kind == 3 ? 4 : kind)] = n_out;
 }
 
 // stand-alone VoxelGrid of one device cloud (alego_voxel_grid)
 __global__ void __launch_bounds__(LMV_THREADS)
-voxel_single_kernel(const float4 *src, int n, float leaf, float4 *dst, u64 *keys, int npad, int *n_out) {
+voxel_single_kernel(const float4 *src, int n, float leaf, float4 *dst, u64 *keys, int *n_out) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
-  u64 *stage = reinterpret_cast<u64 *>(lmv_smem);
   __shared__ float redf[6 * 32 + 8];
   __shared__ int redi[48];
   __shared__ VoxFrame frame;
-  const int m = block_voxel_grid(src, n, leaf, keys, npad, false, stage, LMV_STAGE, dst, redf, redi, &frame);
+  const int m = block_voxel_grid<int>(src, n, leaf, keys, keys + n, lmv_smem, dst, redf, redi, &frame);
   if (threadIdx.x == 0) *n_out = m;
 }
 
@@ -249,42 +246,46 @@ __device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, fl
 #pragma unroll
   for (int t = 0; t < 5; ++t) { bd[t] = 3.402823466e+38f; bi[t] = 0x7fffffff; }
   int found = 0;
-  int r1s[9], r1e[9], r2s[9], r2e[9];
+#pragma unroll 1
+  for (int lz = 0; lz < 3; ++lz) {  // one z layer at a time: 3 columns = up to 12 independent bound loads in flight
+    const int iz = cz + lz - 1;
+    int r1s[3], r1e[3], r2s[3], r2e[3];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) {
-    const int iy = cy + c % 3 - 1, iz = cz + c / 3 - 1;
-    const int h0 = grid_hash(cx - 1, iy, iz, T), h1 = grid_hash(cx, iy, iz, T), h2 = grid_hash(cx + 1, iy, iz, T);
-    r1s[c] = cs[h0];
-    r2e[c] = cs[h2 + 1];
-    if (h2 == h0 + 2) {          // one block: [h0, h2] contiguous
-      r1e[c] = r2e[c];
-      r2s[c] = r2e[c];
-    } else if (h1 == h0 + 1) {   // {cx-1, cx} | {cx+1}
-      r1e[c] = cs[h1 + 1];
-      r2s[c] = cs[h2];
-    } else {                     // {cx-1} | {cx, cx+1}
-      r1e[c] = cs[h0 + 1];
-      r2s[c] = cs[h1];
+    for (int c = 0; c < 3; ++c) {
+      const int iy = cy + c - 1;
+      const int h0 = grid_hash(cx - 1, iy, iz, T), h1 = grid_hash(cx, iy, iz, T), h2 = grid_hash(cx + 1, iy, iz, T);
+      r1s[c] = cs[h0];
+      r2e[c] = cs[h2 + 1];
+      if (h2 == h0 + 2) {          // one block: [h0, h2] contiguous
+        r1e[c] = r2e[c];
+        r2s[c] = r2e[c];
+      } else if (h1 == h0 + 1) {   // {cx-1, cx} | {cx+1}
+        r1e[c] = cs[h1 + 1];
+        r2s[c] = cs[h2];
+      } else {                     // {cx-1} | {cx, cx+1}
+        r1e[c] = cs[h0 + 1];
+        r2s[c] = cs[h1];
+      }
     }
-  }
 #pragma unroll
-  for (int c = 0; c < 9; ++c) {
-    for (int t = r1s[c]; t < r1e[c]; ++t) {
-      const float4 p = sp[t];
-      const float d = l2_simple(qx, qy, qz, p);
-      if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
-    }
-    for (int t = r2s[c]; t < r2e[c]; ++t) {
-      const float4 p = sp[t];
-      const float d = l2_simple(qx, qy, qz, p);
-      if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
+    for (int c = 0; c < 3; ++c) {
+      for (int t = r1s[c]; t < r1e[c]; ++t) {
+        const float4 p = sp[t];
+        const float d = l2_simple(qx, qy, qz, p);
+        if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
+      }
+      for (int t = r2s[c]; t < r2e[c]; ++t) {
+        const float4 p = sp[t];
+        const float d = l2_simple(qx, qy, qz, p);
+        if (d < 1.0f) knn5_offer(d, __float_as_int(p.w), bd, bi, found);
+      }
     }
   }
   return found < 5 ? found : 5;
 }
 
 // K14a/K15a: per query — pointAssociateToMap, exact gated 5-NN; writes the 5 map indices (nn[0] = -1: no residual)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 lm_knn_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, GridIndex g,
               const Pose *__restrict__ m2l, const int *__restrict__ guard, int *__restrict__ nn) {
   const int b = blockIdx.y;
@@ -501,19 +502,19 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEven
   { LAUNCH(h, "lm_prepare"); lm_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_use_ext, h->t_w, h->r_w, h->o2l, h->m2o, h->m2l, B); }
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(lm_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LMV_STAGE * 8));
+    CUDA_TRY(h, cudaFuncSetAttribute(lm_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
     attr_set = true;
   }
   const int cs = h->ds_cap_s, cc = h->ds_cap_c, co = h->ds_cap_o;
-  u64 *sort_c = h->vox_sort, *sort_s = sort_c + (size_t)B * next_pow2(cc), *sort_o = sort_s + (size_t)B * next_pow2(cs + co);
+  u64 *sort_c = h->vox_sort, *sort_s = sort_c + (size_t)B * 2 * cc, *sort_o = sort_s + (size_t)B * 2 * (cs + co);
   { LAUNCH(h, "lm_voxel_3");
-    lm_voxel_kernel<<<dim3(B, 3), LMV_THREADS, LMV_STAGE * 8, s>>>(in, 0, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
+    lm_voxel_kernel<<<dim3(B, 3), LMV_THREADS, LMV_SMEM, s>>>(in, 0, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
         (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
-        h->lm_n, sort_c, sort_s, sort_o, next_pow2(cc), next_pow2(cs + co), next_pow2(co)); }
+        h->lm_n, sort_c, sort_s, sort_o, cc, cs + co, co); }
   { LAUNCH(h, "lm_voxel_total");
-    lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_STAGE * 8, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
+    lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_SMEM, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
         (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
-        h->lm_n, sort_c, sort_s, sort_o, next_pow2(cc), next_pow2(cs + co), next_pow2(co)); }
+        h->lm_n, sort_c, sort_s, sort_o, cc, cs + co, co); }
   if (map_index_event) {  // built concurrently on the side stream (alego_pipeline_step)
     CUDA_TRY(h, cudaStreamWaitEvent(s, map_index_event, 0));
   } else if (h->rebuild_map_every_step || !h->map_index_valid) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
@@ -562,7 +563,7 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
   CUDA_TRY(h, cudaMalloc(&h->lm_plane, (size_t)B * (want_s + want_o) * 8 * sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&h->lm_nn_c, (size_t)B * want_c * 5 * sizeof(int)));
   CUDA_TRY(h, cudaMalloc(&h->lm_nn_s, (size_t)B * (want_s + want_o) * 5 * sizeof(int)));
-  const size_t sort_elems = (size_t)B * ((size_t)next_pow2(want_c) + next_pow2(want_s + want_o) + next_pow2(want_o));
+  const size_t sort_elems = (size_t)B * 2 * ((size_t)want_c + (size_t)(want_s + want_o) + (size_t)want_o);  // ping-pong per cloud
   CUDA_TRY(h, cudaMalloc(&h->vox_sort, sort_elems * sizeof(u64)));
   return ALEGO_OK;
 }
@@ -570,17 +571,16 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
 int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float *out_xyzi, int *n_out) {
   cudaStream_t s = h->stream;
   if (n == 0) { *n_out = 0; return ALEGO_OK; }
-  const int npad = next_pow2(n);
   float4 *d_in = nullptr, *d_out = nullptr;
   u64 *d_keys = nullptr;
   int *d_n = nullptr;
   CUDA_TRY(h, cudaMalloc(&d_in, (size_t)n * sizeof(float4)));
   CUDA_TRY(h, cudaMalloc(&d_out, (size_t)n * sizeof(float4)));
-  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)npad * sizeof(u64)));
+  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)2 * n * sizeof(u64)));
   CUDA_TRY(h, cudaMalloc(&d_n, sizeof(int)));
   CUDA_TRY(h, cudaMemcpyAsync(d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LMV_STAGE * 8));
-  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_STAGE * 8, s>>>(d_in, n, leaf, d_out, d_keys, npad, d_n); }
+  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
+  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM, s>>>(d_in, n, leaf, d_out, d_keys, d_n); }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(n_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));

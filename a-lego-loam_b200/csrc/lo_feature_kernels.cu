@@ -325,10 +325,12 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
 __global__ void __launch_bounds__(LFV_THREADS)
 lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ flabel, const int *__restrict__ start_ring,
                           const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt, int R,
-                          int RC, int pts_cap, int key_cap, float leaf) {
+                          int RC, int pts_cap, float leaf) {
   extern __shared__ __align__(16) uint8_t lfv_smem[];
   float4 *pts = reinterpret_cast<float4 *>(lfv_smem);
-  u64 *keys = reinterpret_cast<u64 *>(lfv_smem + (size_t)pts_cap * sizeof(float4));
+  u64 *keys_a = reinterpret_cast<u64 *>(lfv_smem + (size_t)pts_cap * sizeof(float4));
+  u64 *keys_b = keys_a + pts_cap;
+  void *scratch = keys_b + pts_cap;
   __shared__ float redf[48];
   __shared__ int redi[48];
   __shared__ VoxFrame frame;
@@ -360,11 +362,8 @@ lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__res
   }
   __syncthreads();
   n = min(n, pts_cap);
-  int npad = 1;
-  while (npad < n) npad <<= 1;
-  npad = min(npad, key_cap);
   const int lo = max(start - 5, 0);
-  const int n_out = block_voxel_grid(pts, n, leaf, keys, npad, true, nullptr, 0, lf_stage + base + lo, redf, redi, &frame);
+  const int n_out = block_voxel_grid<unsigned short>(pts, n, leaf, keys_a, keys_b, scratch, lf_stage + base + lo, redf, redi, &frame);
   if (threadIdx.x == 0) ring_feat_cnt[br * 4 + 3] = n_out;
 }
 
@@ -444,8 +443,8 @@ int lo_extract_device(AlegoHandle *h) {
     lo_select_kernel<<<dim3(div_up(R, SEL_WARPS), B), SEL_WARPS * 32, (size_t)SEL_WARPS * pkcap, s>>>(
         h->seg_col, h->seg_ground, h->curv, h->sort_idx, h->start_ring, h->end_ring, h->picked0, h->picked, h->flabel,
         h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, R, RC, pkcap); }
-  const int pts_cap = C, key_cap = next_pow2(C);
-  const size_t lfv_smem = (size_t)pts_cap * sizeof(float4) + (size_t)key_cap * sizeof(u64);
+  const int pts_cap = C;  // a ring holds at most C points (< 65536: 16-bit radix counters)
+  const size_t lfv_smem = (size_t)pts_cap * (sizeof(float4) + 2 * sizeof(u64)) + radix_scratch_bytes<unsigned short>(LFV_THREADS);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(lo_less_flat_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -453,7 +452,7 @@ int lo_extract_device(AlegoHandle *h) {
   }
   { LAUNCH(h, "lo_less_flat_voxel");
     lo_less_flat_voxel_kernel<<<dim3(R, B), LFV_THREADS, lfv_smem, s>>>(h->seg_cloud, h->flabel, h->start_ring, h->end_ring,
-                                                                       h->lf_stage, h->ring_feat_cnt, R, RC, pts_cap, key_cap,
+                                                                       h->lf_stage, h->ring_feat_cnt, R, RC, pts_cap,
                                                                        (float)h->P.less_flat_leaf); }
   const int cur = h->cur;
   { LAUNCH(h, "lo_finalize");

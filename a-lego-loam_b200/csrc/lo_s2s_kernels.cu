@@ -84,59 +84,6 @@ __device__ __forceinline__ double sqdist_walk(const float4 &p, float sx, float s
   return dx * dx + dy * dy + dz * dz;
 }
 
-// The reference finds the 2nd (and 3rd) point by walking the ring-ordered last cloud forwards and backwards from the
-// nearest neighbour over the rings cs-2..cs+2 (:348-395, :439-470), keeping the first strict minimum of the double
-// squared distance below the 25 m^2 gate per class.  The result is the minimum over a fixed candidate set with ties
-// resolved by walk position, so it can be searched through the grid instead of linearly: shells of cells are examined
-// until both minima lie strictly inside the covered radius or the gate radius is exhausted; every candidate carries its
-// ring id in the grid entry and its walk position follows from its index.
-template <bool SURF>
-__device__ void warp_ring_search(const GridIndex &g, int b, float sx, float sy, float sz, int closest, int cs, int nf, double gate,
-                                 WalkMin &m2, WalkMin &m3) {
-  const int lane = threadIdx.x & 31;
-  const int T = g.table_size;
-  const int *cst = g.cell_start + (size_t)b * (T + 4);
-  const float4 *sp = g.sorted + (size_t)b * g.cap;
-  const float inv = 1.0f / g.cell;
-  const int cx = grid_coord(sx, inv), cy = grid_coord(sy, inv), cz = grid_coord(sz, inv);
-  const int max_shell = (int)ceilf(sqrtf((float)gate) / g.cell);
-  for (int r = 0; r <= max_shell; ++r) {
-    const int side = 2 * r + 1, total = side * side * side;
-    for (int c = lane; c < total; c += 32) {
-      const int dz = c / (side * side) - r, rem = c % (side * side), dy = rem / side - r, dx = rem % side - r;
-      if (max(abs(dx), max(abs(dy), abs(dz))) != r) continue;  // only the new shell
-      const int hsh = grid_hash(cx + dx, cy + dy, cz + dz, T);
-      const int e = cst[hsh + 1];
-      for (int t = cst[hsh]; t < e; ++t) {
-        const float4 p = sp[t];
-        const int tag = __float_as_int(p.w);
-        const int k = tag & GRID_INDEX_MASK, ring = tag >> GRID_RING_SHIFT;
-        if (k == closest || ring < cs - 2 || ring > cs + 2) continue;
-        const double pd = sqdist_walk(p, sx, sy, sz);
-        const int pos = k > closest ? k - closest - 1 : nf + (closest - 1 - k);  // position in the reference's walk
-        const bool same = ring == cs;
-        if (SURF) {
-          WalkMin &m = same ? m2 : m3;
-          if (pd < m.d || (pd == m.d && pos < m.pos)) { m.d = pd; m.pos = pos; m.k = k; }
-        } else if (!same) {
-          if (pd < m2.d || (pd == m2.d && pos < m2.pos)) { m2.d = pd; m2.pos = pos; m2.k = k; }
-        }
-      }
-    }
-    // every point not examined yet is strictly farther than r * cell from the query
-    const double covered = (double)((float)r * g.cell) * (double)((float)r * g.cell);
-    const WalkMin a2 = warp_min_walk(m2);
-    bool done = a2.k >= 0 && a2.d < covered;
-    if (SURF) {
-      const WalkMin a3 = warp_min_walk(m3);
-      done = done && a3.k >= 0 && a3.d < covered;
-    }
-    if (done) break;
-  }
-  m2 = warp_min_walk(m2);
-  if (SURF) m3 = warp_min_walk(m3);
-}
-
 #define ASSOC_WARPS 8
 template <bool SURF>
 __global__ void __launch_bounds__(ASSOC_WARPS * 32)
@@ -168,11 +115,38 @@ lo_assoc_kernel(const float4 *__restrict__ feat, int feat_stride, const int *__r
   }
   const int closest = nn.i;
   const int cs = (int)L[closest].w;  // ring id = int(intensity) (:347, :436)
-  // rings cs-2 .. cs+2 take part (break at int(intensity) > cs+2.5 / < cs-2.5, resp. > cs+2 / < cs-2)
-  const int fwd_end = ro[min(max(cs + 3, 0), R)];
-  const int nf = max(fwd_end - (closest + 1), 0);  // length of the forward walk: positions of the backward walk follow it
   WalkMin m2{gate, 0x7fffffff, -1}, m3{gate, 0x7fffffff, -1};
-  warp_ring_search<SURF>(g, b, sx, sy, sz, closest, cs, nf, gate, m2, m3);
+  // rings cs-2 .. cs+2 take part (break at int(intensity) > cs+2.5 / < cs-2.5, resp. > cs+2 / < cs-2)
+  const int fwd_end = ro[min(cs + 3, R)];
+  const int bwd_begin = ro[max(cs - 2, 0)];
+  const int same_lo = ro[min(max(cs, 0), R)], same_hi = ro[min(max(cs + 1, 0), R)];
+  const int nf = max(fwd_end - (closest + 1), 0);
+  for (int t = lane; t < nf; t += 32) {  // forward sweep (:348-371, :439-454)
+    const int k = closest + 1 + t;
+    const double pd = sqdist_walk(L[k], sx, sy, sz);
+    const bool same = k >= same_lo && k < same_hi;
+    if (SURF) {
+      WalkMin &m = same ? m2 : m3;
+      if (pd < m.d || (pd == m.d && t < m.pos)) { m.d = pd; m.pos = t; m.k = k; }
+    } else if (k >= same_hi) {  // ring > closest_scan only
+      if (pd < m2.d || (pd == m2.d && t < m2.pos)) { m2.d = pd; m2.pos = t; m2.k = k; }
+    }
+  }
+  const int nb = max(closest - bwd_begin, 0);
+  for (int t = lane; t < nb; t += 32) {  // backward sweep (:372-395, :455-470)
+    const int k = closest - 1 - t;
+    const double pd = sqdist_walk(L[k], sx, sy, sz);
+    const bool same = k >= same_lo && k < same_hi;
+    const int pos = nf + t;
+    if (SURF) {
+      WalkMin &m = same ? m2 : m3;
+      if (pd < m.d || (pd == m.d && pos < m.pos)) { m.d = pd; m.pos = pos; m.k = k; }
+    } else if (k < same_lo) {  // ring < closest_scan only
+      if (pd < m2.d || (pd == m2.d && pos < m2.pos)) { m2.d = pd; m2.pos = pos; m2.k = k; }
+    }
+  }
+  m2 = warp_min_walk(m2);
+  if (SURF) m3 = warp_min_walk(m3);
   if (lane == 0) {
     const bool ok = m2.k >= 0 && (!SURF || m3.k >= 0);
     co[0] = q;
@@ -329,9 +303,9 @@ int lo_scan2scan_device(AlegoHandle *h) {
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
                                       h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub); }
   // the current clouds become the targets of the next sweep (:531-534): index them, then flip the buffers
-  int rc = grid_build(h, &h->g_surf_last, h->less_flat[cur], (size_t)RC, h->lf_ring_off[cur] + R, R + 1, "surf_last", true);
+  int rc = grid_build(h, &h->g_surf_last, h->less_flat[cur], (size_t)RC, h->lf_ring_off[cur] + R, R + 1, "surf_last");
   if (rc != ALEGO_OK) return rc;
-  rc = grid_build(h, &h->g_corner_last, h->less_sharp[cur], (size_t)R * 120, h->ls_ring_off[cur] + R, R + 1, "corner_last", true);
+  rc = grid_build(h, &h->g_corner_last, h->less_sharp[cur], (size_t)R * 120, h->ls_ring_off[cur] + R, R + 1, "corner_last");
   if (rc != ALEGO_OK) return rc;
   h->cur = prev;
   CUDA_TRY(h, cudaGetLastError());

@@ -150,23 +150,6 @@ __device__ void lm_eval_full(const RS &rs, const double *x, double huber_a, LmSh
   lm_block_reduce(acc, LM_NACC, sh);
 }
 
-template <class RS>
-__device__ double lm_eval_cost(const RS &rs, const double *x, double huber_a, LmShared *sh) {
-  const PoseTrig T(x);
-  double acc[1] = {0};
-  const int n = rs.slots();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int kind;
-    double cpt[3], a[3], b[3], c[3], d;
-    if (!rs.load(i, kind, cpt, a, b, c, d)) continue;
-    double r, w;
-    eval_resid_dev(kind, cpt, a, b, c, d, x, T, &r, nullptr);
-    acc[0] += 0.5 * huber(r, huber_a, &w);
-  }
-  lm_block_reduce(acc, 1, sh);
-  return sh->acc[0];
-}
-
 // in-place Cholesky solve of the symmetric positive definite 6x6 system A s = g; false if not SPD
 __device__ __forceinline__ bool chol6_solve(double A[6][6], const double *g, double *s) {
   for (int i = 0; i < 6; ++i) {
@@ -293,7 +276,11 @@ __device__ LmResult block_lm_solve(const RS &rs, double *x_io, int max_iters, do
     int flag = sh->flag;
     if (flag == LM_FLAG_STOP) break;
     if (flag == LM_FLAG_INVALID) { __syncthreads(); continue; }
-    const double cand = lm_eval_cost(rs, sh->xc, huber_a, sh);
+    // Residuals AND Jacobian at the candidate in one pass: ceres evaluates the cost at the candidate and, when the step
+    // is accepted, the Jacobian at the same point — accepted steps are the common case, so the second pass over the
+    // residuals is saved (the cost of this pass is bit-identical to a cost-only pass: same sums in the same order).
+    lm_eval_full(rs, sh->xc, huber_a, sh);
+    const double cand = sh->acc[27];
     if (threadIdx.x == 0) {
       double step_norm = 0;
       for (int q = 0; q < 6; ++q) step_norm += (sh->x[q] - sh->xc[q]) * (sh->x[q] - sh->xc[q]);
@@ -329,8 +316,7 @@ __device__ LmResult block_lm_solve(const RS &rs, double *x_io, int max_iters, do
     flag = sh->flag;
     if (flag == LM_FLAG_STOP) break;
     if (flag == LM_FLAG_ACCEPT) {
-      lm_eval_full(rs, sh->x, huber_a, sh);
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0) {  // sh->acc still holds the normal equations of the accepted point
         cost = sh->acc[27];
         unpack();
         push_trace(cost);
