@@ -419,7 +419,7 @@ int alego_ip_get(AlegoHandle *h, int seq, AlegoCloudInfo *info, float *segmented
   if (outlier_xyzi && (rc = d2h(h, outlier_xyzi, h->outlier + (size_t)seq * h->out_cap, (size_t)no * sizeof(float4))) != ALEGO_OK) return rc;
   if (n_outlier) *n_outlier = no;
   if (label_image) {
-    if (!h->want_labels) { h->err = "label image disabled"; return ALEGO_NOT_READY; }
+    if ((rc = ip_label_device(h)) != ALEGO_OK) return rc;
     if ((rc = d2h(h, label_image, h->label + base, (size_t)h->RC * sizeof(int))) != ALEGO_OK) return rc;
   }
   return ALEGO_OK;
@@ -632,7 +632,7 @@ int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_ev
 }
 
 // IP -> LO -> LM on whatever h->raw / h->n_pts point at; everything is enqueued, nothing waits.
-static int pipeline_enqueue(AlegoHandle *h) {
+static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   int rc;
   bool any_ext = false;
   for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
@@ -655,6 +655,8 @@ static int pipeline_enqueue(AlegoHandle *h) {
     map_ev = h->ev_join;
   }
   if ((rc = alego_ip_run(h)) != ALEGO_OK) return rc;
+  // ImageProjection is the only reader of the raw sweep: its staging buffer may be refilled from here on
+  if (consumed_ev) CUDA_TRY(h, cudaEventRecord(consumed_ev, h->stream));
   if ((rc = alego_lo_extract(h)) != ALEGO_OK) return rc;
   if ((rc = lo_scan2scan_device(h)) != ALEGO_OK) return rc;
   h->stage_feat_done = false;
@@ -712,8 +714,7 @@ int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t 
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
   h->raw = h->raw_slot[slot];
   h->n_pts = h->n_pts_slot[slot];
-  if ((rc = pipeline_enqueue(h)) != ALEGO_OK) return rc;
-  CUDA_TRY(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
+  if ((rc = pipeline_enqueue(h, h->ev_consumed[slot])) != ALEGO_OK) return rc;
   h->consumed_valid[slot] = true;
   CUDA_TRY(h, cudaMemcpyAsync(h->h_pose_slot[slot], h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_pose[slot], h->stream));
@@ -795,7 +796,11 @@ int64_t alego_debug_get(AlegoHandle *h, const char *name, int seq, void *dst, si
   if (s == "range_mat") { src = h->range + base; bytes = RC * 4; }
   else if (s == "full_cloud") { src = h->cloud + base; bytes = RC * 16; }
   else if (s == "ground_mat") { src = h->ground + base; bytes = RC; }
-  else if (s == "label_mat") { src = h->label + base; bytes = RC * 4; }
+  else if (s == "label_mat") {
+    if (!h->stage_ip_done) return ALEGO_NOT_READY;
+    if (ip_label_device(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
+    src = h->label + base; bytes = RC * 4;
+  }
   else if (s == "startRingIndex") { src = h->start_ring + seq * R; bytes = R * 4; }
   else if (s == "endRingIndex") { src = h->end_ring + seq * R; bytes = R * 4; }
   else if (s == "segmentedCloudGroundFlag") { src = h->seg_ground + base; bytes = M; }

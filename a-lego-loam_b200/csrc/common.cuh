@@ -58,7 +58,8 @@ struct AlegoHandle {
   int lm_every = 1;
   bool rebuild_map_every_step = true;
   bool stage_ip_done = false, stage_feat_done = false;
-  bool want_labels = true;  // materialise label_mat_ (imageProjection.h:25) every sweep
+  bool want_labels = false;  // materialise label_mat_ (imageProjection.h:25) on every sweep instead of on demand
+  bool label_valid = false;  // h->label matches the last ImageProjection pass
   int feat_buf = -1;        // buffer index holding the most recent feature clouds
   std::vector<uint8_t> lm_scan_is_external;  // per seq: inputs set through alego_lm_set_scan
 

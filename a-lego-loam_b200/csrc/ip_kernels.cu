@@ -21,16 +21,15 @@ namespace {
 // cell coordinate is > 2e-3 away from an integer (their error is < 3e-4 cell); otherwise the slow path
 // recomputes with correctly rounded float results obtained through double precision.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool near_integer(double v, double eps) {
-  const double f = v - floor(v);
-  return f < eps || f > 1.0 - eps;
-}
+__device__ __forceinline__ bool near_integer(double v, double eps) { return fabs(v - rint(v)) < eps; }
 
-__device__ bool project_rowcol(float x, float y, float z, const IpDev &P, int &row, int &col) {
-  // ---- row (imageProjection.cpp:79-85)
+__device__ __forceinline__ bool project_rowcol(float x, float y, float z, const IpDev &P, int &row, int &col) {
+  // ---- row (imageProjection.cpp:79-85).  Fast path: the float angle scaled by one precomputed double factor (the
+  // reference's two double divisions only matter within ~1e-13 of a cell boundary; anything within 2e-3 goes to the
+  // exact path below).
   float hyp = sqrtf(x * x + y * y);
   float va = atan2f(z, hyp);
-  double row_f = ((double)va * 180.0 / CUDART_PI + P.ang_bottom) / P.ang_res_y + 0.5;
+  double row_f = (double)va * P.row_scale + P.row_off;
   if (!(row_f > -1.0e6 && row_f < 1.0e6)) return false;
   if (near_integer(row_f, 2e-3)) {
     hyp = (float)sqrt((double)x * (double)x + (double)y * (double)y);
@@ -41,7 +40,7 @@ __device__ bool project_rowcol(float x, float y, float z, const IpDev &P, int &r
   if (row < 0 || row >= P.R) return false;
   // ---- column (:87-97)
   float ha = atan2f(y, x);
-  double col_f = (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
+  double col_f = (2 * CUDART_PI - (double)ha) * P.col_scale;
   if (near_integer(col_f, 2e-3)) {
     ha = (float)atan2((double)y, (double)x);
     col_f = (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
@@ -435,6 +434,9 @@ IpDev make_ip_dev(const AlegoHandle *h) {
   d.ang_res_x = h->P.ang_res_x; d.ang_res_y = h->P.ang_res_y; d.ang_bottom = h->P.ang_bottom;
   d.sensor_mount_ang = h->P.sensor_mount_ang;
   d.seg_theta = h->P.seg_theta;
+  d.row_scale = 180.0 / M_PI / h->P.ang_res_y;
+  d.row_off = h->P.ang_bottom / h->P.ang_res_y + 0.5;
+  d.col_scale = 180.0 / M_PI / h->P.ang_res_x;
   d.sin_x = h->seg_sin_x; d.cos_x = h->seg_cos_x; d.sin_y = h->seg_sin_y; d.cos_y = h->seg_cos_y;
   return d;
 }
@@ -465,10 +467,21 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
     ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,
                                                   h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring,
                                                   h->end_ring, h->M, h->outlier, h->n_outlier, h->out_cap, P); }
-  if (want_labels) {
-    LAUNCH(h, "ip_label");
-    ip_label_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, h->comp_id, h->label, P);
-  }
+  h->label_valid = false;
+  if (want_labels) return ip_label_device(h);
   CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}
+
+// label_mat_ (imageProjection.h:25) is internal to pcCB — nothing downstream reads it — so it is materialised from the
+// component forest only when a caller asks for it (alego_ip_get(label_image), tests).
+int ip_label_device(AlegoHandle *h) {
+  if (h->label_valid) return ALEGO_OK;
+  const IpDev P = make_ip_dev(h);
+  const int cell_blocks = min(div_up(h->RC, 256), 4096);
+  { LAUNCH(h, "ip_label");
+    ip_label_kernel<<<dim3(cell_blocks, h->B), 256, 0, h->stream>>>(h->parent, h->comp_stat, h->comp_id, h->label, P); }
+  CUDA_TRY(h, cudaGetLastError());
+  h->label_valid = true;
   return ALEGO_OK;
 }

@@ -40,11 +40,11 @@ __device__ Best warp_nearest(const GridIndex &g, int b, float qx, float qy, floa
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);
   Best best{3.402823466e+38f, 0x7fffffff};
-  for (int r = 0; r <= max_shell; ++r) {
+  for (int r = 1; r <= max(max_shell, 1); ++r) {
     const int side = 2 * r + 1, total = side * side * side;
     for (int c = lane; c < total; c += 32) {
       const int dz = c / (side * side) - r, rem = c % (side * side), dy = rem / side - r, dx = rem % side - r;
-      if (max(abs(dx), max(abs(dy), abs(dz))) != r) continue;  // only the new shell
+      if (r > 1 && max(abs(dx), max(abs(dy), abs(dz))) != r) continue;  // only the new shell (the first pass takes the whole 3x3x3 cube)
       const int hsh = grid_hash(cx + dx, cy + dy, cz + dz, T);
       const int e = cs[hsh + 1];
       for (int t = cs[hsh]; t < e; ++t) {
@@ -115,36 +115,45 @@ lo_assoc_kernel(const float4 *__restrict__ feat, int feat_stride, const int *__r
   }
   const int closest = nn.i;
   const int cs = (int)L[closest].w;  // ring id = int(intensity) (:347, :436)
-  WalkMin m2{gate, 0x7fffffff, -1}, m3{gate, 0x7fffffff, -1};
-  // rings cs-2 .. cs+2 take part (break at int(intensity) > cs+2.5 / < cs-2.5, resp. > cs+2 / < cs-2)
+  // rings cs-2 .. cs+2 take part (break at int(intensity) > cs+2.5 / < cs-2.5, resp. > cs+2 / < cs-2).  The cloud is ring
+  // ordered, so the sequential walks decompose into contiguous index ranges: same ring above / below `closest` (surf:
+  // min_idx2) and the neighbouring rings above / below (surf: min_idx3, corner: min_idx2).  A lane meets its candidates
+  // in walk order, so the reference's strict `point_dist < min_dist` keeps the earliest of equal distances inside the
+  // lane; the walk position only enters the cross-lane reduction.
   const int fwd_end = ro[min(cs + 3, R)];
   const int bwd_begin = ro[max(cs - 2, 0)];
   const int same_lo = ro[min(max(cs, 0), R)], same_hi = ro[min(max(cs + 1, 0), R)];
   const int nf = max(fwd_end - (closest + 1), 0);
-  for (int t = lane; t < nf; t += 32) {  // forward sweep (:348-371, :439-454)
-    const int k = closest + 1 + t;
-    const double pd = sqdist_walk(L[k], sx, sy, sz);
-    const bool same = k >= same_lo && k < same_hi;
-    if (SURF) {
-      WalkMin &m = same ? m2 : m3;
-      if (pd < m.d || (pd == m.d && t < m.pos)) { m.d = pd; m.pos = t; m.k = k; }
-    } else if (k >= same_hi) {  // ring > closest_scan only
-      if (pd < m2.d || (pd == m2.d && t < m2.pos)) { m2.d = pd; m2.pos = t; m2.k = k; }
+  double d2 = gate, d3 = gate;
+  int k2 = -1, k3 = -1;
+  if (SURF) {
+#pragma unroll 4
+    for (int k = closest + 1 + lane; k < same_hi; k += 32) {  // forward, same ring (:348-371)
+      const double pd = sqdist_walk(L[k], sx, sy, sz);
+      if (pd < d2) { d2 = pd; k2 = k; }
+    }
+#pragma unroll 4
+    for (int k = closest - 1 - lane; k >= same_lo; k -= 32) {  // backward, same ring (:372-395)
+      const double pd = sqdist_walk(L[k], sx, sy, sz);
+      if (pd < d2) { d2 = pd; k2 = k; }
     }
   }
-  const int nb = max(closest - bwd_begin, 0);
-  for (int t = lane; t < nb; t += 32) {  // backward sweep (:372-395, :455-470)
-    const int k = closest - 1 - t;
-    const double pd = sqdist_walk(L[k], sx, sy, sz);
-    const bool same = k >= same_lo && k < same_hi;
-    const int pos = nf + t;
-    if (SURF) {
-      WalkMin &m = same ? m2 : m3;
-      if (pd < m.d || (pd == m.d && pos < m.pos)) { m.d = pd; m.pos = pos; m.k = k; }
-    } else if (k < same_lo) {  // ring < closest_scan only
-      if (pd < m2.d || (pd == m2.d && pos < m2.pos)) { m2.d = pd; m2.pos = pos; m2.k = k; }
+  {
+    double &dn = SURF ? d3 : d2;
+    int &kn = SURF ? k3 : k2;
+#pragma unroll 4
+    for (int k = max(closest + 1, same_hi) + lane; k < fwd_end; k += 32) {  // forward, rings above (:439-454)
+      const double pd = sqdist_walk(L[k], sx, sy, sz);
+      if (pd < dn) { dn = pd; kn = k; }
+    }
+#pragma unroll 4
+    for (int k = min(closest - 1, same_lo - 1) - lane; k >= bwd_begin; k -= 32) {  // backward, rings below (:455-470)
+      const double pd = sqdist_walk(L[k], sx, sy, sz);
+      if (pd < dn) { dn = pd; kn = k; }
     }
   }
+  auto walk_pos = [&](int k) { return k < 0 ? 0x7fffffff : (k > closest ? k - closest - 1 : nf + closest - 1 - k); };
+  WalkMin m2{d2, walk_pos(k2), k2}, m3{d3, walk_pos(k3), k3};
   m2 = warp_min_walk(m2);
   if (SURF) m3 = warp_min_walk(m3);
   if (lane == 0) {

@@ -262,6 +262,21 @@ def main():
     launches = g.launch_count() - l0
     clocks = sampler.stop(t_wall0, t_wall1)
 
+    # H2D probe: what this box's PCIe link gives a plain pinned-memory copy of one step's sweeps (context for e2e, which is
+    # link-bound once the pass itself is faster than the copy)
+    probe_src = torch.empty(int(host[0].nbytes), dtype=torch.uint8).pin_memory()
+    probe_dst = torch.empty(int(host[0].nbytes), dtype=torch.uint8, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(4):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_probe_gbs = 4 * probe_src.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del probe_src, probe_dst
+
     # ---------------- pass B: end to end, host buffers in, poses out ----------------
     # alego_pipeline_submit / _collect: every sweep is copied from pinned HOST memory inside the timed region (on the copy
     # stream, overlapping the previous pass) and every step's poses are read back to the host
@@ -282,7 +297,8 @@ def main():
     ms_e2e_host = (time.perf_counter() - t_host0) * 1e3
     # device events on the compute stream bracket the region; the first H2D runs on the copy stream, so the (slightly
     # larger) host wall clock between the two synchronisation points is taken when it exceeds the event time
-    ms_e2e = max(g.timer_elapsed_ms(2, 3), ms_e2e_host)
+    ms_e2e_dev = g.timer_elapsed_ms(2, 3)
+    ms_e2e = max(ms_e2e_dev, ms_e2e_host)
 
     # ---------------- pass C: per-kernel CUDA events on the same workload ----------------
     fill(2 * n_steps)
@@ -340,7 +356,8 @@ def main():
                        "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 16 + B * 4), "d2h_bytes_per_step": B * 12 * 8,
-                    "ms_per_step": ms_e2e / K, "host_wall_ms_per_step": ms_e2e_host / K,
+                    "ms_per_step": ms_e2e / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
+                    "h2d_probe_gbs": round(h2d_probe_gbs, 1),
                     "api": "alego_pipeline_submit/_collect, pinned host sweeps, 2 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
