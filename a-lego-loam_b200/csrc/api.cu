@@ -150,8 +150,6 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   h->n_pts = h->n_pts_own;
   h->raw_slot[0] = h->raw_own;
   h->n_pts_slot[0] = h->n_pts_own;
-  DMALLOC(h, h->first_valid, B);
-  DMALLOC(h, h->last_valid, B);
   DMALLOC(h, h->winner, B * RC);
   DMALLOC(h, h->cloud, B * RC);
   DMALLOC(h, h->range, B * RC);
@@ -183,6 +181,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   DMALLOC(h, h->flabel, B * RC);
   DMALLOC(h, h->sort_idx, B * RC);
   DMALLOC(h, h->sort_scratch, B * RC);
+  DMALLOC(h, h->lfv_keys, B * RC);
   DMALLOC(h, h->ring_feat_cnt, B * R * 4);
   DMALLOC(h, h->ring_sharp, B * R * 12);
   DMALLOC(h, h->ring_less_sharp, B * R * 120);
@@ -276,9 +275,9 @@ void alego_destroy(AlegoHandle *h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto p : h->stage_raw) cudaFree(p);
   for (auto p : h->stage_n) cudaFree(p);
-  void *ptrs[] = {h->raw_own, h->n_pts_own, h->first_valid, h->last_valid, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
+  void *ptrs[] = {h->raw_own, h->n_pts_own, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
                   h->comp_id, h->label, h->rowcnt, h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring, h->end_ring,
-                  h->M, h->outlier, h->n_outlier, h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch,
+                  h->M, h->outlier, h->n_outlier, h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,
                   h->n_feat, h->sharp, h->flat, h->lf_stage, h->vox_sort, h->less_sharp[0], h->less_sharp[1], h->less_flat[0],
                   h->less_flat[1], h->ls_ring_off[0], h->ls_ring_off[1], h->lf_ring_off[0], h->lf_ring_off[1], h->lo_params, h->t_w,

@@ -76,8 +76,6 @@ struct AlegoHandle {
   int32_t *h_n_pts_slot[2] = {nullptr, nullptr};  // pinned copies of the caller's n_points
   std::vector<float4 *> stage_raw;  // sweeps pre-staged in HBM (alego_stage_*)
   std::vector<int *> stage_n;
-  int *first_valid = nullptr;  // [B]
-  int *last_valid = nullptr;   // [B]
   int *winner = nullptr;       // [B][RC]  index of the last input point that fell in the cell (-1 none)
   float4 *cloud = nullptr;     // [B][RC]  full_cloud_
   float *range = nullptr;      // [B][RC]  range_mat_ (f32 is lossless: the reference stores a float sqrt)
@@ -105,7 +103,8 @@ struct AlegoHandle {
   uint8_t *picked = nullptr;   // [B][RC]  ... after extractFeatures
   int *flabel = nullptr;       // [B][RC]  cloud_label_
   int *sort_idx = nullptr;     // [B][RC]  cloud_sort_idx_
-  unsigned long long *sort_scratch = nullptr;  // [B][RC]
+  unsigned long long *sort_scratch = nullptr;  // [B][RC]  sort words (segment sort slow path; less-flat voxel keys, buffer A)
+  unsigned long long *lfv_keys = nullptr;      // [B][RC]  less-flat voxel keys, buffer B
   int *ring_feat_cnt = nullptr;  // [B][R][4]  sharp, less_sharp, flat, less_flat_ds per ring
   int *ring_sharp = nullptr;     // [B][R][12]
   int *ring_less_sharp = nullptr;// [B][R][120]

@@ -21,62 +21,101 @@ namespace {
 // cell coordinate is > 2e-3 away from an integer (their error is < 3e-4 cell); otherwise the slow path
 // recomputes with correctly rounded float results obtained through double precision.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool near_integer(double v, double eps) { return fabs(v - rint(v)) < eps; }
+
+// atan2f for the fast path only: |error| < 1e-6 rad (degree-15 odd minimax polynomial on [0,1], 1.5e-7, plus the
+// approximate division and the quadrant folds).  Returns false for operands it does not cover (zero / denormal / huge).
+#define ALEGO_FAST_ATAN_ERR 1e-6
+__device__ __forceinline__ bool fast_atan2(float y, float x, float &r) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  if (!(mx > 1e-30f && mx < 1e30f)) return false;
+  const float t = __fdividef(mn, mx);
+  const float u = t * t;
+  float p = -0.00405456405133009f;
+  p = __fmaf_rn(p, u, 0.021862948313355446f);
+  p = __fmaf_rn(p, u, -0.055912312120199203f);
+  p = __fmaf_rn(p, u, 0.09642196446657181f);
+  p = __fmaf_rn(p, u, -0.1390862911939621f);
+  p = __fmaf_rn(p, u, 0.19946566224098206f);
+  p = __fmaf_rn(p, u, -0.33329859375953674f);
+  p = __fmaf_rn(p, u, 0.9999993443489075f);
+  float a = p * t;
+  if (ay > ax) a = 1.57079637f - a;
+  if (x < 0.f) a = 3.14159274f - a;
+  r = copysignf(a, y);
+  return true;
+}
+
+// Exact forms: what the reference evaluates (float atan2f / hypotf results, double scaling, :79-80, :87-88)
+__device__ __noinline__ double exact_row_f(float x, float y, float z, const IpDev &P) {
+  const float hyp = (float)sqrt((double)x * (double)x + (double)y * (double)y);
+  const float va = (float)atan2((double)z, (double)hyp);
+  return ((double)va * 180.0 / CUDART_PI + P.ang_bottom) / P.ang_res_y + 0.5;
+}
+__device__ __noinline__ double exact_col_f(float x, float y, const IpDev &P) {
+  const float ha = (float)atan2((double)y, (double)x);
+  return (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
+}
 
 __device__ __forceinline__ bool project_rowcol(float x, float y, float z, const IpDev &P, int &row, int &col) {
-  // ---- row (imageProjection.cpp:79-85).  Fast path: the float angle scaled by one precomputed double factor (the
-  // reference's two double divisions only matter within ~1e-13 of a cell boundary; anything within 2e-3 goes to the
-  // exact path below).
-  float hyp = sqrtf(x * x + y * y);
-  float va = atan2f(z, hyp);
-  double row_f = (double)va * P.row_scale + P.row_off;
-  if (!(row_f > -1.0e6 && row_f < 1.0e6)) return false;
-  if (near_integer(row_f, 2e-3)) {
-    hyp = (float)sqrt((double)x * (double)x + (double)y * (double)y);
-    va = (float)atan2((double)z, (double)hyp);
-    row_f = ((double)va * 180.0 / CUDART_PI + P.ang_bottom) / P.ang_res_y + 0.5;
+  // ---- row (imageProjection.cpp:79-85).  Fast path: approximate float angle scaled by one precomputed double factor;
+  // accepted only when the cell coordinate is farther from an integer than the fast path's error bound (P.eps_row /
+  // P.eps_col, >= 2e-3 cell), otherwise the exact form decides.
+  const float s2 = x * x + y * y;
+  const float hyp = s2 * rsqrtf(fmaxf(s2, 1e-30f));
+  float va = 0.f, ha = 0.f;
+  const bool fast_row = fast_atan2(z, hyp, va), fast_col = fast_atan2(y, x, ha);
+  // float cell coordinates: the float scaling adds < 1e-6 * |coordinate| to the angle error (covered by eps_row / eps_col)
+  const float row_ff = __fmaf_rn(va, P.row_scale_f, P.row_off_f);
+  const float col_ff = (6.283185307f - ha) * P.col_scale_f;
+  const bool row_sure = fast_row && fabsf(row_ff - rintf(row_ff)) >= P.eps_row && fabsf(row_ff) < 1.0e6f;
+  const bool col_sure = fast_col && fabsf(col_ff - rintf(col_ff)) >= P.eps_col;
+  if (row_sure) {
+    row = (int)row_ff;
+  } else {
+    const double row_f = exact_row_f(x, y, z, P);
+    if (!(row_f > -1.0e6 && row_f < 1.0e6)) return false;
+    row = (int)row_f;
   }
-  row = (int)row_f;
   if (row < 0 || row >= P.R) return false;
   // ---- column (:87-97)
-  float ha = atan2f(y, x);
-  double col_f = (2 * CUDART_PI - (double)ha) * P.col_scale;
-  if (near_integer(col_f, 2e-3)) {
-    ha = (float)atan2((double)y, (double)x);
-    col_f = (((double)(-ha) + 2 * CUDART_PI) * 180.0 / CUDART_PI) / P.ang_res_x;
-  }
-  col = (int)col_f;
+  col = col_sure ? (int)col_ff : (int)exact_col_f(x, y, P);
   if (col >= P.C) col -= P.C;
   if (col < 0 || col >= P.C) return false;
   return true;
 }
 
-__global__ void ip_reset_kernel(int *first_valid, int *last_valid, int B) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    first_valid[b] = 0x7fffffff;
-    last_valid[b] = -1;
-  }
-}
-
 __device__ __forceinline__ bool finite3(const float4 &p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
 
+// K1a.  A spinning sensor emits its points firing by firing: ring index fastest, azimuth slowest.  A warp that processed
+// 32 CONSECUTIVE points would therefore scatter its 32 winner updates over 32 image rows (32 L2 sectors per instruction,
+// measured as the limiter of this kernel).  Instead a CTA stages a tile of 32*R consecutive points in shared memory with
+// coalesced 16-byte loads and lane l of a warp then takes point  l*R + j  of the tile: for ring-fastest input the lanes
+// of one instruction hit consecutive columns of ONE row (4 sectors); for any other order the mapping is merely as
+// scattered as the naive one.  The staging rows are padded to R+1 points so the transposed reads are conflict free.
 __global__ void __launch_bounds__(256) ip_project_kernel(const float4 *__restrict__ raw, const int *__restrict__ n_pts,
-                                                         int *__restrict__ winner, int *first_valid, int *last_valid, int Nmax,
-                                                         IpDev P) {
+                                                         int *__restrict__ winner, int Nmax, IpDev P) {
+  extern __shared__ float4 s_tile[];  // [32][R+1]
   const int b = blockIdx.y;
   const int n = min(n_pts[b], Nmax);
   const float4 *src = raw + (size_t)b * Nmax;
   int *win = winner + (size_t)b * P.RC;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = ldg_f4(src + i);
-    if (!finite3(p)) continue;  // pcl::removeNaNFromPointCloud (:59)
-    // first / last valid point (orientation, :62-63): only run boundaries touch the atomics
-    if (i == 0 || !finite3(ldg_f4(src + i - 1))) atomicMin(first_valid + b, i);
-    if (i == n - 1 || !finite3(ldg_f4(src + i + 1))) atomicMax(last_valid + b, i);
-    int row, col;
-    if (!project_rowcol(p.x, p.y, p.z, P, row, col)) continue;
-    atomicMax(win + row * P.C + col, i);  // the later point of a cell wins (:103)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int tile_pts = 32 * P.R;
+  for (int tile = blockIdx.x * tile_pts; tile < n; tile += gridDim.x * tile_pts) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < tile_pts; t += blockDim.x)
+      if (tile + t < n) s_tile[t + t / P.R] = ldg_f4(src + tile + t);
+    __syncthreads();
+    for (int j = warp; j < P.R; j += nwarp) {
+      const int t = lane * P.R + j, i = tile + t;
+      if (i >= n) continue;
+      const float4 p = s_tile[t + lane];
+      if (!finite3(p)) continue;  // pcl::removeNaNFromPointCloud (:59)
+      int row, col;
+      if (!project_rowcol(p.x, p.y, p.z, P, row, col)) continue;
+      atomicMax(win + row * P.C + col, i);  // the later point of a cell wins (:103)
+    }
   }
 }
 
@@ -312,8 +351,8 @@ __device__ __forceinline__ CellClass classify(int cell, int row, int col, const 
 
 __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat,
                                                           const uint8_t *__restrict__ ground, int4 *__restrict__ rowcnt,
-                                                          const float4 *__restrict__ raw, const int *first_valid,
-                                                          const int *last_valid, float *orient, int Nmax, IpDev P) {
+                                                          const float4 *__restrict__ raw, const int *__restrict__ n_pts,
+                                                          float *orient, int Nmax, IpDev P) {
   const int b = blockIdx.y, row = blockIdx.x;
   const size_t base = (size_t)b * P.RC;
   int nk = 0, no = 0, nr = 0;
@@ -324,16 +363,34 @@ __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict_
     nr += c.rootflag;
   }
   __shared__ int s[3][8];
+  __shared__ int s_fv, s_lv;
   nk = warp_sum_i(nk); no = warp_sum_i(no); nr = warp_sum_i(nr);
   if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = nk; s[1][threadIdx.x >> 5] = no; s[2][threadIdx.x >> 5] = nr; }
+  if (threadIdx.x == 0) { s_fv = 0x7fffffff; s_lv = -1; }
   __syncthreads();
+  if (row == 0) {  // first / last point that survives removeNaNFromPointCloud (:59,:62-63): scan inwards from both ends
+    const int n = min(n_pts[b], Nmax);
+    const float4 *src = raw + (size_t)b * Nmax;
+    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+      const int i = c0 + threadIdx.x;
+      const bool f = i < n && finite3(src[i]);
+      if (f) atomicMin(&s_fv, i);
+      if (__syncthreads_or(f)) break;
+    }
+    for (int c0 = n - 1; c0 >= 0; c0 -= blockDim.x) {
+      const int i = c0 - threadIdx.x;
+      const bool f = i >= 0 && finite3(src[i]);
+      if (f) atomicMax(&s_lv, i);
+      if (__syncthreads_or(f)) break;
+    }
+  }
   if (threadIdx.x == 0) {
     int a = 0, o = 0, r = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s[0][w]; o += s[1][w]; r += s[2][w]; }
     rowcnt[b * P.R + row] = make_int4(a, o, r, 0);
     if (row == 0) {  // start/end orientation (:62-72): float atan2, float32 message fields
       float so = 0.f, eo = 0.f;
-      const int fv = first_valid[b], lv = last_valid[b];
+      const int fv = s_fv, lv = s_lv;
       if (lv >= 0 && fv <= lv) {
         const float4 p0 = raw[(size_t)b * Nmax + fv], p1 = raw[(size_t)b * Nmax + lv];
         so = -(float)atan2((double)p0.y, (double)p0.x);
@@ -437,6 +494,10 @@ IpDev make_ip_dev(const AlegoHandle *h) {
   d.row_scale = 180.0 / M_PI / h->P.ang_res_y;
   d.row_off = h->P.ang_bottom / h->P.ang_res_y + 0.5;
   d.col_scale = 180.0 / M_PI / h->P.ang_res_x;
+  d.row_scale_f = (float)d.row_scale; d.row_off_f = (float)d.row_off; d.col_scale_f = (float)d.col_scale;
+  // uncertainty band of the fast path in cells: 4x (angle error bound x scale + float rounding of a coordinate < 1.5 C)
+  d.eps_row = (float)std::max(2e-3, 4.0 * (ALEGO_FAST_ATAN_ERR * d.row_scale + 2e-7 * (h->R + std::fabs(d.row_off))));
+  d.eps_col = (float)std::max(2e-3, 4.0 * (2.0 * ALEGO_FAST_ATAN_ERR * d.col_scale + 2e-7 * 1.5 * h->C));
   d.sin_x = h->seg_sin_x; d.cos_x = h->seg_cos_x; d.sin_y = h->seg_sin_y; d.cos_y = h->seg_cos_y;
   return d;
 }
@@ -445,11 +506,16 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   const IpDev P = make_ip_dev(h);
   const int B = h->B;
   cudaStream_t s = h->stream;
-  const int pt_blocks = min(div_up(h->Nmax, 256), 4096);
+  const int pt_blocks = min(div_up(h->Nmax, 32 * P.R), 4096);
   const int cell_blocks = min(div_up(h->RC, 256), 4096);
-  { LAUNCH(h, "ip_reset"); ip_reset_kernel<<<div_up(B, 128), 128, 0, s>>>(h->first_valid, h->last_valid, B); }
+  static bool proj_attr_set = false;
+  if (!proj_attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(ip_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(32 * (ALEGO_MAX_RINGS + 1) * sizeof(float4))));
+    proj_attr_set = true;
+  }
   { LAUNCH(h, "ip_project");
-    ip_project_kernel<<<dim3(pt_blocks, B), 256, 0, s>>>(h->raw, h->n_pts, h->winner, h->first_valid, h->last_valid, h->Nmax, P); }
+    ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(h->raw, h->n_pts, h->winner, h->Nmax, P); }
   { LAUNCH(h, "ip_gather");
     ip_gather_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->raw, h->winner, h->cloud, h->range, h->ground, h->Nmax, P); }
   const int gpairs = min(P.ground_scan_id, P.R - 1) * P.C;
@@ -461,8 +527,8 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->parent, P); }
   { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ip_rowcount");
-    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->raw, h->first_valid,
-                                                   h->last_valid, h->orient, h->Nmax, P); }
+    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->raw, h->n_pts, h->orient,
+                                                   h->Nmax, P); }
   { LAUNCH(h, "ip_compact");
     ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,
                                                   h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring,

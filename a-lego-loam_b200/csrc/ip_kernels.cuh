@@ -5,7 +5,8 @@
 struct IpDev {
   int R, C, RC, ground_scan_id, seg_valid_point_num, seg_valid_line_num, seg_min_cluster;
   double ang_res_x, ang_res_y, ang_bottom, sensor_mount_ang, seg_theta;
-  double row_scale, row_off, col_scale;  // fast-path forms of the row / column scaling (exact forms near cell boundaries)
+  double row_scale, row_off, col_scale;
+  float row_scale_f, row_off_f, col_scale_f, eps_row, eps_col;  // fast-path forms of the row / column scaling (exact forms near cell boundaries)
   double sin_x, cos_x, sin_y, cos_y;  // sin/cos of seg_alpha_x / seg_alpha_y (utility.h:60-61), host libm
 };
 

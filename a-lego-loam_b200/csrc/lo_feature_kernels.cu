@@ -320,51 +320,109 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
   }
 }
 
-// per-ring less_flat_scan (:279-285) + VoxelGrid (:288-293).  Output staged at lf_stage[lo...] of the ring.
-#define LFV_THREADS 256
-__global__ void __launch_bounds__(LFV_THREADS)
+// per-ring less_flat_scan (:279-285) + VoxelGrid (:288-293): one WARP per (ring, sequence) — a ring holds a few hundred
+// points, far too few to feed a CTA-wide sort (sort_voxel.cuh, warp variant).  Output staged at lf_stage[lo...] of the ring.
+#define LFV_WARPS 4
+#define LFV_MAX_CHUNKS 256  // 8192 columns / 32
+__global__ void __launch_bounds__(LFV_WARPS * 32)
 lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ flabel, const int *__restrict__ start_ring,
-                          const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt, int R,
-                          int RC, int pts_cap, float leaf) {
-  extern __shared__ __align__(16) uint8_t lfv_smem[];
-  float4 *pts = reinterpret_cast<float4 *>(lfv_smem);
-  u64 *keys_a = reinterpret_cast<u64 *>(lfv_smem + (size_t)pts_cap * sizeof(float4));
-  u64 *keys_b = keys_a + pts_cap;
-  void *scratch = keys_b + pts_cap;
-  __shared__ float redf[48];
-  __shared__ int redi[48];
-  __shared__ VoxFrame frame;
-  __shared__ int seg_sp[6], seg_ep[6];
-  const int ring = blockIdx.x, b = blockIdx.y, br = b * R + ring;
+                          const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt,
+                          u64 *__restrict__ keys_a, u64 *__restrict__ keys_b, int R, int RC, float leaf) {
+  __shared__ int s_hist[LFV_WARPS][WVOX_MAX_PASSES * WVOX_RADIX];
+  __shared__ unsigned s_member[LFV_WARPS][LFV_MAX_CHUNKS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int ring = blockIdx.x * LFV_WARPS + warp, b = blockIdx.y;
+  if (ring >= R) return;  // warp-uniform; the kernel has no block-wide barrier
+  const int br = b * R + ring;
   const size_t base = (size_t)b * RC;
   const int start = start_ring[br], end = end_ring[br];
-  if (threadIdx.x < 6) {
-    int sp, ep;
-    segment_bounds(start, end, threadIdx.x, sp, ep);
-    seg_sp[threadIdx.x] = sp;
-    seg_ep[threadIdx.x] = ep;
-  }
-  __syncthreads();
-  // ordered compaction of {k in a processed segment : cloud_label_[k] <= 0}
-  int n = 0;
-  for (int k0 = start; k0 < end; k0 += LFV_THREADS) {  // the segments tile [start, end-1]
-    const int k = k0 + threadIdx.x;
-    bool member = false;
-    if (k < end) {
+  // {k in a processed segment : cloud_label_[k] <= 0}; the six segments tile [start, end-1], a segment with sp >= ep
+  // (at most one point) is skipped by the reference (:179)
+  int sp[6], ep[6];
+  bool all_segments = true;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) member |= (seg_sp[j] < seg_ep[j] && k >= seg_sp[j] && k <= seg_ep[j]);
-      member = member && flabel[base + k] <= 0;
-    }
-    int total;
-    const int ex = block_excl_scan(member ? 1 : 0, redi, &total);
-    if (member && n + ex < pts_cap) pts[n + ex] = seg_cloud[base + k];
-    n += total;
+  for (int j = 0; j < 6; ++j) {
+    segment_bounds(start, end, j, sp[j], ep[j]);
+    all_segments &= sp[j] < ep[j];
   }
-  __syncthreads();
-  n = min(n, pts_cap);
+  auto in_segment = [&](int k) {
+    if (all_segments) return true;
+    bool m = false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) m |= (sp[j] < ep[j] && k >= sp[j] && k <= ep[j]);
+    return m;
+  };
   const int lo = max(start - 5, 0);
-  const int n_out = block_voxel_grid<unsigned short>(pts, n, leaf, keys_a, keys_b, scratch, lf_stage + base + lo, redf, redi, &frame);
-  if (threadIdx.x == 0) ring_feat_cnt[br * 4 + 3] = n_out;
+  const float4 *pts = seg_cloud + base + start;  // key low word = k - start
+  float4 *out = lf_stage + base + lo;
+  unsigned *member_bits = s_member[warp];
+  // ---- membership masks + bounding box over the finite members (getMinMax3D)
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  int n = 0;
+  for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
+    const int k = k0 + lane;
+    const bool member = k < end && in_segment(k) && flabel[base + k] <= 0;
+    if (member) {
+      const float4 p = pts[k - start];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      }
+    }
+    const unsigned mm = __ballot_sync(0xffffffffu, member);
+    if (lane == 0) member_bits[ch] = mm;
+    n += __popc(mm);
+  }
+  __syncwarp();
+  if (n == 0) {
+    if (lane == 0) ring_feat_cnt[br * 4 + 3] = 0;
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  const WarpVoxFrame frame = warp_vox_frame(mn, mx, leaf);
+  if (frame.overflow) {  // "leaf size is too small": output = input
+    int run = 0;
+    for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
+      const unsigned mm = member_bits[ch];
+      if ((mm >> lane) & 1u) out[run + __popc(mm & lt_mask)] = pts[k0 + lane - start];
+      run += __popc(mm);
+    }
+    if (lane == 0) ring_feat_cnt[br * 4 + 3] = run;
+    return;
+  }
+  // ---- (voxel key, position) words + the digit histograms of every pass
+  const int npass = (frame.key_bits + WVOX_BITS - 1) / WVOX_BITS;
+  int *hist = s_hist[warp];
+  for (int t = lane; t < npass * WVOX_RADIX; t += 32) hist[t] = 0;
+  __syncwarp();
+  u64 *ka = keys_a + base + lo, *kb = keys_b + base + lo;
+  const unsigned pad_key = (unsigned)frame.n_cells;  // non-finite points sort behind every voxel
+  int run = 0, nv = 0;
+  for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
+    const unsigned mm = member_bits[ch];
+    const bool member = (mm >> lane) & 1u;
+    unsigned vk = pad_key;
+    bool fin = false;
+    if (member) {
+      const float4 p = pts[k0 + lane - start];
+      fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+      if (fin) vk = warp_vox_key(p, frame);
+      ka[run + __popc(mm & lt_mask)] = ((u64)vk << 32) | (unsigned)(k0 + lane - start);
+    }
+    run += __popc(mm);
+    nv += __popc(__ballot_sync(0xffffffffu, fin));
+    warp_vox_hist_add(hist, vk, member, npass);
+  }
+  __syncwarp();
+  const u64 *keys = warp_radix_sort(ka, kb, n, npass, hist);
+  const int n_out = warp_vox_centroids(keys, nv, pts, out);
+  if (lane == 0) ring_feat_cnt[br * 4 + 3] = n_out;
 }
 
 // ring-major concatenation: index lists, feature clouds, ring offsets of the clouds that become the next
@@ -443,17 +501,10 @@ int lo_extract_device(AlegoHandle *h) {
     lo_select_kernel<<<dim3(div_up(R, SEL_WARPS), B), SEL_WARPS * 32, (size_t)SEL_WARPS * pkcap, s>>>(
         h->seg_col, h->seg_ground, h->curv, h->sort_idx, h->start_ring, h->end_ring, h->picked0, h->picked, h->flabel,
         h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, R, RC, pkcap); }
-  const int pts_cap = C;  // a ring holds at most C points (< 65536: 16-bit radix counters)
-  const size_t lfv_smem = (size_t)pts_cap * (sizeof(float4) + 2 * sizeof(u64)) + radix_scratch_bytes<unsigned short>(LFV_THREADS);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(lo_less_flat_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   { LAUNCH(h, "lo_less_flat_voxel");
-    lo_less_flat_voxel_kernel<<<dim3(R, B), LFV_THREADS, lfv_smem, s>>>(h->seg_cloud, h->flabel, h->start_ring, h->end_ring,
-                                                                       h->lf_stage, h->ring_feat_cnt, R, RC, pts_cap,
-                                                                       (float)h->P.less_flat_leaf); }
+    lo_less_flat_voxel_kernel<<<dim3(div_up(R, LFV_WARPS), B), LFV_WARPS * 32, 0, s>>>(
+        h->seg_cloud, h->flabel, h->start_ring, h->end_ring, h->lf_stage, h->ring_feat_cnt, h->sort_scratch, h->lfv_keys, R, RC,
+        (float)h->P.less_flat_leaf); }
   const int cur = h->cur;
   { LAUNCH(h, "lo_finalize");
     lo_finalize_kernel<<<dim3(R, B), 128, 0, s>>>(h->seg_cloud, h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat,

@@ -222,3 +222,167 @@ static __device__ int block_voxel_grid(const float4 *pts, int n, float leaf, u64
   __syncthreads();
   return run_base;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-synchronous variant for small clouds (one ring of the less-flat cloud, laserOdometry.cpp:288-293): ONE WARP does
+// the whole VoxelGrid of a point subset, no block barriers, so a CTA packs several independent clouds.
+//  * digit ranks come from __match_any_sync (peers sharing a digit) instead of per-thread counter columns: a pass costs
+//    ~15 warp instructions per 32 words, independent of the block size;
+//  * the digit histograms of ALL passes are taken in the sweep that builds the keys, so every pass is a single
+//    read + scatter; passes whose digit is constant over the cloud (the high bits, usually) are skipped;
+//  * the (key, position) words ping-pong between two global buffers (L2 resident: a ring is a few KB).
+// Same ordering contract as block_voxel_grid: stable by voxel key, sums in ascending input position.
+struct WarpVoxFrame {
+  float inv;
+  int min_b[3];
+  int mul[3];
+  int overflow;
+  int key_bits;
+  int n_cells;
+};
+
+__device__ __forceinline__ WarpVoxFrame warp_vox_frame(const float mn[3], const float mx[3], float leaf) {
+  WarpVoxFrame f;
+  const float inv = 1.0f / leaf;
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                  dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  f.overflow = (dx * dy * dz > 2147483647ll) || !(mx[0] >= mn[0]);
+  f.inv = inv;
+  int div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    f.min_b[a] = (int)floorf(mn[a] * inv);
+    div_b[a] = (int)floorf(mx[a] * inv) - f.min_b[a] + 1;
+  }
+  f.mul[0] = 1; f.mul[1] = div_b[0]; f.mul[2] = div_b[0] * div_b[1];
+  const long long cells = (long long)div_b[0] * div_b[1] * div_b[2];
+  if (cells > 0 && cells < 2147483647ll) {
+    f.n_cells = (int)cells;
+    int kb = 1;
+    while ((1ll << kb) <= cells) ++kb;
+    f.key_bits = kb;
+  } else {
+    f.n_cells = -1;
+    f.key_bits = 32;
+  }
+  return f;
+}
+
+__device__ __forceinline__ unsigned warp_vox_key(const float4 &p, const WarpVoxFrame &f) {
+  const int i0 = (int)(floorf(p.x * f.inv) - (float)f.min_b[0]);
+  const int i1 = (int)(floorf(p.y * f.inv) - (float)f.min_b[1]);
+  const int i2 = (int)(floorf(p.z * f.inv) - (float)f.min_b[2]);
+  return (unsigned)(i0 * f.mul[0] + i1 * f.mul[1] + i2 * f.mul[2]);
+}
+
+#define WVOX_BITS 8
+#define WVOX_RADIX 256
+#define WVOX_MAX_PASSES 4
+// hist: [WVOX_MAX_PASSES][256] ints of shared memory private to the warp, zeroed by the caller before the key sweep and
+// filled by warp_vox_hist_add.  8-bit digits: a 21-bit voxel index needs 3 passes; __match_any_sync ranks any digit width.
+__device__ __forceinline__ void warp_vox_hist_add(int *hist, unsigned vk, bool valid, int npass) {
+  const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+  for (int p = 0; p < npass; ++p) {
+    const int d = (int)((vk >> (p * WVOX_BITS)) & (WVOX_RADIX - 1));
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : WVOX_RADIX);
+    if (valid && (peers & lt_mask) == 0) hist[p * WVOX_RADIX + d] += __popc(peers);
+  }
+  __syncwarp();
+}
+
+// Stable LSD sort of a[0..n) by bits [32, 32 + 8*npass) using the precomputed histograms (which it turns into digit
+// offsets in place).  Returns the sorted buffer.
+__device__ __forceinline__ u64 *warp_radix_sort(u64 *a, u64 *b, int n, int npass, int *hist) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int p = 0; p < npass; ++p) {
+    int *dbase = hist + p * WVOX_RADIX;
+    // exclusive scan of the 256 digit counts (8 per lane); a digit that holds every word makes the pass the identity
+    int c[8], sum = 0;
+    bool all_in_one = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      c[q] = dbase[lane * 8 + q];
+      all_in_one |= c[q] == n;
+      sum += c[q];
+    }
+    if (__any_sync(0xffffffffu, all_in_one)) continue;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - sum;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      dbase[lane * 8 + q] = run;
+      run += c[q];
+    }
+    __syncwarp();
+    const int shift = 32 + p * WVOX_BITS;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+      u64 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        e[u] = i < n ? a[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i0 + u * 32 >= n) break;
+        const bool valid = i < n;
+        const int d = (int)((e[u] >> shift) & (WVOX_RADIX - 1));
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : WVOX_RADIX);
+        const int rank = __popc(peers & lt_mask);
+        const int dst = valid ? dbase[d] + rank : 0;
+        __syncwarp();
+        if (valid && rank == 0) dbase[d] += __popc(peers);
+        if (valid) b[dst] = e[u];
+        __syncwarp();
+      }
+    }
+    u64 *t = a;
+    a = b;
+    b = t;
+  }
+  __syncwarp();
+  return a;
+}
+
+// One output per run of equal voxel keys among keys[0..nv) (sorted), in key order; the low word of a key is the index of
+// its point in pts.  Returns the number of outputs.
+__device__ __forceinline__ int warp_vox_centroids(const u64 *keys, int nv, const float4 *__restrict__ pts, float4 *out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int run_base = 0;
+  for (int t0 = 0; t0 < nv; t0 += 32) {
+    const int t = t0 + lane;
+    bool head = false;
+    u64 k = 0;
+    if (t < nv) {
+      k = keys[t];
+      head = (t == 0) || ((unsigned)(keys[t - 1] >> 32) != (unsigned)(k >> 32));
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int cnt = 0;
+      const unsigned vk = (unsigned)(k >> 32);
+      u64 ku = k;
+      for (int u = t;;) {
+        const float4 p = pts[(unsigned)(ku & 0xffffffffu)];
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+        ++cnt;
+        if (++u >= nv) break;
+        ku = keys[u];
+        if ((unsigned)(ku >> 32) != vk) break;
+      }
+      const float fn = (float)cnt;
+      out[run_base + __popc(hm & lt_mask)] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
+    }
+    run_base += __popc(hm);
+  }
+  return run_base;
+}

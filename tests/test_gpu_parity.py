@@ -143,6 +143,30 @@ def test_ip_sub_cell_jitter(alego, ob):
     g.close()
 
 
+@pytest.mark.parametrize("preset", [1, 2])
+def test_ip_rays_anywhere_in_the_cell(alego, ob, preset):
+    """Rays jittered over the WHOLE cell (+-0.5): hundreds of points per sweep fall inside the fast path's uncertainty band
+    around a binning boundary and are decided by the exact form; the range image and everything derived from it must
+    still equal the oracle's (glibc atan2f / hypotf) bit for bit.  Also: points exactly on the axes and at the origin."""
+    P = alego.default_params(preset)
+    scans = make_scans(alego, P, [21, 22, 23], jitter_cells=0.4999)
+    special = np.array([[0, 0, 0, 1], [5, 0, 0, 1], [-5, 0, 0, 1], [0, 5, 0, 1], [0, -5, 0, 1], [0, 0, 5, 1], [0, 0, -5, 1],
+                        [3, 3, 0, 1], [-3, 3, -0.5, 1], [1e-20, 1e-20, 0, 1], [-0.0, -7, -1, 1]], np.float32)
+    scans[2] = np.concatenate([scans[2], special])
+    g = alego.Alego(P, n_seq=3, max_points=max(len(s) for s in scans))
+    buf, n = g.pack_scans(scans)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for b, s in enumerate(scans):
+        o = ob.Oracle(P)
+        o.ip(s)
+        assert min(o.get("min_margin_row"), o.get("min_margin_col")) < 2e-3  # the uncertainty band was exercised
+        o.lo_features()
+        check_ip(g, o, b, "seq%d" % b)
+        check_features(g, o, b, "seq%d" % b)
+    g.close()
+
+
 @pytest.mark.parametrize("preset", [0, 1, 3])
 def test_feature_sort_tie_heavy(alego, ob, preset):
     """Noise-free sweeps: whole stretches of a ring share one curvature value, so the feature picks depend on the order
