@@ -193,6 +193,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   DMALLOC(h, h->sharp, B * R * 12);
   DMALLOC(h, h->flat, B * R * 24);
   DMALLOC(h, h->lf_stage, B * RC);
+  DMALLOC(h, h->az_stage, B * RC);
   CUDA_TRY(h, cudaMemsetAsync(h->n_feat, 0, B * 4 * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->picked, 0, B * RC, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->flabel, 0, B * RC * sizeof(int), h->stream));
@@ -201,15 +202,19 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
     DMALLOC(h, h->less_flat[k], B * RC);
     DMALLOC(h, h->ls_ring_off[k], B * (R + 1));
     DMALLOC(h, h->lf_ring_off[k], B * (R + 1));
+    DMALLOC(h, h->az_pts[k], B * RC);
+    DMALLOC(h, h->az_off[k], B * R * (AZ_BINS + 1));
+    CUDA_TRY(h, cudaMemsetAsync(h->az_off[k], 0, B * R * (AZ_BINS + 1) * sizeof(int), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->ls_ring_off[k], 0, B * (R + 1) * sizeof(int), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->lf_ring_off[k], 0, B * (R + 1) * sizeof(int), h->stream));
   }
   // scan-to-scan
-  int rc = grid_alloc(h, &h->g_surf_last, (int)RC, 1.0f);
+  int rc = grid_alloc(h, &h->g_surf_last, (int)RC, 0.5f);  // dense cloud (every ring voxelised on its own): small cells keep the buckets short
   if (rc != ALEGO_OK) return rc;
   rc = grid_alloc(h, &h->g_corner_last, (int)(R * 120), 1.0f);
   if (rc != ALEGO_OK) return rc;
   DMALLOC(h, h->lo_params, B * 6);
+  DMALLOC(h, h->lo_pose, B);
   DMALLOC(h, h->t_w, B * 3);
   DMALLOC(h, h->r_w, B * 9);
   DMALLOC(h, h->lo_init, B);
@@ -280,7 +285,7 @@ void alego_destroy(AlegoHandle *h) {
                   h->M, h->outlier, h->n_outlier, h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,
                   h->n_feat, h->sharp, h->flat, h->lf_stage, h->vox_sort, h->less_sharp[0], h->less_sharp[1], h->less_flat[0],
-                  h->less_flat[1], h->ls_ring_off[0], h->ls_ring_off[1], h->lf_ring_off[0], h->lf_ring_off[1], h->lo_params, h->t_w,
+                  h->less_flat[1], h->ls_ring_off[0], h->ls_ring_off[1], h->lf_ring_off[0], h->lf_ring_off[1], h->lo_pose, h->az_stage, h->az_pts[0], h->az_pts[1], h->az_off[0], h->az_off[1], h->lo_params, h->t_w,
                   h->r_w, h->lo_init, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->lo_report, h->lo_trace,
                   h->lo_trace_n, h->map_corner, h->map_surf, h->n_map_corner, h->n_map_surf, h->lm_in_corner, h->lm_in_surf,
                   h->lm_in_outlier, h->lm_in_n, h->lm_use_ext, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total,

@@ -120,11 +120,15 @@ struct AlegoHandle {
   float4 *less_flat[2] = {nullptr, nullptr};   // [B][RC]     surf_last_ / less_flat
   int *ls_ring_off[2] = {nullptr, nullptr};    // [B][R+1]
   int *lf_ring_off[2] = {nullptr, nullptr};    // [B][R+1]
+  float4 *az_stage = nullptr;                  // [B][RC]     per-ring azimuth-binned less-flat points (staging)
+  float4 *az_pts[2] = {nullptr, nullptr};      // [B][RC]     ... aligned with less_flat[k]: (x, y, z, position in ring)
+  int *az_off[2] = {nullptr, nullptr};         // [B][R][AZ_BINS+1] bin starts inside each ring
   int cur = 0;                                 // which buffer holds the CURRENT scan's clouds
 
   // ---------------- LaserOdometry scan-to-scan ----------------
   GridIndex g_surf_last, g_corner_last;
   double *lo_params = nullptr;  // [B][6]
+  Pose *lo_pose = nullptr;      // [B] transformToStart of the current params_ (refreshed before each association)
   double *t_w = nullptr;        // [B][3]
   double *r_w = nullptr;        // [B][9]
   int *lo_init = nullptr;       // [B]
@@ -258,6 +262,41 @@ __device__ __forceinline__ int block_excl_scan(int v, int *smem, int *total) {
   if (total) *total = smem[32];
   return smem[wid] + inc - v;
 }
+
+// Approximate atan2f for decisions that are re-checked exactly (ImageProjection's row / column binning) or only need a
+// conservative bound (azimuth bins of LaserOdometry's ring search): |error| < 1e-6 rad (degree-15 odd minimax polynomial on [0,1], 1.5e-7, plus the
+// approximate division and the quadrant folds).  Returns false for operands it does not cover (zero / denormal / huge).
+#define ALEGO_FAST_ATAN_ERR 1e-6
+__device__ __forceinline__ bool fast_atan2(float y, float x, float &r) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  if (!(mx > 1e-30f && mx < 1e30f)) return false;
+  const float t = __fdividef(mn, mx);
+  const float u = t * t;
+  float p = -0.00405456405133009f;
+  p = __fmaf_rn(p, u, 0.021862948313355446f);
+  p = __fmaf_rn(p, u, -0.055912312120199203f);
+  p = __fmaf_rn(p, u, 0.09642196446657181f);
+  p = __fmaf_rn(p, u, -0.1390862911939621f);
+  p = __fmaf_rn(p, u, 0.19946566224098206f);
+  p = __fmaf_rn(p, u, -0.33329859375953674f);
+  p = __fmaf_rn(p, u, 0.9999993443489075f);
+  float a = p * t;
+  if (ay > ax) a = 1.57079637f - a;
+  if (x < 0.f) a = 3.14159274f - a;
+  r = copysignf(a, y);
+  return true;
+}
+
+// Azimuth bins of a ring-ordered feature cloud (LaserOdometry's adjacent-ring search): 64 bins of 5.625 degrees, bin index
+// wraps (azimuth pi and -pi are the same direction).  The 1e-6 rad error of fast_atan2 is covered by the search margins.
+#define AZ_BINS 64
+__device__ __forceinline__ float az_angle(float x, float y) {
+  float a;
+  if (!fast_atan2(y, x, a)) a = 0.f;  // on the axis of rotation (or absurd magnitudes): any bin, see lo_assoc
+  return a;
+}
+__device__ __forceinline__ int az_bin_unwrapped(float a) { return (int)floorf((a + 3.14159274f) * (AZ_BINS / 6.28318531f)); }
 
 // Rz(yaw)*Ry(pitch)*Rx(roll) and the trig terms, as in every cost function of utility.h:128-158
 struct PoseTrig {

@@ -22,30 +22,6 @@ namespace {
 // recomputes with correctly rounded float results obtained through double precision.
 // ---------------------------------------------------------------------------------------------------
 
-// atan2f for the fast path only: |error| < 1e-6 rad (degree-15 odd minimax polynomial on [0,1], 1.5e-7, plus the
-// approximate division and the quadrant folds).  Returns false for operands it does not cover (zero / denormal / huge).
-#define ALEGO_FAST_ATAN_ERR 1e-6
-__device__ __forceinline__ bool fast_atan2(float y, float x, float &r) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  if (!(mx > 1e-30f && mx < 1e30f)) return false;
-  const float t = __fdividef(mn, mx);
-  const float u = t * t;
-  float p = -0.00405456405133009f;
-  p = __fmaf_rn(p, u, 0.021862948313355446f);
-  p = __fmaf_rn(p, u, -0.055912312120199203f);
-  p = __fmaf_rn(p, u, 0.09642196446657181f);
-  p = __fmaf_rn(p, u, -0.1390862911939621f);
-  p = __fmaf_rn(p, u, 0.19946566224098206f);
-  p = __fmaf_rn(p, u, -0.33329859375953674f);
-  p = __fmaf_rn(p, u, 0.9999993443489075f);
-  float a = p * t;
-  if (ay > ax) a = 1.57079637f - a;
-  if (x < 0.f) a = 3.14159274f - a;
-  r = copysignf(a, y);
-  return true;
-}
-
 // Exact forms: what the reference evaluates (float atan2f / hypotf results, double scaling, :79-80, :87-88)
 __device__ __noinline__ double exact_row_f(float x, float y, float z, const IpDev &P) {
   const float hyp = (float)sqrt((double)x * (double)x + (double)y * (double)y);

@@ -1,9 +1,10 @@
 // lo_s2s_kernels.cu — LaserOdometry scan-to-scan on the device: replaces src/laserOdometry.cpp:316-535 and
 // transformToStart (:728-740).
 //
-// K10 lo_assoc<SURF>  : one warp per feature point — transformToStart, exact 1-NN in the last cloud through
+// K10 lo_assoc<SURF>  : one 8-lane group per feature point — transformToStart, exact 1-NN in the last cloud through
 //                       the hashed grid (kd-tree replacement), then the adjacent-ring walk (:342-396, :432-470)
-//                       as a lane-parallel argmin that keeps the sequential walk's tie rule
+//                       as a lane-parallel argmin over (distance, walk position); surf: only inside the azimuth window
+//                       that can hold a closer point (rings are binned by azimuth in lo_less_flat_voxel)
 // K11/K12 lo_solve    : one CTA per sequence — Corner/Surf residuals, Huber, 6x6 reduction, LM (solver.cuh);
 //                       phase 1 = surf blocks only (:410-421), phase 2 = surf + corner blocks (:484-495) and
 //                       the pose integration (:504-508)
@@ -14,49 +15,68 @@
 
 namespace {
 
+// One GROUP of G lanes (a power of two <= 32) serves one query: when the candidate sets are small a full warp per query
+// mostly idles and every reduction / control instruction is paid per warp.  All shuffles use the group's own lane mask,
+// groups of one warp diverge freely.
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+  return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31 & ~(G - 1)));
+}
+template <int G> __device__ __forceinline__ int group_lane() { return threadIdx.x & (G - 1); }
+
 struct Best {
   float d;
   int i;
 };
 __device__ __forceinline__ bool better(float d, int i, const Best &b) { return d < b.d || (d == b.d && i < b.i); }
-__device__ __forceinline__ Best warp_min_best(Best v) {
+template <int G> __device__ __forceinline__ Best group_min_best(Best v, unsigned gm) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = G / 2; o > 0; o >>= 1) {
     Best w;
-    w.d = __shfl_xor_sync(0xffffffffu, v.d, o);
-    w.i = __shfl_xor_sync(0xffffffffu, v.i, o);
+    w.d = __shfl_xor_sync(gm, v.d, o);
+    w.i = __shfl_xor_sync(gm, v.i, o);
     if (better(w.d, w.i, v)) v = w;
   }
   return v;
 }
 
-// exact nearest neighbour of (qx,qy,qz) by one warp: grows the searched cube shell by shell until the best
-// distance is covered (or the gate radius is exhausted).  Returns index -1 when nothing lies within max_shell.
-__device__ Best warp_nearest(const GridIndex &g, int b, float qx, float qy, float qz, int max_shell) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void nearest_visit_cell(const int *__restrict__ cs, const float4 *__restrict__ sp, int hsh, float qx, float qy,
+                                                   float qz, Best &best) {
+  const int e = cs[hsh + 1];
+  for (int t = cs[hsh]; t < e; ++t) {
+    const float4 p = sp[t];
+    const float d = l2_simple(qx, qy, qz, p);
+    const int idx = __float_as_int(p.w) & GRID_INDEX_MASK;
+    if (better(d, idx, best)) { best.d = d; best.i = idx; }
+  }
+}
+
+// exact nearest neighbour of (qx,qy,qz) by one lane group (kd_*_last_->nearestKSearch(point_sel, 1, ...), :341,:431):
+// the 3x3x3 cube of cells first, then shell by shell until the best distance is covered (or the gate radius is
+// exhausted).  Candidates are ranked by (float distance, index).  Returns index -1 when nothing lies within max_shell.
+template <int G> __device__ Best group_nearest(const GridIndex &g, int b, float qx, float qy, float qz, int max_shell, unsigned gm) {
+  const int gl = group_lane<G>();
   const int T = g.table_size;
   const int *cs = g.cell_start + (size_t)b * (T + 4);
   const float4 *sp = g.sorted + (size_t)b * g.cap;
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);
   Best best{3.402823466e+38f, 0x7fffffff};
-  for (int r = 1; r <= max(max_shell, 1); ++r) {
-    const int side = 2 * r + 1, total = side * side * side;
-    for (int c = lane; c < total; c += 32) {
-      const int dz = c / (side * side) - r, rem = c % (side * side), dy = rem / side - r, dx = rem % side - r;
-      if (r > 1 && max(abs(dx), max(abs(dy), abs(dz))) != r) continue;  // only the new shell (the first pass takes the whole 3x3x3 cube)
-      const int hsh = grid_hash(cx + dx, cy + dy, cz + dz, T);
-      const int e = cs[hsh + 1];
-      for (int t = cs[hsh]; t < e; ++t) {
-        const float4 p = sp[t];
-        const float d = l2_simple(qx, qy, qz, p);
-        const int idx = __float_as_int(p.w) & GRID_INDEX_MASK;
-        if (better(d, idx, best)) { best.d = d; best.i = idx; }
-      }
-    }
-    best = warp_min_best(best);
-    const float covered = (float)r * g.cell;
+#pragma unroll
+  for (int c = gl; c < 27; c += G) {
+    const int dz = c / 9 - 1, dy = (c % 9) / 3 - 1, dx = c % 3 - 1;
+    nearest_visit_cell(cs, sp, grid_hash(cx + dx, cy + dy, cz + dz, T), qx, qy, qz, best);
+  }
+  best = group_min_best<G>(best, gm);
+  for (int r = 2; r <= max_shell; ++r) {
+    const float covered = (float)(r - 1) * g.cell;
     if (best.i != 0x7fffffff && best.d <= covered * covered) break;
+    const int side = 2 * r + 1, total = side * side * side;
+    for (int c = gl; c < total; c += G) {
+      const int dz = c / (side * side) - r, rem = c % (side * side), dy = rem / side - r, dx = rem % side - r;
+      if (max(abs(dx), max(abs(dy), abs(dz))) != r) continue;  // only the new shell
+      nearest_visit_cell(cs, sp, grid_hash(cx + dx, cy + dy, cz + dz, T), qx, qy, qz, best);
+    }
+    best = group_min_best<G>(best, gm);
   }
   if (best.i == 0x7fffffff) best.i = -1;
   return best;
@@ -67,13 +87,13 @@ struct WalkMin {
   int pos;  // position in the sequential walk order (forward sweep first, then backward)
   int k;
 };
-__device__ __forceinline__ WalkMin warp_min_walk(WalkMin v) {
+template <int G> __device__ __forceinline__ WalkMin group_min_walk(WalkMin v, unsigned gm) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = G / 2; o > 0; o >>= 1) {
     WalkMin w;
-    w.d = __shfl_xor_sync(0xffffffffu, v.d, o);
-    w.pos = __shfl_xor_sync(0xffffffffu, v.pos, o);
-    w.k = __shfl_xor_sync(0xffffffffu, v.k, o);
+    w.d = __shfl_xor_sync(gm, v.d, o);
+    w.pos = __shfl_xor_sync(gm, v.pos, o);
+    w.k = __shfl_xor_sync(gm, v.k, o);
     if (w.d < v.d || (w.d == v.d && w.pos < v.pos)) v = w;
   }
   return v;
@@ -84,79 +104,156 @@ __device__ __forceinline__ double sqdist_walk(const float4 &p, float sx, float s
   return dx * dx + dy * dy + dz * dz;
 }
 
-#define ASSOC_WARPS 8
-template <bool SURF>
-__global__ void __launch_bounds__(ASSOC_WARPS * 32)
+struct WalkCtx {  // one query of the adjacent-ring walk
+  float sx, sy, sz;
+  int closest, nf;  // nf = number of forward-sweep positions (walk position of a backward candidate = nf + distance)
+  __device__ __forceinline__ int pos(int k) const { return k > closest ? k - closest - 1 : nf + closest - 1 - k; }
+};
+__device__ __forceinline__ void walk_offer(WalkMin &m, double pd, int pos, int k) {
+  if (pd < m.d || (pd == m.d && pos < m.pos)) { m.d = pd; m.pos = pos; m.k = k; }
+}
+
+// Azimuth window that holds every point closer than sqrt(d2) to a query at horizontal range rho and azimuth a_q:
+// dist(p, q) >= rho * sin|daz| for |daz| <= 90 degrees, so |daz| < asin(D / rho) <= s + 0.571 s^3 (s = D / rho <= 1).
+// Margins cover fast_atan2 (1e-6 rad) on both sides and the float evaluation.  full: the bound says nothing (D ~ rho).
+__device__ __forceinline__ void az_window(double d2, float rho, float &w, bool &full) {
+  const float D = sqrtf((float)d2) * 1.0001f + 1e-4f;
+  const float s = D / rho;
+  full = !(s < 0.99f);
+  w = s + 0.571f * s * s * s + 2e-4f;
+}
+// bins [b0, b0 + nb) (wrapping) of the window around azimuth a_q
+__device__ __forceinline__ void az_window_bins(float a_q, float w, bool full, int &b0, int &nb) {
+  b0 = 0;
+  nb = AZ_BINS;
+  if (!full) {
+    const int u0 = az_bin_unwrapped(a_q - w), u1 = az_bin_unwrapped(a_q + w);
+    nb = min(u1 - u0 + 1, AZ_BINS);
+    b0 = u0 & (AZ_BINS - 1);
+  }
+}
+
+// candidates of the ring starting at ring_begin inside the bins, offered to the lane's private minimum
+template <int G>
+__device__ __forceinline__ void az_scan_ring(const float4 *__restrict__ az, const int *__restrict__ off, int ring_begin, int b0, int nb,
+                                             const WalkCtx &c, WalkMin &m, int gl) {
+  const int e = b0 + nb;  // exclusive end in unwrapped bins (< 2*AZ_BINS): at most two contiguous index ranges
+  const int s0 = off[b0], e0 = off[min(e, AZ_BINS)];
+  const int e1 = e > AZ_BINS ? off[e - AZ_BINS] : 0;
+  const float4 *ring = az + ring_begin;
+  for (int t = s0 + gl; t < e0; t += G) {
+    const float4 p = ring[t];
+    const int k = ring_begin + __float_as_int(p.w);
+    if (k != c.closest) walk_offer(m, sqdist_walk(p, c.sx, c.sy, c.sz), c.pos(k), k);
+  }
+  for (int t = gl; t < e1; t += G) {
+    const float4 p = ring[t];
+    const int k = ring_begin + __float_as_int(p.w);
+    if (k != c.closest) walk_offer(m, sqdist_walk(p, c.sx, c.sy, c.sz), c.pos(k), k);
+  }
+}
+
+// params_ -> (R, t) of transformToStart, once per sequence instead of six double sin/cos per query
+__global__ void lo_pose_kernel(const double *__restrict__ lo_params, Pose *__restrict__ lo_pose, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double *x = lo_params + b * 6;
+  const PoseTrig T(x);
+  for (int q = 0; q < 9; ++q) lo_pose[b].R[q] = T.R[q];
+  for (int q = 0; q < 3; ++q) lo_pose[b].t[q] = x[q];
+}
+
+// One GROUP of G lanes serves one query (surf: 8 — a few cells and a few dozen ring points; corner: 32 — the walk covers
+// up to 480 points)
+#define ASSOC_THREADS 256
+#define LO_G_SURF 8
+#define LO_G_CORNER 32
+template <bool SURF, int G>
+__global__ void __launch_bounds__(ASSOC_THREADS)
 lo_assoc_kernel(const float4 *__restrict__ feat, int feat_stride, const int *__restrict__ n_feat, const float4 *__restrict__ last,
-                size_t last_stride, const int *__restrict__ ring_off, GridIndex g, const double *__restrict__ lo_params,
-                const int *__restrict__ lo_init, float *__restrict__ res, int *__restrict__ corr, int R, double gate) {
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * ASSOC_WARPS + warp;
+                size_t last_stride, const int *__restrict__ ring_off, GridIndex g, const Pose *__restrict__ lo_pose,
+                const int *__restrict__ lo_init, float *__restrict__ res, int *__restrict__ corr, int R, double gate,
+                const float4 *__restrict__ az_pts, const int *__restrict__ az_off) {
+  const int b = blockIdx.y, gl = group_lane<G>();
+  const unsigned gm = group_mask<G>();
+  const int q = blockIdx.x * (ASSOC_THREADS / G) + threadIdx.x / G;
   const int nq = n_feat[b * 4 + (SURF ? 2 : 0)];
   if (q >= nq || !lo_init[b]) return;
   const float4 cp = feat[(size_t)b * feat_stride + q];
-  const double *x = lo_params + b * 6;
-  const PoseTrig T(x);
+  const Pose &T = lo_pose[b];  // Rz*Ry*Rx and translation of params_, evaluated once per sequence (lo_pose_kernel)
   // transformToStart (:728-740): double rotation + translation, stored as float
-  const float sx = (float)(T.R[0] * cp.x + T.R[1] * cp.y + T.R[2] * cp.z + x[0]);
-  const float sy = (float)(T.R[3] * cp.x + T.R[4] * cp.y + T.R[5] * cp.z + x[1]);
-  const float sz = (float)(T.R[6] * cp.x + T.R[7] * cp.y + T.R[8] * cp.z + x[2]);
+  const float sx = (float)(T.R[0] * cp.x + T.R[1] * cp.y + T.R[2] * cp.z + T.t[0]);
+  const float sy = (float)(T.R[3] * cp.x + T.R[4] * cp.y + T.R[5] * cp.z + T.t[1]);
+  const float sz = (float)(T.R[6] * cp.x + T.R[7] * cp.y + T.R[8] * cp.z + T.t[2]);
   const int CW = SURF ? 4 : 3;
   int *co = corr + ((size_t)b * feat_stride + q) * CW;
   const float4 *L = last + (size_t)b * last_stride;
   const int *ro = ring_off + b * (R + 1);
   const int n_last = ro[R];
-  int max_shell = (int)ceilf(sqrtf((float)gate) / g.cell) + 1;
+  const int max_shell = (int)ceilf(sqrtf((float)gate) / g.cell) + 1;
   Best nn{0.f, -1};
-  if (n_last > 0) nn = warp_nearest(g, b, sx, sy, sz, max_shell);
+  if (n_last > 0) nn = group_nearest<G>(g, b, sx, sy, sz, max_shell, gm);
   if (nn.i < 0 || !((double)nn.d < gate)) {  // search_dist[0] < nearest_feature_dist (:343, :433)
-    if (lane == 0) co[1] = -1;
+    if (gl == 0) co[1] = -1;
     return;
   }
   const int closest = nn.i;
   const int cs = (int)L[closest].w;  // ring id = int(intensity) (:347, :436)
   // rings cs-2 .. cs+2 take part (break at int(intensity) > cs+2.5 / < cs-2.5, resp. > cs+2 / < cs-2).  The cloud is ring
   // ordered, so the sequential walks decompose into contiguous index ranges: same ring above / below `closest` (surf:
-  // min_idx2) and the neighbouring rings above / below (surf: min_idx3, corner: min_idx2).  A lane meets its candidates
-  // in walk order, so the reference's strict `point_dist < min_dist` keeps the earliest of equal distances inside the
-  // lane; the walk position only enters the cross-lane reduction.
+  // min_idx2) and the neighbouring rings above / below (surf: min_idx3, corner: min_idx2).  The reference keeps the FIRST
+  // candidate of minimal distance in walk order (strict `point_dist < min_dist`): candidates are ranked by
+  // (distance, walk position).
   const int fwd_end = ro[min(cs + 3, R)];
   const int bwd_begin = ro[max(cs - 2, 0)];
   const int same_lo = ro[min(max(cs, 0), R)], same_hi = ro[min(max(cs + 1, 0), R)];
   const int nf = max(fwd_end - (closest + 1), 0);
-  double d2 = gate, d3 = gate;
-  int k2 = -1, k3 = -1;
+  const WalkCtx c{sx, sy, sz, closest, nf};
+  WalkMin m2{gate, 0x7fffffff, -1}, m3{gate, 0x7fffffff, -1};
   if (SURF) {
-#pragma unroll 4
-    for (int k = closest + 1 + lane; k < same_hi; k += 32) {  // forward, same ring (:348-371)
-      const double pd = sqdist_walk(L[k], sx, sy, sz);
-      if (pd < d2) { d2 = pd; k2 = k; }
+    // The walk visits every point of up to five rings (~1500 candidates).  Only points inside the azimuth window of the
+    // current best distance can win, and the rings are indexed by azimuth bin (lo_less_flat_voxel): round 1 looks inside
+    // the 1 m window; a class whose best stays above that is searched again inside the window of what round 1 established
+    // (the gate when it found nothing).  Same (distance, walk position) minimum as the full walk.
+    const float a_q = az_angle(sx, sy), rho = sqrtf(sx * sx + sy * sy);
+    const float4 *AZ = az_pts + (size_t)b * last_stride;
+    const int *AO = az_off + (size_t)b * R * (AZ_BINS + 1);
+    const double d_round1 = fmin(1.0, gate);
+    double bound2 = d_round1, bound3 = d_round1;
+    for (int round = 0; round < 2; ++round) {
+      WalkMin l2{gate, 0x7fffffff, -1}, l3{gate, 0x7fffffff, -1};
+      float w;
+      bool full;
+      int b0 = 0, nb = AZ_BINS;
+      if (bound2 > 0) {
+        az_window(bound2, rho, w, full);
+        az_window_bins(a_q, w, full, b0, nb);
+        if (cs >= 0 && cs < R) az_scan_ring<G>(AZ, AO + cs * (AZ_BINS + 1), same_lo, b0, nb, c, l2, gl);
+        m2 = group_min_walk<G>(l2, gm);
+      }
+      if (bound3 > 0) {
+        if (bound3 != bound2) {
+          az_window(bound3, rho, w, full);
+          az_window_bins(a_q, w, full, b0, nb);
+        }
+        for (int r = max(cs - 2, 0); r <= min(cs + 2, R - 1); ++r)
+          if (r != cs) az_scan_ring<G>(AZ, AO + r * (AZ_BINS + 1), ro[r], b0, nb, c, l3, gl);
+        m3 = group_min_walk<G>(l3, gm);
+      }
+      // settled: the best lies strictly inside the searched radius (everything outside the window is farther)
+      bound2 = (bound2 > 0 && !(m2.d < bound2 * 0.9999)) ? (round == 0 ? m2.d : 0.0) : 0.0;
+      bound3 = (bound3 > 0 && !(m3.d < bound3 * 0.9999)) ? (round == 0 ? m3.d : 0.0) : 0.0;
+      if (!(bound2 > 0) && !(bound3 > 0)) break;
     }
-#pragma unroll 4
-    for (int k = closest - 1 - lane; k >= same_lo; k -= 32) {  // backward, same ring (:372-395)
-      const double pd = sqdist_walk(L[k], sx, sy, sz);
-      if (pd < d2) { d2 = pd; k2 = k; }
-    }
+  } else {
+    WalkMin l2{gate, 0x7fffffff, -1};
+    for (int k = max(closest + 1, same_hi) + gl; k < fwd_end; k += G)  // forward, rings above (:439-454)
+      walk_offer(l2, sqdist_walk(L[k], sx, sy, sz), c.pos(k), k);
+    for (int k = min(closest - 1, same_lo - 1) - gl; k >= bwd_begin; k -= G)  // backward, rings below (:455-470)
+      walk_offer(l2, sqdist_walk(L[k], sx, sy, sz), c.pos(k), k);
+    m2 = group_min_walk<G>(l2, gm);
   }
-  {
-    double &dn = SURF ? d3 : d2;
-    int &kn = SURF ? k3 : k2;
-#pragma unroll 4
-    for (int k = max(closest + 1, same_hi) + lane; k < fwd_end; k += 32) {  // forward, rings above (:439-454)
-      const double pd = sqdist_walk(L[k], sx, sy, sz);
-      if (pd < dn) { dn = pd; kn = k; }
-    }
-#pragma unroll 4
-    for (int k = min(closest - 1, same_lo - 1) - lane; k >= bwd_begin; k -= 32) {  // backward, rings below (:455-470)
-      const double pd = sqdist_walk(L[k], sx, sy, sz);
-      if (pd < dn) { dn = pd; kn = k; }
-    }
-  }
-  auto walk_pos = [&](int k) { return k < 0 ? 0x7fffffff : (k > closest ? k - closest - 1 : nf + closest - 1 - k); };
-  WalkMin m2{d2, walk_pos(k2), k2}, m3{d3, walk_pos(k3), k3};
-  m2 = warp_min_walk(m2);
-  if (SURF) m3 = warp_min_walk(m3);
-  if (lane == 0) {
+  if (gl == 0) {
     const bool ok = m2.k >= 0 && (!SURF || m3.k >= 0);
     co[0] = q;
     co[1] = ok ? closest : -1;
@@ -295,18 +392,20 @@ int lo_scan2scan_device(AlegoHandle *h) {
   cudaStream_t s = h->stream;
   const int cur = h->cur, prev = 1 - cur;
   const double gate = h->P.nearest_feature_dist, hub = h->P.huber_delta;
+  { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
   { LAUNCH(h, "lo_assoc_surf");
-    lo_assoc_kernel<true><<<dim3(div_up(R * 24, ASSOC_WARPS), B), ASSOC_WARPS * 32, 0, s>>>(
-        h->flat, R * 24, h->n_feat, h->less_flat[prev], (size_t)RC, h->lf_ring_off[prev], h->g_surf_last, h->lo_params, h->lo_init,
-        h->lo_surf_res, h->lo_surf_corr, R, gate); }
+    lo_assoc_kernel<true, LO_G_SURF><<<dim3(div_up(R * 24, ASSOC_THREADS / LO_G_SURF), B), ASSOC_THREADS, 0, s>>>(
+        h->flat, R * 24, h->n_feat, h->less_flat[prev], (size_t)RC, h->lf_ring_off[prev], h->g_surf_last, h->lo_pose, h->lo_init,
+        h->lo_surf_res, h->lo_surf_corr, R, gate, h->az_pts[prev], h->az_off[prev]); }
   { LAUNCH(h, "lo_solve_surf");
     lo_solve_kernel<<<B, 256, 0, s>>>(1, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
                                       h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub); }
+  { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
   { LAUNCH(h, "lo_assoc_corner");
-    lo_assoc_kernel<false><<<dim3(div_up(R * 12, ASSOC_WARPS), B), ASSOC_WARPS * 32, 0, s>>>(
-        h->sharp, R * 12, h->n_feat, h->less_sharp[prev], (size_t)R * 120, h->ls_ring_off[prev], h->g_corner_last, h->lo_params,
-        h->lo_init, h->lo_corner_res, h->lo_corner_corr, R, gate); }
+    lo_assoc_kernel<false, LO_G_CORNER><<<dim3(div_up(R * 12, ASSOC_THREADS / LO_G_CORNER), B), ASSOC_THREADS, 0, s>>>(
+        h->sharp, R * 12, h->n_feat, h->less_sharp[prev], (size_t)R * 120, h->ls_ring_off[prev], h->g_corner_last, h->lo_pose,
+        h->lo_init, h->lo_corner_res, h->lo_corner_corr, R, gate, nullptr, nullptr); }
   { LAUNCH(h, "lo_solve_corner");
     lo_solve_kernel<<<B, 256, 0, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
