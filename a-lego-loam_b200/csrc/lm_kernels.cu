@@ -64,16 +64,15 @@ __global__ void lm_prepare_kernel(const int *use_ext, const double *t_w, const d
 }
 
 #define LMV_THREADS 1024
-#define LMV_SMEM (radix_scratch_bytes<int>(LMV_THREADS))  // radix-sort scratch (64 KB of digit counters)
+#define LMV_WARPS (LMV_THREADS / 32)
+#define LMV_SMEM (sizeof(VoxShared<LMV_WARPS>))
 // kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launch)
 __global__ void __launch_bounds__(LMV_THREADS)
 lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s, float4 *ds_o,
                 float4 *total, float4 *ds_total, int cap_c, int cap_s, int cap_o, int *lm_n, u64 *sort_c, u64 *sort_s, u64 *sort_o,
                 int sort_cap_c, int sort_cap_s, int sort_cap_o) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
-  __shared__ float redf[6 * 32 + 8];
-  __shared__ int redi[48];
-  __shared__ VoxFrame frame;
+  VoxShared<LMV_WARPS> *sh = reinterpret_cast<VoxShared<LMV_WARPS> *>(lmv_smem);
   const int b = blockIdx.x, kind = first_kind + blockIdx.y;
   const float4 *src;
   int n;
@@ -100,7 +99,7 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
   }
   n = min(n, sort_cap);
   // ping-pong key buffers [2][sort_cap] in global memory (L2 resident), digit counters in shared memory
-  const int n_out = block_voxel_grid<int>(src, n, leaf, keys, keys + sort_cap, lmv_smem, dst, redf, redi, &frame);
+  const int n_out = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + sort_cap, dst, sh, nullptr, nullptr);
   if (threadIdx.x == 0) lm_n[b * 8 + (kind == 3 ? 4 : kind)] = n_out;
 }
 
@@ -108,10 +107,8 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
 __global__ void __launch_bounds__(LMV_THREADS)
 voxel_single_kernel(const float4 *src, int n, float leaf, float4 *dst, u64 *keys, int *n_out) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
-  __shared__ float redf[6 * 32 + 8];
-  __shared__ int redi[48];
-  __shared__ VoxFrame frame;
-  const int m = block_voxel_grid<int>(src, n, leaf, keys, keys + n, lmv_smem, dst, redf, redi, &frame);
+  VoxShared<LMV_WARPS> *sh = reinterpret_cast<VoxShared<LMV_WARPS> *>(lmv_smem);
+  const int m = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + n, dst, sh, nullptr, nullptr);
   if (threadIdx.x == 0) *n_out = m;
 }
 

@@ -5,7 +5,7 @@
 //                           the ±6 window of ranges / columns is staged in shared memory
 // K8a   lo_sort_segments  : per ring segment, the exact permutation std::sort would produce (:185)
 // K8b   lo_select         : one warp per ring walks its 6 segments in order (:188-286)
-// K9    lo_less_flat_voxel: per-ring VoxelGrid(0.4) of the less-flat points (:279-293)
+// K9    lo_less_flat_voxel: per-ring VoxelGrid(0.4) of the less-flat points (:279-293) + azimuth bins of the result
 //       lo_finalize       : ring-major concatenation of the per-ring lists / clouds
 #include "common.cuh"
 #include "lo_kernels.cuh"
@@ -320,63 +320,13 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
   }
 }
 
-// Azimuth index of one ring of the less-flat cloud (the next sweep's surf_last_): a stable counting sort of the ring's
-// points into AZ_BINS azimuth bins.  lo_assoc<SURF> walks "every point of rings cs-2..cs+2" (laserOdometry.cpp:348-395)
-// only inside the azimuth window that can hold a point closer than its current best — same result, ~10x fewer candidates.
-// dst[j] = (x, y, z, position of the point inside the ring); off[0..AZ_BINS] = bin starts.  cnt: >= 2*AZ_BINS ints of
-// shared memory private to the warp.
-__device__ __forceinline__ void warp_az_bins(const float4 *pts, int n, float4 *dst, int *off, int *cnt) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  for (int t = lane; t < AZ_BINS; t += 32) cnt[t] = 0;
-  __syncwarp();
-  for (int t0 = 0; t0 < n; t0 += 32) {
-    const int t = t0 + lane;
-    const bool valid = t < n;
-    int bin = AZ_BINS;
-    if (valid) {
-      const float4 p = pts[t];
-      bin = az_bin_unwrapped(az_angle(p.x, p.y)) & (AZ_BINS - 1);
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (valid && (peers & lt_mask) == 0) cnt[bin] += __popc(peers);
-    __syncwarp();
-  }
-  // exclusive scan of the 64 counts, two per lane
-  const int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
-  int inc = c0 + c1;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const int ex = inc - (c0 + c1);
-  __syncwarp();
-  cnt[2 * lane] = ex; cnt[2 * lane + 1] = ex + c0;
-  off[2 * lane] = ex; off[2 * lane + 1] = ex + c0;
-  if (lane == 31) off[AZ_BINS] = inc;
-  __syncwarp();
-  for (int t0 = 0; t0 < n; t0 += 32) {
-    const int t = t0 + lane;
-    const bool valid = t < n;
-    int bin = AZ_BINS;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      p = pts[t];
-      bin = az_bin_unwrapped(az_angle(p.x, p.y)) & (AZ_BINS - 1);
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    const int rank = __popc(peers & lt_mask);
-    const int d = valid ? cnt[bin] + rank : 0;
-    __syncwarp();
-    if (valid && rank == 0) cnt[bin] += __popc(peers);
-    if (valid) dst[d] = make_float4(p.x, p.y, p.z, __int_as_float(t));
-    __syncwarp();
-  }
-}
-
-// per-ring less_flat_scan (:279-285) + VoxelGrid (:288-293): one WARP per (ring, sequence) — a ring holds a few hundred
-// points, far too few to feed a CTA-wide sort (sort_voxel.cuh, warp variant).  Output staged at lf_stage[lo...] of the ring.
+// per-ring less_flat_scan (:279-285) + VoxelGrid (:288-293): one CTA of LFV_WARPS warps per (ring, sequence)
+// (sort_voxel.cuh).  Output staged at lf_stage[lo...] of the ring.
+//
+// Then the azimuth index of the ring's output (the next sweep's surf_last_): a stable counting sort of the ring's points
+// into AZ_BINS azimuth bins.  lo_assoc<SURF> walks "every point of rings cs-2..cs+2" (laserOdometry.cpp:348-395) only
+// inside the azimuth window that can hold a point closer than its current best — same result, ~10x fewer candidates.
+// az_stage[j] = (x, y, z, position of the point inside the ring); az_off[0..AZ_BINS] = bin starts.
 #define LFV_WARPS 4
 #define LFV_MAX_CHUNKS 256  // 8192 columns / 32
 __global__ void __launch_bounds__(LFV_WARPS * 32)
@@ -384,12 +334,10 @@ lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__res
                           const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt,
                           u64 *__restrict__ keys_a, u64 *__restrict__ keys_b, float4 *__restrict__ az_stage,
                           int *__restrict__ az_off, int R, int RC, float leaf) {
-  __shared__ int s_hist[LFV_WARPS][WVOX_MAX_PASSES * WVOX_RADIX];
-  __shared__ unsigned s_member[LFV_WARPS][LFV_MAX_CHUNKS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int ring = blockIdx.x * LFV_WARPS + warp, b = blockIdx.y;
-  if (ring >= R) return;  // warp-uniform; the kernel has no block-wide barrier
+  __shared__ VoxShared<LFV_WARPS> sh;
+  __shared__ unsigned s_member[LFV_MAX_CHUNKS];
+  __shared__ int s_chunk_base[LFV_MAX_CHUNKS];
+  const int ring = blockIdx.x, b = blockIdx.y;
   const int br = b * R + ring;
   const size_t base = (size_t)b * RC;
   const int start = start_ring[br], end = end_ring[br];
@@ -402,89 +350,41 @@ lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__res
     segment_bounds(start, end, j, sp[j], ep[j]);
     all_segments &= sp[j] < ep[j];
   }
-  auto in_segment = [&](int k) {
-    if (all_segments) return true;
-    bool m = false;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) m |= (sp[j] < ep[j] && k >= sp[j] && k <= ep[j]);
-    return m;
-  };
   const int lo = max(start - 5, 0);
-  const float4 *pts = seg_cloud + base + start;  // key low word = k - start
+  const float4 *pts = seg_cloud + base + start;  // item i = kept point start + i
+  const int *lab = flabel + base + start;
   float4 *out = lf_stage + base + lo;
-  unsigned *member_bits = s_member[warp];
-  // ---- membership masks + bounding box over the finite members (getMinMax3D)
-  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-  int n = 0;
-  for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
-    const int k = k0 + lane;
-    const bool member = k < end && in_segment(k) && flabel[base + k] <= 0;
-    if (member) {
-      const float4 p = pts[k - start];
-      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
-      }
-    }
-    const unsigned mm = __ballot_sync(0xffffffffu, member);
-    if (lane == 0) member_bits[ch] = mm;
-    n += __popc(mm);
-  }
-  __syncwarp();
-  int *azo = az_off + (size_t)br * (AZ_BINS + 1);
-  if (n == 0) {
-    if (lane == 0) ring_feat_cnt[br * 4 + 3] = 0;
-    for (int t = lane; t <= AZ_BINS; t += 32) azo[t] = 0;
-    return;
-  }
+  auto member = [&](int i) {
+    bool m = all_segments;
+    if (!m) {
+      const int k = start + i;
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+      for (int j = 0; j < 6; ++j) m |= (sp[j] < ep[j] && k >= sp[j] && k <= ep[j]);
     }
-  const WarpVoxFrame frame = warp_vox_frame(mn, mx, leaf);
-  if (frame.overflow) {  // "leaf size is too small": output = input
-    int run = 0;
-    for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
-      const unsigned mm = member_bits[ch];
-      if ((mm >> lane) & 1u) out[run + __popc(mm & lt_mask)] = pts[k0 + lane - start];
-      run += __popc(mm);
-    }
-    if (lane == 0) ring_feat_cnt[br * 4 + 3] = run;
-    __syncwarp();
-    warp_az_bins(out, run, az_stage + base + lo, azo, s_hist[warp]);
+    return m && lab[i] <= 0;
+  };
+  const int n_out = block_voxel_grid8<LFV_WARPS, true>(pts, max(end - start, 0), member, leaf, keys_a + base + lo, keys_b + base + lo, out,
+                                                       &sh, s_member, s_chunk_base);
+  if (threadIdx.x == 0) ring_feat_cnt[br * 4 + 3] = n_out;
+  // ---- azimuth bins of the ring's output
+  int *azo = az_off + (size_t)br * (AZ_BINS + 1);
+  if (n_out == 0) {
+    for (int t = threadIdx.x; t <= AZ_BINS; t += blockDim.x) azo[t] = 0;
     return;
   }
-  // ---- (voxel key, position) words + the digit histograms of every pass
-  const int npass = (frame.key_bits + WVOX_BITS - 1) / WVOX_BITS;
-  int *hist = s_hist[warp];
-  for (int t = lane; t < npass * WVOX_RADIX; t += 32) hist[t] = 0;
-  __syncwarp();
-  u64 *ka = keys_a + base + lo, *kb = keys_b + base + lo;
-  const unsigned pad_key = (unsigned)frame.n_cells;  // non-finite points sort behind every voxel
-  int run = 0, nv = 0;
-  for (int k0 = start, ch = 0; k0 < end; k0 += 32, ++ch) {
-    const unsigned mm = member_bits[ch];
-    const bool member = (mm >> lane) & 1u;
-    unsigned vk = pad_key;
-    bool fin = false;
-    if (member) {
-      const float4 p = pts[k0 + lane - start];
-      fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-      if (fin) vk = warp_vox_key(p, frame);
-      ka[run + __popc(mm & lt_mask)] = ((u64)vk << 32) | (unsigned)(k0 + lane - start);
-    }
-    run += __popc(mm);
-    nv += __popc(__ballot_sync(0xffffffffu, fin));
-    warp_vox_hist_add(hist, vk, member, npass);
-  }
-  __syncwarp();
-  const u64 *keys = warp_radix_sort(ka, kb, n, npass, hist);
-  const int n_out = warp_vox_centroids(keys, nv, pts, out);
-  if (lane == 0) ring_feat_cnt[br * 4 + 3] = n_out;
-  __syncwarp();
-  warp_az_bins(out, n_out, az_stage + base + lo, azo, s_hist[warp]);
+  float4 *azs = az_stage + base + lo;
+  block_counting_pass<LFV_WARPS>(
+      n_out, &sh,
+      [&](int i) {
+        const float4 p = out[i];
+        return az_bin_unwrapped(az_angle(p.x, p.y)) & (AZ_BINS - 1);
+      },
+      [&](int i, int d) {
+        const float4 p = out[i];
+        azs[d] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+      },
+      false);
+  for (int t = threadIdx.x; t <= AZ_BINS; t += blockDim.x) azo[t] = sh.dbase[t];
 }
 
 // ring-major concatenation: index lists, feature clouds, ring offsets of the clouds that become the next
@@ -568,7 +468,7 @@ int lo_extract_device(AlegoHandle *h) {
         h->seg_col, h->seg_ground, h->curv, h->sort_idx, h->start_ring, h->end_ring, h->picked0, h->picked, h->flabel,
         h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, R, RC, pkcap); }
   { LAUNCH(h, "lo_less_flat_voxel");
-    lo_less_flat_voxel_kernel<<<dim3(div_up(R, LFV_WARPS), B), LFV_WARPS * 32, 0, s>>>(
+    lo_less_flat_voxel_kernel<<<dim3(R, B), LFV_WARPS * 32, 0, s>>>(
         h->seg_cloud, h->flabel, h->start_ring, h->end_ring, h->lf_stage, h->ring_feat_cnt, h->sort_scratch, h->lfv_keys, h->az_stage,
         h->az_off[h->cur], R, RC, (float)h->P.less_flat_leaf); }
   const int cur = h->cur;

@@ -9,240 +9,45 @@
 // input is returned unchanged.  PCL sorts with std::sort on the key alone, so the summation order inside a
 // voxel is an accident of introsort; here points of a voxel are summed in ascending input order (a STABLE sort by
 // key of the position-ordered list), which is deterministic and equals the oracle's "stable" variant bit for bit.
-// One CTA handles one cloud.
 //
-// The sort is an LSD radix sort, 4 bits per pass over only the significant bits of the key (a cloud spans a few
-// hundred cells per axis: 4-6 passes): each thread owns a contiguous slice of the list (stability), counts its digits
-// in a private shared-memory column, a register-level vector scan turns the 16 x nthreads counts into destinations,
-// and the slice is scattered in order.  3 barriers per pass instead of one per bitonic stage (55-120 of them).
+// One CTA of NW warps handles one cloud (NW = 4 for one ring of the less-flat cloud, 32 for LaserMapping's clouds).
+// The sort is an LSD radix sort with 8-bit digits over only the significant bits of the key (a 21-bit voxel index:
+// 3 passes; a pass whose digit is constant over the cloud is skipped).  Every warp owns a contiguous slice of the list
+// (stability); the rank of a word inside its 32-word chunk comes from __match_any_sync (the lanes that share its digit),
+// so a pass costs ~15 warp instructions per chunk, and the per-warp digit counts (NW x 256 in shared memory) are turned
+// into destinations by one column sweep + one 256-entry scan.  The (key, position) words ping-pong between two global
+// buffers (L2 resident).
 #pragma once
 #include "common.cuh"
 
 typedef unsigned long long u64;
-#define VOX_RADIX_BITS 4
-#define VOX_RADIX 16
-
-// shared-memory footprint of the sort scratch for a block of `nt` threads with counter type CT
-template <typename CT>
-__host__ __device__ constexpr size_t radix_scratch_bytes(int nt) {
-  return (size_t)VOX_RADIX * nt * sizeof(CT) + (size_t)(VOX_RADIX * 33) * sizeof(int);
-}
-
-// Stable sort of a[0..n) by bits [32, 32+key_bits).  a, b: ping-pong buffers (shared or global memory).  scratch:
-// radix_scratch_bytes<CT>(blockDim.x) bytes of shared memory, 4-byte aligned.  CT must hold n.  Returns the buffer
-// that holds the sorted list.  All threads of the block must call; ends with a barrier.
-template <typename CT>
-__device__ u64 *block_radix_sort(u64 *a, u64 *b, int n, int key_bits, void *scratch) {
-  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
-  CT *cnt = reinterpret_cast<CT *>(scratch);                           // [16][nt], column tid is private
-  int *wtot = reinterpret_cast<int *>(cnt + (size_t)VOX_RADIX * nt);   // [16][32] per-warp totals -> exclusive prefixes
-  int *dbase = wtot + VOX_RADIX * 32;                                  // [16] first destination of each digit
-  const int E = ((n + nt - 1) / nt) | 1;  // odd slice length: conflict-free 8-byte shared-memory accesses
-  const int lo = min(tid * E, n), hi = min(lo + E, n);
-  for (int shift = 32; shift < 32 + key_bits; shift += VOX_RADIX_BITS) {
-#pragma unroll
-    for (int d = 0; d < VOX_RADIX; ++d) cnt[d * nt + tid] = 0;
-    for (int i = lo; i < hi; ++i) ++cnt[(int)((a[i] >> shift) & (VOX_RADIX - 1)) * nt + tid];
-    int c[VOX_RADIX], inc[VOX_RADIX];
-#pragma unroll
-    for (int d = 0; d < VOX_RADIX; ++d) {
-      c[d] = (int)cnt[d * nt + tid];
-      int v = c[d];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-      }
-      inc[d] = v;
-    }
-    if (lane == 31) {
-#pragma unroll
-      for (int d = 0; d < VOX_RADIX; ++d) wtot[d * 32 + wid] = inc[d];
-    }
-    __syncthreads();
-    if (wid == 0) {
-      int run = 0;
-      if (lane < VOX_RADIX)
-        for (int w = 0; w < nw; ++w) {
-          const int t = wtot[lane * 32 + w];
-          wtot[lane * 32 + w] = run;
-          run += t;
-        }
-      int ex = run;  // digit totals -> exclusive scan over the 16 digits
-#pragma unroll
-      for (int o = 1; o < VOX_RADIX; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, ex, o);
-        if (lane >= o) ex += t;
-      }
-      if (lane < VOX_RADIX) dbase[lane] = ex - run;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int d = 0; d < VOX_RADIX; ++d) cnt[d * nt + tid] = (CT)(dbase[d] + wtot[d * 32 + wid] + inc[d] - c[d]);
-    for (int i = lo; i < hi; ++i) {
-      const u64 e = a[i];
-      const int d = (int)((e >> shift) & (VOX_RADIX - 1));
-      const int dst = (int)cnt[d * nt + tid];
-      cnt[d * nt + tid] = (CT)(dst + 1);
-      b[dst] = e;
-    }
-    __syncthreads();
-    u64 *t = a;
-    a = b;
-    b = t;
-  }
-  return a;
-}
+#define VOX_BITS 8
+#define VOX_RADIX 256
+#define VOX_WIN 64
 
 struct VoxFrame {
   float inv;
   int min_b[3];
   int mul[3];
   int overflow;
-  int n_valid;
   int key_bits;  // bits that hold every voxel index AND the index one past the last (the key of non-finite points)
   int n_cells;
 };
 
-// Block-wide VoxelGrid.  pts: n input points (shared or global memory).  keys_a / keys_b: two buffers of n words
-// (shared or global memory).  scratch: radix_scratch_bytes<CT>(blockDim.x) bytes of shared memory.  out: room for n
-// points.  redf: >= 6*warps floats, redi: >= 40 ints of shared scratch.  Returns the number of output points (same
-// value in every thread).
-template <typename CT>
-static __device__ int block_voxel_grid(const float4 *pts, int n, float leaf, u64 *keys_a, u64 *keys_b, void *scratch, float4 *out,
-                                       float *redf, int *redi, VoxFrame *frame) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (n <= 0) return 0;
-  // ---- bounding box over finite points (getMinMax3D)
-  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const float4 p = pts[t];
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-    }
-  __syncthreads();
-  if (lane == 0)
-    for (int a = 0; a < 3; ++a) { redf[wid * 6 + a] = mn[a]; redf[wid * 6 + 3 + a] = mx[a]; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < nw; ++w)
-      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], redf[w * 6 + a]); mx[a] = fmaxf(mx[a], redf[w * 6 + 3 + a]); }
-    const float inv = 1.0f / leaf;
-    const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
-                    dz = (long long)((mx[2] - mn[2]) * inv) + 1;
-    frame->overflow = (dx * dy * dz > 2147483647ll) || !(mx[0] >= mn[0]);
-    frame->inv = inv;
-    int div_b[3];
-    for (int a = 0; a < 3; ++a) {
-      frame->min_b[a] = (int)floorf(mn[a] * inv);
-      div_b[a] = (int)floorf(mx[a] * inv) - frame->min_b[a] + 1;
-    }
-    frame->mul[0] = 1; frame->mul[1] = div_b[0]; frame->mul[2] = div_b[0] * div_b[1];
-    const long long cells = (long long)div_b[0] * div_b[1] * div_b[2];
-    if (cells > 0 && cells < 2147483647ll) {
-      frame->n_cells = (int)cells;
-      int kb = 1;
-      while ((1ll << kb) <= cells) ++kb;
-      frame->key_bits = kb;
-    } else {  // degenerate extents (the reference's index arithmetic wraps): sort all 32 key bits
-      frame->n_cells = -1;
-      frame->key_bits = 32;
-    }
-  }
-  __syncthreads();
-  if (frame->overflow) {  // "leaf size is too small": output = input
-    for (int t = threadIdx.x; t < n; t += blockDim.x) out[t] = pts[t];
-    __syncthreads();
-    return n;
-  }
-  const float inv = frame->inv;
-  // ---- (voxel key, input position) words; non-finite points get the key one past the last voxel and sort to the end
-  int nvalid_local = 0;
-  const unsigned pad_key = (unsigned)frame->n_cells;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    unsigned vk = pad_key;
-    const float4 p = pts[t];
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-      const int i0 = (int)(floorf(p.x * inv) - (float)frame->min_b[0]);
-      const int i1 = (int)(floorf(p.y * inv) - (float)frame->min_b[1]);
-      const int i2 = (int)(floorf(p.z * inv) - (float)frame->min_b[2]);
-      vk = (unsigned)(i0 * frame->mul[0] + i1 * frame->mul[1] + i2 * frame->mul[2]);
-      ++nvalid_local;
-    }
-    keys_a[t] = ((u64)vk << 32) | (unsigned)t;
-  }
-  nvalid_local = warp_sum_i(nvalid_local);
-  if (lane == 0) redi[wid] = nvalid_local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < nw; ++w) s += redi[w];
-    frame->n_valid = s;
-  }
-  __syncthreads();
-  const int nv = frame->n_valid;
-  // ---- stable sort by voxel key
-  const u64 *keys = block_radix_sort<CT>(keys_a, keys_b, n, frame->key_bits, scratch);
-  // ---- one output per run of equal voxel keys, in key order
-  int run_base = 0;
-  for (int c0 = 0; c0 < nv; c0 += blockDim.x) {
-    const int t = c0 + threadIdx.x;
-    bool head = false;
-    u64 k = 0;
-    if (t < nv) {
-      k = keys[t];
-      head = (t == 0) || ((unsigned)(keys[t - 1] >> 32) != (unsigned)(k >> 32));
-    }
-    int total;
-    const int ex = block_excl_scan(head ? 1 : 0, redi, &total);
-    if (head) {
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      int cnt = 0;
-      const unsigned vk = (unsigned)(k >> 32);
-      for (int u = t; u < nv; ++u) {
-        const u64 ku = keys[u];
-        if ((unsigned)(ku >> 32) != vk) break;
-        const float4 p = pts[(unsigned)(ku & 0xffffffffu)];
-        sx += p.x; sy += p.y; sz += p.z; si += p.w;
-        ++cnt;
-      }
-      const float fn = (float)cnt;
-      out[run_base + ex] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
-    }
-    run_base += total;
-  }
-  __syncthreads();
-  return run_base;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-synchronous variant for small clouds (one ring of the less-flat cloud, laserOdometry.cpp:288-293): ONE WARP does
-// the whole VoxelGrid of a point subset, no block barriers, so a CTA packs several independent clouds.
-//  * digit ranks come from __match_any_sync (peers sharing a digit) instead of per-thread counter columns: a pass costs
-//    ~15 warp instructions per 32 words, independent of the block size;
-//  * the digit histograms of ALL passes are taken in the sweep that builds the keys, so every pass is a single
-//    read + scatter; passes whose digit is constant over the cloud (the high bits, usually) are skipped;
-//  * the (key, position) words ping-pong between two global buffers (L2 resident: a ring is a few KB).
-// Same ordering contract as block_voxel_grid: stable by voxel key, sums in ascending input position.
-struct WarpVoxFrame {
-  float inv;
-  int min_b[3];
-  int mul[3];
-  int overflow;
-  int key_bits;
-  int n_cells;
+template <int NW>
+struct VoxShared {
+  float4 win_pt[NW][VOX_WIN];    // per-warp window of the sorted list (centroid pass)
+  unsigned win_key[NW][VOX_WIN];
+  int hist[NW][VOX_RADIX];       // per-warp digit counts, then the warp's offset inside each digit
+  int dbase[VOX_RADIX + 1];      // first destination of each digit
+  int wsum[NW];
+  float red[NW][6];
+  VoxFrame frame;
+  int flag, n, nv;
 };
 
-__device__ __forceinline__ WarpVoxFrame warp_vox_frame(const float mn[3], const float mx[3], float leaf) {
-  WarpVoxFrame f;
+__device__ __forceinline__ VoxFrame vox_frame(const float mn[3], const float mx[3], float leaf) {
+  VoxFrame f;
   const float inv = 1.0f / leaf;
   const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
                   dz = (long long)((mx[2] - mn[2]) * inv) + 1;
@@ -261,52 +66,71 @@ __device__ __forceinline__ WarpVoxFrame warp_vox_frame(const float mn[3], const 
     int kb = 1;
     while ((1ll << kb) <= cells) ++kb;
     f.key_bits = kb;
-  } else {
+  } else {  // degenerate extents (the reference's index arithmetic wraps): sort all 32 key bits
     f.n_cells = -1;
     f.key_bits = 32;
   }
   return f;
 }
 
-__device__ __forceinline__ unsigned warp_vox_key(const float4 &p, const WarpVoxFrame &f) {
+__device__ __forceinline__ unsigned vox_key(const float4 &p, const VoxFrame &f) {
   const int i0 = (int)(floorf(p.x * f.inv) - (float)f.min_b[0]);
   const int i1 = (int)(floorf(p.y * f.inv) - (float)f.min_b[1]);
   const int i2 = (int)(floorf(p.z * f.inv) - (float)f.min_b[2]);
   return (unsigned)(i0 * f.mul[0] + i1 * f.mul[1] + i2 * f.mul[2]);
 }
 
-#define WVOX_BITS 8
-#define WVOX_RADIX 256
-#define WVOX_MAX_PASSES 4
-// hist: [WVOX_MAX_PASSES][256] ints of shared memory private to the warp, zeroed by the caller before the key sweep and
-// filled by warp_vox_hist_add.  8-bit digits: a 21-bit voxel index needs 3 passes; __match_any_sync ranks any digit width.
-__device__ __forceinline__ void warp_vox_hist_add(int *hist, unsigned vk, bool valid, int npass) {
-  const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
-  for (int p = 0; p < npass; ++p) {
-    const int d = (int)((vk >> (p * WVOX_BITS)) & (WVOX_RADIX - 1));
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : WVOX_RADIX);
-    if (valid && (peers & lt_mask) == 0) hist[p * WVOX_RADIX + d] += __popc(peers);
-  }
-  __syncwarp();
+// slice of warp w when n items are split into NW contiguous, chunk-aligned slices
+template <int NW>
+__device__ __forceinline__ void vox_slice(int n, int w, int &lo, int &hi) {
+  const int S = (((n + NW - 1) / NW) + 31) & ~31;
+  lo = min(w * S, n);
+  hi = min(lo + S, n);
 }
 
-// Stable LSD sort of a[0..n) by bits [32, 32 + 8*npass) using the precomputed histograms (which it turns into digit
-// offsets in place).  Returns the sorted buffer.
-__device__ __forceinline__ u64 *warp_radix_sort(u64 *a, u64 *b, int n, int npass, int *hist) {
-  const int lane = threadIdx.x & 31;
+// One stable counting-sort pass over items [0, n).  digit(i) in [0, VOX_RADIX) is evaluated twice per item (count, then
+// scatter); emit(i, dst) stores item i at its destination.  After the call sh->dbase[d] is the first destination of
+// digit d (dbase[VOX_RADIX] = n).  With allow_skip a pass whose items all share one digit is the identity: nothing is
+// emitted and false is returned.  All threads of the block must call; ends with a barrier.
+template <int NW, class Digit, class Emit>
+__device__ __forceinline__ bool block_counting_pass(int n, VoxShared<NW> *sh, Digit digit, Emit emit, bool allow_skip) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  for (int p = 0; p < npass; ++p) {
-    int *dbase = hist + p * WVOX_RADIX;
-    // exclusive scan of the 256 digit counts (8 per lane); a digit that holds every word makes the pass the identity
+  int lo, hi;
+  vox_slice<NW>(n, w, lo, hi);
+  int *hist = sh->hist[w];
+  for (int t = lane; t < VOX_RADIX; t += 32) hist[t] = 0;
+  __syncwarp();
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < hi;
+    const int d = valid ? digit(i) : VOX_RADIX;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt_mask) == 0) hist[d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over the warps (a warp's words of a digit follow those of the warps before it) + total
+  for (int d = threadIdx.x; d < VOX_RADIX; d += NW * 32) {
+    int run = 0;
+#pragma unroll 4
+    for (int ww = 0; ww < NW; ++ww) {
+      const int t = sh->hist[ww][d];
+      sh->hist[ww][d] = run;
+      run += t;
+    }
+    sh->dbase[d] = run;
+  }
+  __syncthreads();
+  if (w == 0) {  // exclusive scan of the 256 digit totals, 8 per lane
     int c[8], sum = 0;
-    bool all_in_one = false;
+    bool one = false;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      c[q] = dbase[lane * 8 + q];
-      all_in_one |= c[q] == n;
+      c[q] = sh->dbase[lane * 8 + q];
+      one |= c[q] == n;
       sum += c[q];
     }
-    if (__any_sync(0xffffffffu, all_in_one)) continue;
     int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -316,73 +140,241 @@ __device__ __forceinline__ u64 *warp_radix_sort(u64 *a, u64 *b, int n, int npass
     int run = inc - sum;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      dbase[lane * 8 + q] = run;
+      sh->dbase[lane * 8 + q] = run;
       run += c[q];
     }
-    __syncwarp();
-    const int shift = 32 + p * WVOX_BITS;
-    for (int i0 = 0; i0 < n; i0 += 128) {
-      u64 e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 32 + lane;
-        e[u] = i < n ? a[i] : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 32 + lane;
-        if (i0 + u * 32 >= n) break;
-        const bool valid = i < n;
-        const int d = (int)((e[u] >> shift) & (WVOX_RADIX - 1));
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : WVOX_RADIX);
-        const int rank = __popc(peers & lt_mask);
-        const int dst = valid ? dbase[d] + rank : 0;
-        __syncwarp();
-        if (valid && rank == 0) dbase[d] += __popc(peers);
-        if (valid) b[dst] = e[u];
-        __syncwarp();
-      }
-    }
-    u64 *t = a;
-    a = b;
-    b = t;
+    const bool any_one = __any_sync(0xffffffffu, one);
+    if (lane == 31) { sh->dbase[VOX_RADIX] = inc; sh->flag = any_one ? 1 : 0; }
   }
-  __syncwarp();
+  __syncthreads();
+  if (allow_skip && sh->flag) return false;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < hi;
+    const int d = valid ? digit(i) : VOX_RADIX;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & lt_mask);
+    const int dst = valid ? sh->dbase[d] + hist[d] + rank : 0;
+    __syncwarp();
+    if (valid && rank == 0) hist[d] += __popc(peers);
+    if (valid) emit(i, dst);
+    __syncwarp();
+  }
+  __syncthreads();
+  return true;
+}
+
+// Stable sort of a[0..n) by bits [32, 32+key_bits).  a, b: ping-pong buffers in global memory.  Returns the buffer that
+// holds the sorted list.  All threads of the block must call; ends with a barrier.
+template <int NW>
+__device__ u64 *block_radix_sort8(u64 *a, u64 *b, int n, int key_bits, VoxShared<NW> *sh) {
+  for (int shift = 32; shift < 32 + key_bits; shift += VOX_BITS) {
+    const u64 *src = a;
+    u64 *dst = b;
+    const bool moved = block_counting_pass<NW>(
+        n, sh, [&](int i) { return (int)((src[i] >> shift) & (VOX_RADIX - 1)); }, [&](int i, int d) { dst[d] = src[i]; }, true);
+    if (moved) {
+      u64 *t = a;
+      a = b;
+      b = t;
+    }
+  }
   return a;
 }
 
-// One output per run of equal voxel keys among keys[0..nv) (sorted), in key order; the low word of a key is the index of
-// its point in pts.  Returns the number of outputs.
-__device__ __forceinline__ int warp_vox_centroids(const u64 *keys, int nv, const float4 *__restrict__ pts, float4 *out) {
+// One output per run of equal voxel keys among the sorted keys[0..nv); this warp handles the runs that START in
+// [lo, hi) (a chunk-aligned slice) and writes them from out[run_base] on, in key order.  The low word of a key is the
+// index of its point in pts.  A run is summed by the lane that owns its first element, strictly in list order (float
+// sums).  The 64 list entries starting at the chunk are staged in shared memory first (independent, coalesced loads), so
+// the sequential run walk does not chain two global-memory round trips per element; only a run reaching beyond the
+// window continues from global memory.  count_only: just count the runs.  Returns the number of runs of the slice.
+__device__ __forceinline__ int warp_vox_centroids(const u64 *keys, int lo, int hi, int nv, const float4 *__restrict__ pts, float4 *out,
+                                                  int run_base, unsigned *win_key, float4 *win_pt, bool count_only) {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int run_base = 0;
-  for (int t0 = 0; t0 < nv; t0 += 32) {
+  int runs = 0;
+  // voxel key of the element before the slice (no voxel has key 0xffffffff: pad keys sort behind nv)
+  unsigned prev_last = lo > 0 && lo < nv ? (unsigned)(keys[lo - 1] >> 32) : 0xffffffffu;
+  for (int t0 = lo; t0 < hi; t0 += 32) {
     const int t = t0 + lane;
+    if (count_only) {
+      const unsigned vk = t < hi ? (unsigned)(keys[t] >> 32) : 0u;
+      unsigned pv = __shfl_up_sync(0xffffffffu, vk, 1);
+      if (lane == 0) pv = prev_last;
+      runs += __popc(__ballot_sync(0xffffffffu, t < hi && vk != pv));
+      prev_last = __shfl_sync(0xffffffffu, vk, 31);
+      continue;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int u = t0 + h * 32 + lane;
+      if (u < nv) {
+        const u64 k = keys[u];
+        win_key[h * 32 + lane] = (unsigned)(k >> 32);
+        win_pt[h * 32 + lane] = pts[(unsigned)(k & 0xffffffffu)];
+      }
+    }
+    __syncwarp();
+    const int wend = min(nv - t0, VOX_WIN);  // valid window entries
     bool head = false;
-    u64 k = 0;
-    if (t < nv) {
-      k = keys[t];
-      head = (t == 0) || ((unsigned)(keys[t - 1] >> 32) != (unsigned)(k >> 32));
+    unsigned vk = 0;
+    if (t < hi) {
+      vk = win_key[lane];
+      head = vk != (lane == 0 ? prev_last : win_key[lane - 1]);
     }
     const unsigned hm = __ballot_sync(0xffffffffu, head);
     if (head) {
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
       int cnt = 0;
-      const unsigned vk = (unsigned)(k >> 32);
-      u64 ku = k;
-      for (int u = t;;) {
-        const float4 p = pts[(unsigned)(ku & 0xffffffffu)];
+      int w = lane;
+      for (; w < wend && win_key[w] == vk; ++w) {
+        const float4 p = win_pt[w];
         sx += p.x; sy += p.y; sz += p.z; si += p.w;
         ++cnt;
-        if (++u >= nv) break;
-        ku = keys[u];
-        if ((unsigned)(ku >> 32) != vk) break;
+      }
+      if (w == VOX_WIN) {  // the run may continue beyond the window
+        for (int u = t0 + VOX_WIN; u < nv; ++u) {
+          const u64 ku = keys[u];
+          if ((unsigned)(ku >> 32) != vk) break;
+          const float4 p = pts[(unsigned)(ku & 0xffffffffu)];
+          sx += p.x; sy += p.y; sz += p.z; si += p.w;
+          ++cnt;
+        }
       }
       const float fn = (float)cnt;
-      out[run_base + __popc(hm & lt_mask)] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
+      out[run_base + runs + __popc(hm & lt_mask)] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
     }
-    run_base += __popc(hm);
+    runs += __popc(hm);
+    prev_last = win_key[min(31, hi - t0 - 1)];
   }
-  return run_base;
+  return runs;
+}
+
+// Block-wide VoxelGrid of the points {pts[i] : i < n_src, member(i)} in ascending i.  MASKED = false: every i < n_src
+// takes part (member is not called).  MASKED = true: member_bits / chunk_base are ceil(n_src/32) words of shared memory.
+// ka / kb: two buffers of (number of members) words in global memory.  out: room for as many points.  Returns the number
+// of output points (same value in every thread).  All threads of the block (NW warps) must call.
+template <int NW, bool MASKED, class Member>
+__device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Member member, float leaf, u64 *ka, u64 *kb, float4 *out,
+                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int nch = (n_src + 31) >> 5;
+  // ---- membership + bounding box over the finite members (getMinMax3D)
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  for (int ch = w; ch < nch; ch += NW) {
+    const int i = ch * 32 + lane;
+    const bool m = i < n_src && (!MASKED || member(i));
+    if (m) {
+      const float4 p = pts[i];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      }
+    }
+    if (MASKED) {
+      const unsigned mm = __ballot_sync(0xffffffffu, m);
+      if (lane == 0) { member_bits[ch] = mm; chunk_base[ch] = __popc(mm); }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  if (lane == 0)
+    for (int a = 0; a < 3; ++a) { sh->red[w][a] = mn[a]; sh->red[w][3 + a] = mx[a]; }
+  __syncthreads();
+  if (w == 0) {
+    int n = n_src;
+    if (MASKED) {  // exclusive scan of the chunk populations
+      int carry = 0;
+      for (int c0 = 0; c0 < nch; c0 += 32) {
+        const int v = c0 + lane < nch ? chunk_base[c0 + lane] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (c0 + lane < nch) chunk_base[c0 + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      n = carry;
+    }
+    if (lane == 0) {
+      for (int ww = 1; ww < NW; ++ww)
+        for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], sh->red[ww][a]); mx[a] = fmaxf(mx[a], sh->red[ww][3 + a]); }
+      sh->frame = vox_frame(mn, mx, leaf);
+      sh->n = n;
+    }
+  }
+  __syncthreads();
+  const int n = sh->n;
+  if (n <= 0) return 0;
+  const VoxFrame frame = sh->frame;
+  if (frame.overflow) {  // "leaf size is too small": output = input
+    for (int ch = w; ch < nch; ch += NW) {
+      const int i = ch * 32 + lane;
+      if (MASKED) {
+        const unsigned mm = member_bits[ch];
+        if ((mm >> lane) & 1u) out[chunk_base[ch] + __popc(mm & lt_mask)] = pts[i];
+      } else if (i < n_src) {
+        out[i] = pts[i];
+      }
+    }
+    __syncthreads();
+    return n;
+  }
+  // ---- (voxel key, input position) words; non-finite points get the key one past the last voxel and sort to the end
+  const unsigned pad_key = (unsigned)frame.n_cells;
+  int nfin = 0;
+  for (int ch = w; ch < nch; ch += NW) {
+    const int i = ch * 32 + lane;
+    unsigned mm = 0xffffffffu;
+    bool m = i < n_src;
+    if (MASKED) {
+      mm = member_bits[ch];
+      m = (mm >> lane) & 1u;
+    }
+    if (m) {
+      const float4 p = pts[i];
+      unsigned vk = pad_key;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        vk = vox_key(p, frame);
+        ++nfin;
+      }
+      const int pos = MASKED ? chunk_base[ch] + __popc(mm & lt_mask) : i;
+      ka[pos] = ((u64)vk << 32) | (unsigned)i;
+    }
+  }
+  nfin = warp_sum_i(nfin);
+  if (lane == 0) sh->wsum[w] = nfin;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int ww = 0; ww < NW; ++ww) s += sh->wsum[ww];
+    sh->nv = s;
+  }
+  __syncthreads();
+  const int nv = sh->nv;
+  // ---- stable sort by voxel key
+  const u64 *keys = block_radix_sort8<NW>(ka, kb, n, frame.key_bits, sh);
+  // ---- centroids: every warp counts the runs that start in its slice, then writes them behind those of the warps before
+  int lo, hi;
+  vox_slice<NW>(nv, w, lo, hi);
+  const int my_runs = warp_vox_centroids(keys, lo, hi, nv, pts, out, 0, sh->win_key[w], sh->win_pt[w], true);
+  if (lane == 0) sh->wsum[w] = my_runs;
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int ww = 0; ww < NW; ++ww) {
+    const int t = sh->wsum[ww];
+    if (ww < w) before += t;
+    total += t;
+  }
+  warp_vox_centroids(keys, lo, hi, nv, pts, out, before, sh->win_key[w], sh->win_pt[w], false);
+  __syncthreads();
+  return total;
 }
