@@ -116,6 +116,7 @@ def lib():
         "alego_synchronize": (C.c_int, [H]),
         "alego_get_params": (C.c_int, [H, C.POINTER(AlegoParams)]),
         "alego_n_seq": (C.c_int, [H]),
+        "alego_set_point_stride": (C.c_int, [H, C.c_int]),
         "alego_host_alloc": (C.c_void_p, [C.c_size_t]),
         "alego_host_free": (None, [C.c_void_p]),
         "alego_ip_process": (C.c_int, [H, C.c_void_p, C.c_void_p]),
@@ -160,7 +161,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "alego_default_params", "alego_create", "alego_destroy", "alego_last_error", "alego_synchronize", "alego_get_params",
-    "alego_n_seq", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
+    "alego_n_seq", "alego_set_point_stride", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
     "alego_lo_get_features", "alego_lo_scan2scan", "alego_lo_get_state", "alego_lo_set_params", "alego_lm_set_map",
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
     "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
@@ -205,6 +206,7 @@ class Alego:
         self.n_seq = n_seq
         self.R, self.Cc = params.n_scan, params.horizon_scan
         self.max_points = max_points or self.R * self.Cc
+        self.point_stride = 4
         self.h = C.c_void_p()
         rc = self.L.alego_create(C.byref(self.params), device, n_seq, self.max_points, C.byref(self.h))
         if rc != OK:
@@ -228,15 +230,21 @@ class Alego:
         raise AlegoError("rc=%d: %s" % (rc, self.L.alego_last_error(self.h).decode()))
 
     # ---- ImageProjection
+    def set_point_stride(self, floats_per_point):
+        """4 = (x, y, z, intensity) per input point (default), 3 = packed (x, y, z): see alego_set_point_stride."""
+        self._chk(self.L.alego_set_point_stride(self.h, floats_per_point))
+        self.point_stride = floats_per_point
+
     def pack_scans(self, scans):
-        """list of (n_i,4) float32 arrays -> ([n_seq, max_points, 4] float32, [n_seq] int32)"""
+        """list of (n_i,4) float32 arrays -> ([n_seq, max_points, point_stride] float32, [n_seq] int32)"""
         assert len(scans) == self.n_seq
-        buf = np.zeros((self.n_seq, self.max_points, 4), np.float32)
+        st = self.point_stride
+        buf = np.zeros((self.n_seq, self.max_points, st), np.float32)
         n = np.zeros(self.n_seq, np.int32)
         for b, s in enumerate(scans):
             s = np.ascontiguousarray(s, np.float32).reshape(-1, 4)
             n[b] = len(s)
-            buf[b, :len(s)] = s
+            buf[b, :len(s)] = s[:, :st]
         return buf, n
 
     def ip_process(self, buf, n):

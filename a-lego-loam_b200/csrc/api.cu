@@ -320,6 +320,13 @@ int alego_get_params(const AlegoHandle *h, AlegoParams *out) {
 }
 int alego_n_seq(const AlegoHandle *h) { return h ? h->B : ALEGO_BAD_ARG; }
 
+int alego_set_point_stride(AlegoHandle *h, int floats_per_point) {
+  if (!h || (floats_per_point != 3 && floats_per_point != 4)) return ALEGO_BAD_ARG;
+  if (h->n_submitted != h->n_collected) { h->err = "alego_set_point_stride while submitted steps are in flight"; return ALEGO_NOT_READY; }
+  h->in_stride = floats_per_point;
+  return ALEGO_OK;
+}
+
 void *alego_host_alloc(size_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
@@ -373,13 +380,14 @@ static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyz
     total += n_points[b];
   }
   CUDA_TRY(h, cudaMemcpyAsync(n_dev, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, st));
+  const size_t pt_bytes = (size_t)h->in_stride * sizeof(float), row = (size_t)h->Nmax * h->in_stride;  // floats per sequence
+  float *dst = reinterpret_cast<float *>(raw);
   if (total * 10 >= (size_t)h->B * h->Nmax * 9) {  // nearly full rows: one DMA
-    CUDA_TRY(h, cudaMemcpyAsync(raw, xyzi_host, (size_t)h->B * h->Nmax * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, xyzi_host, (size_t)h->B * h->Nmax * pt_bytes, cudaMemcpyHostToDevice, st));
   } else {
     for (int b = 0; b < h->B; ++b)
       if (n_points[b] > 0)
-        CUDA_TRY(h, cudaMemcpyAsync(raw + (size_t)b * h->Nmax, xyzi_host + (size_t)b * h->Nmax * 4, (size_t)n_points[b] * sizeof(float4),
-                                    cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dst + (size_t)b * row, xyzi_host + (size_t)b * row, (size_t)n_points[b] * pt_bytes, cudaMemcpyHostToDevice, st));
   }
   return ALEGO_OK;
 }

@@ -39,6 +39,7 @@ struct KernelProfile {
 struct AlegoHandle {
   AlegoParams P;
   int dev = 0, B = 0, Nmax = 0, R = 0, C = 0, RC = 0;
+  int in_stride = 4;  // floats per input point: 4 = x,y,z,intensity; 3 = packed x,y,z (alego_set_point_stride)
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;    // map-index build overlapped with IP + LO (alego_pipeline_step)
   cudaStream_t copy_stream = nullptr;    // H2D of the next sweep overlapped with the current pass (alego_pipeline_submit)

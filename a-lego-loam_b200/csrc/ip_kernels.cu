@@ -63,30 +63,55 @@ __device__ __forceinline__ bool project_rowcol(float x, float y, float z, const 
 
 __device__ __forceinline__ bool finite3(const float4 &p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
 
+// Input point i of a sweep buffer holding `stride` floats per point: 4 = (x, y, z, intensity), one 16-byte load;
+// 3 = (x, y, z) packed, 25 % fewer bytes over PCIe.  The intensity of the input is never read by the reference's path —
+// pcCB overwrites it with row + col/10000 (imageProjection.cpp:101).
+__device__ __forceinline__ float4 load_point(const float *__restrict__ sweep, int i, int stride) {
+  if (stride == 4) return ldg_f4(reinterpret_cast<const float4 *>(sweep) + i);
+  const float *p = sweep + (size_t)i * 3;
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+}
+
 // K1a.  A spinning sensor emits its points firing by firing: ring index fastest, azimuth slowest.  A warp that processed
 // 32 CONSECUTIVE points would therefore scatter its 32 winner updates over 32 image rows (32 L2 sectors per instruction,
 // measured as the limiter of this kernel).  Instead a CTA stages a tile of 32*R consecutive points in shared memory with
 // coalesced 16-byte loads and lane l of a warp then takes point  l*R + j  of the tile: for ring-fastest input the lanes
 // of one instruction hit consecutive columns of ONE row (4 sectors); for any other order the mapping is merely as
 // scattered as the naive one.  The staging rows are padded to R+1 points so the transposed reads are conflict free.
-__global__ void __launch_bounds__(256) ip_project_kernel(const float4 *__restrict__ raw, const int *__restrict__ n_pts,
-                                                         int *__restrict__ winner, int Nmax, IpDev P) {
-  extern __shared__ float4 s_tile[];  // [32][R+1]
+__global__ void __launch_bounds__(256) ip_project_kernel(const float *__restrict__ raw, const int *__restrict__ n_pts,
+                                                         int *__restrict__ winner, int Nmax, int stride, IpDev P) {
+  extern __shared__ float4 s_tile[];  // stride 4: [32][R+1] points; stride 3: [32][3R+1] floats
   const int b = blockIdx.y;
   const int n = min(n_pts[b], Nmax);
-  const float4 *src = raw + (size_t)b * Nmax;
+  const float *src = raw + (size_t)b * Nmax * stride;
   int *win = winner + (size_t)b * P.RC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int tile_pts = 32 * P.R;
+  float *sf = reinterpret_cast<float *>(s_tile);
+  const int frow = 3 * P.R + 1;
   for (int tile = blockIdx.x * tile_pts; tile < n; tile += gridDim.x * tile_pts) {
     __syncthreads();
-    for (int t = threadIdx.x; t < tile_pts; t += blockDim.x)
-      if (tile + t < n) s_tile[t + t / P.R] = ldg_f4(src + tile + t);
+    // staging row l = points [tile + l*R, tile + (l+1)*R): contiguous in the sweep, so every warp load is coalesced
+    for (int l = warp; l < 32; l += nwarp) {
+      const int first = tile + l * P.R, cnt = min(P.R, n - first);
+      if (stride == 4) {
+        for (int j = lane; j < cnt; j += 32) s_tile[l * (P.R + 1) + j] = ldg_f4(reinterpret_cast<const float4 *>(src) + first + j);
+      } else {
+        const float *rf = src + (size_t)first * 3;
+        for (int f = lane; f < cnt * 3; f += 32) sf[l * frow + f] = __ldg(rf + f);
+      }
+    }
     __syncthreads();
     for (int j = warp; j < P.R; j += nwarp) {
-      const int t = lane * P.R + j, i = tile + t;
+      const int i = tile + lane * P.R + j;
       if (i >= n) continue;
-      const float4 p = s_tile[t + lane];
+      float4 p;
+      if (stride == 4) {
+        p = s_tile[lane * (P.R + 1) + j];
+      } else {
+        const float *q = sf + lane * frow + 3 * j;
+        p = make_float4(q[0], q[1], q[2], 0.f);
+      }
       if (!finite3(p)) continue;  // pcl::removeNaNFromPointCloud (:59)
       int row, col;
       if (!project_rowcol(p.x, p.y, p.z, P, row, col)) continue;
@@ -95,7 +120,7 @@ __global__ void __launch_bounds__(256) ip_project_kernel(const float4 *__restric
   }
 }
 
-__global__ void __launch_bounds__(256) ip_gather_kernel(const float4 *__restrict__ raw, int *__restrict__ winner,
+__global__ void __launch_bounds__(256) ip_gather_kernel(const float *__restrict__ raw, int stride, int *__restrict__ winner,
                                                         float4 *__restrict__ cloud, float *__restrict__ range,
                                                         uint8_t *__restrict__ ground, int Nmax, IpDev P) {
   const int b = blockIdx.y;
@@ -106,7 +131,7 @@ __global__ void __launch_bounds__(256) ip_gather_kernel(const float4 *__restrict
     float r = ALEGO_EMPTY_RANGE;
     if (w >= 0) {
       winner[base + cell] = -1;  // ready for the next sweep
-      const float4 p = ldg_f4(raw + (size_t)b * Nmax + w);
+      const float4 p = load_point(raw + (size_t)b * Nmax * stride, w, stride);
       const int row = cell / P.C, col = cell - row * P.C;
       r = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);                      // (:99) float sum, float sqrt
       o = make_float4(p.x, p.y, p.z, (float)((double)row + (double)col / 10000.0));  // (:101)
@@ -327,7 +352,7 @@ __device__ __forceinline__ CellClass classify(int cell, int row, int col, const 
 
 __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat,
                                                           const uint8_t *__restrict__ ground, int4 *__restrict__ rowcnt,
-                                                          const float4 *__restrict__ raw, const int *__restrict__ n_pts,
+                                                          const float *__restrict__ raw, int stride, const int *__restrict__ n_pts,
                                                           float *orient, int Nmax, IpDev P) {
   const int b = blockIdx.y, row = blockIdx.x;
   const size_t base = (size_t)b * P.RC;
@@ -346,16 +371,16 @@ __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict_
   __syncthreads();
   if (row == 0) {  // first / last point that survives removeNaNFromPointCloud (:59,:62-63): scan inwards from both ends
     const int n = min(n_pts[b], Nmax);
-    const float4 *src = raw + (size_t)b * Nmax;
+    const float *src = raw + (size_t)b * Nmax * stride;
     for (int c0 = 0; c0 < n; c0 += blockDim.x) {
       const int i = c0 + threadIdx.x;
-      const bool f = i < n && finite3(src[i]);
+      const bool f = i < n && finite3(load_point(src, i, stride));
       if (f) atomicMin(&s_fv, i);
       if (__syncthreads_or(f)) break;
     }
     for (int c0 = n - 1; c0 >= 0; c0 -= blockDim.x) {
       const int i = c0 - threadIdx.x;
-      const bool f = i >= 0 && finite3(src[i]);
+      const bool f = i >= 0 && finite3(load_point(src, i, stride));
       if (f) atomicMax(&s_lv, i);
       if (__syncthreads_or(f)) break;
     }
@@ -368,7 +393,8 @@ __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict_
       float so = 0.f, eo = 0.f;
       const int fv = s_fv, lv = s_lv;
       if (lv >= 0 && fv <= lv) {
-        const float4 p0 = raw[(size_t)b * Nmax + fv], p1 = raw[(size_t)b * Nmax + lv];
+        const float *sw = raw + (size_t)b * Nmax * stride;
+        const float4 p0 = load_point(sw, fv, stride), p1 = load_point(sw, lv, stride);
         so = -(float)atan2((double)p0.y, (double)p0.x);
         eo = (float)((double)(-(float)atan2((double)p1.y, (double)p1.x)) + 2 * CUDART_PI);
         if ((double)(eo - so) > 3 * CUDART_PI) eo = (float)((double)eo - 2 * CUDART_PI);
@@ -491,9 +517,9 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
     proj_attr_set = true;
   }
   { LAUNCH(h, "ip_project");
-    ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(h->raw, h->n_pts, h->winner, h->Nmax, P); }
+    ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(reinterpret_cast<const float *>(h->raw), h->n_pts, h->winner, h->Nmax, h->in_stride, P); }
   { LAUNCH(h, "ip_gather");
-    ip_gather_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->raw, h->winner, h->cloud, h->range, h->ground, h->Nmax, P); }
+    ip_gather_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(reinterpret_cast<const float *>(h->raw), h->in_stride, h->winner, h->cloud, h->range, h->ground, h->Nmax, P); }
   const int gpairs = min(P.ground_scan_id, P.R - 1) * P.C;
   if (gpairs > 0) {
     LAUNCH(h, "ip_ground");
@@ -503,7 +529,7 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->parent, P); }
   { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ip_rowcount");
-    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->raw, h->n_pts, h->orient,
+    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, reinterpret_cast<const float *>(h->raw), h->in_stride, h->n_pts, h->orient,
                                                    h->Nmax, P); }
   { LAUNCH(h, "ip_compact");
     ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,

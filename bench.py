@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--map-corner", type=int, default=50000)
     ap.add_argument("--map-surf", type=int, default=200000)
     ap.add_argument("--cpu-sweeps", type=int, default=40, help="bounded CPU sample: sweeps per sequence")
+    ap.add_argument("--point-stride", type=int, default=3, choices=[3, 4],
+                    help="floats per input point: 3 = packed x,y,z (the path never reads the sensor intensity), 4 = x,y,z,intensity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -174,10 +176,11 @@ def run_reference(args, alego, P, rank, world):
 # algorithmic bytes per launch of the kernels that have a streaming model
 def algorithmic_bytes(name, st):
     pts, cells, kept, B = st["points"], st["cells"], st["kept"], st["B"]
+    pb = 4.0 * st["stride"]  # bytes per input point
     gfrac = st["ground_rows"] / st["R"]
     table = {
-        "ip_project": 20.0 * pts,                      # read 16 B/pt + 4 B winner atomic
-        "ip_gather": 4.0 * cells + 16.0 * pts + 21.0 * cells,  # winner + gathered point -> cloud(16) + range(4) + ground(1)
+        "ip_project": (pb + 4.0) * pts,                # read the point + 4 B winner atomic
+        "ip_gather": 4.0 * cells + pb * pts + 21.0 * cells,  # winner + gathered point -> cloud(16) + range(4) + ground(1)
         "ip_ground": (2 * 16.0 + 1.0) * cells * gfrac,
         "ccl_init": (4 + 1 + 4 + 8) * cells,
         "ccl_merge": 12.0 * cells,
@@ -222,13 +225,15 @@ def main():
     seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, rank=rank)
     g = alego.Alego(P, n_seq=B, device=local_rank)
     g.pipeline_config(lm_every=args.lm_every, rebuild_map_index_every_step=True)
+    g.set_point_stride(args.point_stride)
+    PS = args.point_stride
     for b in range(B):
         s = seqs[b % N_UNIQUE]
         g.lm_set_map(b, s["map_corner"], s["map_surf"])
     Nmax = g.max_points
     # pinned host sweep buffers, refilled per pass: A = sweeps [0,n), B = [n,2n), C = [2n,3n) of every sequence,
     # so LaserOdometry / LaserMapping always see consecutive sweeps of a trajectory
-    host = [alego.pinned_empty((B, Nmax, 4), np.float32) for _ in range(n_steps)]
+    host = [alego.pinned_empty((B, Nmax, PS), np.float32) for _ in range(n_steps)]
     host_n = [np.zeros(B, np.int32) for _ in range(n_steps)]
     pts_per_step = []
 
@@ -236,7 +241,7 @@ def main():
         for t in range(n_steps):
             for u in range(min(N_UNIQUE, B)):
                 sw = seqs[u]["sweeps"][first_sweep + t]
-                host[t][u::N_UNIQUE, :len(sw)] = sw
+                host[t][u::N_UNIQUE, :len(sw)] = sw[:, :PS]
                 host_n[t][u::N_UNIQUE] = len(sw)
             pts_per_step.append(int(host_n[t].sum()))
 
@@ -281,8 +286,9 @@ def main():
     # alego_pipeline_submit / _collect: every sweep is copied from pinned HOST memory inside the timed region (on the copy
     # stream, overlapping the previous pass) and every step's poses are read back to the host
     fill(n_steps)
-    for t in range(W):
-        g.pipeline_step(host[t], host_n[t], want_poses=True)
+    for t in range(W):  # warm-up through the same asynchronous API (its staging buffers are allocated on first use)
+        g.pipeline_submit(host[t], host_n[t])
+        g.pipeline_collect()
     barrier()
     t_host0 = time.perf_counter()
     g.timer_mark(2)
@@ -327,7 +333,7 @@ def main():
         value = scans / (ms_dev * 1e-3)
         e2e_value = scans / (ms_e2e * 1e-3)
         st = {"points": float(np.mean(pts_per_step)), "cells": float(B * P.n_scan * P.horizon_scan), "kept": kept, "B": B,
-              "ground_rows": min(P.ground_scan_id + 1, P.n_scan), "R": P.n_scan}
+              "ground_rows": min(P.ground_scan_id + 1, P.n_scan), "R": P.n_scan, "stride": PS}
         total_kernel_ms = sum(ms for _, ms in prof.values())
         kernels = {}
         for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
@@ -352,10 +358,11 @@ def main():
             "config": {"workload": "%s IP+LO+LM, local map %dk corner + %dk surf rebuilt-indexed every sweep, lm_every=%d" %
                                    (args.preset, args.map_corner // 1000, args.map_surf // 1000, args.lm_every),
                        "n_seq_per_gpu": B, "scans_per_step": B * world, "points_per_scan": st["points"] / B,
-                       "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 16 / 1e6),
+                       "point_stride_floats": PS,
+                       "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 4 * PS / 1e6),
                        "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 16 + B * 4), "d2h_bytes_per_step": B * 12 * 8,
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 4 * PS + B * 4), "d2h_bytes_per_step": B * 12 * 8,
                     "ms_per_step": ms_e2e / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
                     "h2d_probe_gbs": round(h2d_probe_gbs, 1),
                     "api": "alego_pipeline_submit/_collect, pinned host sweeps, 2 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},

@@ -104,13 +104,19 @@ int alego_synchronize(AlegoHandle *h);
 int alego_get_params(const AlegoHandle *h, AlegoParams *out);
 int alego_n_seq(const AlegoHandle *h);
 
+/* Layout of the sweep buffers handed to alego_ip_* / alego_stage_upload / alego_pipeline_*: 4 floats per point
+ * (x, y, z, intensity — the default, a decoded pcl::PointXYZI) or 3 (packed x, y, z).  The reference never reads the
+ * sensor intensity on this path (pcCB overwrites it with row + col/10000, imageProjection.cpp:101), so the packed form
+ * gives identical results with 25 % fewer bytes over PCIe.  Applies to every later upload. */
+int alego_set_point_stride(AlegoHandle *h, int floats_per_point);
+
 /* Pinned host memory for the sweep buffers (cudaMallocHost) so that the H2D copies are asynchronous. */
 void *alego_host_alloc(size_t bytes);
 void alego_host_free(void *p);
 
 /* ---- ImageProjection: replaces ImageProjection::pcCB + labelComponents
  *      (src/imageProjection.cpp:49-208, 210-316) -------------------------------------------------- */
-/* xyzi_host: [n_seq][max_points_per_scan][4] float32 (x,y,z,intensity) — the decoded
+/* xyzi_host: [n_seq][max_points_per_scan][stride] float32 (stride 4: x,y,z,intensity; 3: x,y,z) — the decoded
  * sensor_msgs::PointCloud2 of /lslidar_point_cloud; n_points[n_seq].  Copies H2D (async on the
  * handle's stream; pass pinned memory for true overlap) and runs the IP kernels. */
 int alego_ip_process(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);

@@ -112,6 +112,30 @@ def test_ip_edge_cases(alego, ob):
     g.close()
 
 
+def test_packed_xyz_input_matches_xyzi(alego, ob):
+    """alego_set_point_stride(3): 12-byte points give the same ImageProjection / feature results (with NaN holes too)."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    scans = make_scans(alego, P, [31, 32])
+    rng = np.random.default_rng(5)
+    scans[1] = scans[1].copy()
+    scans[1][rng.choice(len(scans[1]), 300, replace=False), rng.integers(0, 3, 300)] = np.nan
+    scans[1][0, 1] = np.nan
+    scans[1][-1, 0] = np.nan
+    g = alego.Alego(P, n_seq=2)
+    g.set_point_stride(3)
+    buf, n = g.pack_scans(scans)
+    assert buf.shape[-1] == 3
+    g.ip_process(buf, n)
+    g.lo_extract()
+    for b, s in enumerate(scans):
+        o = ob.Oracle(P)
+        o.ip(s)
+        o.lo_features()
+        check_ip(g, o, b, "packed%d" % b)
+        check_features(g, o, b, "packed%d" % b)
+    g.close()
+
+
 def test_ip_zero_points_is_not_an_error(alego):
     P = alego.default_params(alego.PRESET_VLP16_1800)
     g = alego.Alego(P, n_seq=2)
