@@ -37,13 +37,13 @@ __global__ void init_state_kernel(double *lo_params, double *t_w, double *r_w, i
   use_ext[b] = 0;
 }
 
-__global__ void pose_pack_kernel(const Pose *m2l, const double *lm_params, const double *t_w, double *pose_out, int B) {
+__global__ void pose_pack_kernel(const Pose *m2l, const double *lm_params, const Pose *lo_pose, double *pose_out, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double *po = pose_out + b * 12;
   for (int q = 0; q < 3; ++q) po[q] = m2l[b].t[q];
   for (int q = 0; q < 6; ++q) po[3 + q] = lm_params[b * 6 + q];
-  for (int q = 0; q < 3; ++q) po[9 + q] = t_w[b * 3 + q];
+  for (int q = 0; q < 3; ++q) po[9 + q] = lo_pose[b].t[q];
 }
 
 int check(AlegoHandle *h, int seq) {
@@ -52,8 +52,18 @@ int check(AlegoHandle *h, int seq) {
   return ALEGO_OK;
 }
 
+// The pipeline runs its LaserMapping stage on the side stream: anything that reads results or continues stage by stage on
+// the main stream first makes the main stream wait for what the side stream has been given.
+int join_side(AlegoHandle *h) {
+  if (!h->side_busy) return ALEGO_OK;
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side_tail, 0));
+  h->side_busy = false;
+  return ALEGO_OK;
+}
+
 int d2h(AlegoHandle *h, void *dst, const void *src, size_t bytes) {
   if (!bytes) return ALEGO_OK;
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return ALEGO_OK;
@@ -138,6 +148,9 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   for (auto &e : h->timer) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lo_done, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side_tail, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lm_done[k], cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_consumed[k], cudaEventDisableTiming));
@@ -167,12 +180,17 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   DMALLOC(h, h->end_ring, B * R);
   DMALLOC(h, h->M, B);
   h->out_cap = std::max(1, (h->R - std::min(h->P.ground_scan_id + 1, h->R))) * ((h->C + 4) / 5);
-  DMALLOC(h, h->outlier, B * h->out_cap);
-  DMALLOC(h, h->n_outlier, B);
+  for (int k = 0; k < 2; ++k) {
+    DMALLOC(h, h->outlier_buf[k], B * h->out_cap);
+    DMALLOC(h, h->n_outlier_buf[k], B);
+    CUDA_TRY(h, cudaMemsetAsync(h->n_outlier_buf[k], 0, B * sizeof(int), h->stream));
+    DMALLOC(h, h->o2l_lo[k], B);
+  }
+  h->outlier = h->outlier_buf[0];
+  h->n_outlier = h->n_outlier_buf[0];
   DMALLOC(h, h->orient, B * 4);
   CUDA_TRY(h, cudaMemsetAsync(h->winner, 0xFF, B * RC * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->M, 0, B * sizeof(int), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->n_outlier, 0, B * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->n_pts, 0, B * sizeof(int), h->stream));
   // features
   DMALLOC(h, h->curv, B * RC);
@@ -254,6 +272,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   h->lm_scan_is_external.assign(B, 0);
   init_state_kernel<<<div_up(n_seq, 128), 128, 0, h->stream>>>(h->lo_params, h->t_w, h->r_w, h->lo_init, h->lm_params, h->m2o, h->o2l,
                                                                h->m2l, h->lm_use_ext, n_seq);
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaMemcpyAsync(h->o2l_lo[k], h->o2l, B * sizeof(Pose), cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return ALEGO_OK;
@@ -276,13 +295,17 @@ void alego_destroy(AlegoHandle *h) {
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_lo_done) cudaEventDestroy(h->ev_lo_done);
+  if (h->ev_side_tail) cudaEventDestroy(h->ev_side_tail);
+  for (int k = 0; k < 2; ++k)
+    if (h->ev_lm_done[k]) cudaEventDestroy(h->ev_lm_done[k]);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto p : h->stage_raw) cudaFree(p);
   for (auto p : h->stage_n) cudaFree(p);
   void *ptrs[] = {h->raw_own, h->n_pts_own, h->winner, h->cloud, h->range, h->ground, h->parent, h->comp_stat,
                   h->comp_id, h->label, h->rowcnt, h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring, h->end_ring,
-                  h->M, h->outlier, h->n_outlier, h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys,
+                  h->M, h->outlier_buf[0], h->outlier_buf[1], h->n_outlier_buf[0], h->n_outlier_buf[1], h->o2l_lo[0], h->o2l_lo[1], h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,
                   h->n_feat, h->sharp, h->flat, h->lf_stage, h->vox_sort, h->less_sharp[0], h->less_sharp[1], h->less_flat[0],
                   h->less_flat[1], h->ls_ring_off[0], h->ls_ring_off[1], h->lf_ring_off[0], h->lf_ring_off[1], h->lo_pose, h->az_stage, h->az_pts[0], h->az_pts[1], h->az_off[0], h->az_off[1], h->lo_params, h->t_w,
@@ -310,6 +333,7 @@ void alego_destroy(AlegoHandle *h) {
 const char *alego_last_error(const AlegoHandle *h) { return h ? h->err.c_str() : "null handle"; }
 int alego_synchronize(AlegoHandle *h) {
   if (!h) return ALEGO_BAD_ARG;
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return ALEGO_OK;
 }
@@ -392,12 +416,20 @@ static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyz
   return ALEGO_OK;
 }
 
-int alego_ip_run(AlegoHandle *h) {
-  if (!h) return ALEGO_BAD_ARG;
-  CUDA_TRY(h, cudaSetDevice(h->dev));
+static int ip_run_internal(AlegoHandle *h) {
+  // the outlier cloud travels to LaserMapping with the feature clouds of the same sweep: same buffer parity
+  h->outlier = h->outlier_buf[h->cur];
+  h->n_outlier = h->n_outlier_buf[h->cur];
   const int rc = ip_run_device(h, h->want_labels);
   if (rc == ALEGO_OK) { h->stage_ip_done = true; h->stage_feat_done = false; }
   return rc;
+}
+
+int alego_ip_run(AlegoHandle *h) {
+  if (!h) return ALEGO_BAD_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
+  return ip_run_internal(h);
 }
 
 int alego_ip_process(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points) {
@@ -442,6 +474,7 @@ int alego_lo_extract(AlegoHandle *h) {
   if (!h) return ALEGO_BAD_ARG;
   if (!h->stage_ip_done) { h->err = "alego_lo_extract before alego_ip_process"; return ALEGO_NOT_READY; }
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   const int rc = lo_extract_device(h);
   if (rc == ALEGO_OK) { h->stage_feat_done = true; h->feat_buf = h->cur; }
   return rc;
@@ -474,6 +507,7 @@ int alego_lo_scan2scan(AlegoHandle *h, AlegoSolveReport *reports) {
   if (!h) return ALEGO_BAD_ARG;
   if (!h->stage_feat_done) { h->err = "alego_lo_scan2scan before alego_lo_extract"; return ALEGO_NOT_READY; }
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   int rc = lo_scan2scan_device(h);
   if (rc != ALEGO_OK) return rc;
   h->stage_feat_done = false;  // the features were consumed (they are now the "last" clouds)
@@ -499,6 +533,7 @@ int alego_lo_set_params(AlegoHandle *h, int seq, const double params[6]) {
   int rc = check(h, seq);
   if (rc != ALEGO_OK || !params) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   CUDA_TRY(h, cudaMemcpyAsync(h->lo_params + seq * 6, params, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return ALEGO_OK;
@@ -527,11 +562,12 @@ int alego_lm_set_map(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t 
   if (rc != ALEGO_OK) return rc;
   if (n_corner < 0 || n_surf < 0 || (n_corner && !corner_xyzi) || (n_surf && !surf_xyzi)) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   const int old_c = h->map_cap_c, old_s = h->map_cap_s;
   if ((rc = realloc_keep(h, &h->map_corner, &h->map_cap_c, n_corner)) != ALEGO_OK) return rc;
   if ((rc = realloc_keep(h, &h->map_surf, &h->map_cap_s, n_surf)) != ALEGO_OK) return rc;
-  if (h->map_cap_c != old_c && (rc = grid_alloc(h, &h->g_map_corner, h->map_cap_c, 1.01f)) != ALEGO_OK) return rc;
-  if (h->map_cap_s != old_s && (rc = grid_alloc(h, &h->g_map_surf, h->map_cap_s, 1.01f)) != ALEGO_OK) return rc;
+  if (h->map_cap_c != old_c && (rc = grid_alloc(h, &h->g_map_corner, h->map_cap_c, 1.01f, 1)) != ALEGO_OK) return rc;
+  if (h->map_cap_s != old_s && (rc = grid_alloc(h, &h->g_map_surf, h->map_cap_s, 1.01f, 1)) != ALEGO_OK) return rc;
   if (n_corner) CUDA_TRY(h, cudaMemcpyAsync(h->map_corner + (size_t)seq * h->map_cap_c, corner_xyzi, (size_t)n_corner * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
   if (n_surf) CUDA_TRY(h, cudaMemcpyAsync(h->map_surf + (size_t)seq * h->map_cap_s, surf_xyzi, (size_t)n_surf * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->n_map_corner + seq, &n_corner, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -547,6 +583,7 @@ int alego_lm_set_scan(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t
   if (rc != ALEGO_OK) return rc;
   if (n_corner < 0 || n_surf < 0 || n_outlier < 0) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   if ((rc = realloc_keep(h, &h->lm_in_corner, &h->lm_cap_c, n_corner)) != ALEGO_OK) return rc;
   if ((rc = realloc_keep(h, &h->lm_in_surf, &h->lm_cap_s, n_surf)) != ALEGO_OK) return rc;
   if ((rc = realloc_keep(h, &h->lm_in_outlier, &h->lm_cap_o, n_outlier)) != ALEGO_OK) return rc;
@@ -566,6 +603,7 @@ int alego_lm_set_odom(AlegoHandle *h, int seq, const double t[3], const double r
   int rc = check(h, seq);
   if (rc != ALEGO_OK || !t || !r) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   Pose p;
   std::memcpy(p.t, t, sizeof p.t);
   std::memcpy(p.R, r, sizeof p.R);
@@ -577,9 +615,10 @@ int alego_lm_set_odom(AlegoHandle *h, int seq, const double t[3], const double r
 int alego_lm_scan2map(AlegoHandle *h, AlegoSolveReport *reports) {
   if (!h) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   int rc = lm_ensure_buffers(h, 0, 0, 0);
   if (rc != ALEGO_OK) return rc;
-  rc = lm_scan2map_device(h, h->lm_guard, true);
+  rc = lm_scan2map_device(h, h->lm_guard, true, false);
   if (rc != ALEGO_OK) return rc;
   if (reports) {
     if ((rc = d2h(h, reports, h->lm_report, h->B * sizeof(AlegoSolveReport))) != ALEGO_OK) return rc;
@@ -608,6 +647,7 @@ int alego_lm_set_params(AlegoHandle *h, int seq, const double params[6]) {
   int rc = check(h, seq);
   if (rc != ALEGO_OK || !params) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
   CUDA_TRY(h, cudaMemcpyAsync(h->lm_params + seq * 6, params, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return ALEGO_OK;
@@ -639,51 +679,76 @@ int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_ev
   if (!h || lm_every < 0) return ALEGO_BAD_ARG;
   h->lm_every = lm_every;
   h->rebuild_map_every_step = rebuild_map_index_every_step != 0;
-  h->overlap_map_build = use_cuda_graph >= 0;  // third argument: < 0 disables the side-stream map-index build (debugging); graphs reserved
+  h->overlap_lm = use_cuda_graph >= 0;  // third argument: < 0 keeps LaserMapping on the main stream (no overlap with the next sweep's front end)
   return ALEGO_OK;
 }
 
 // IP -> LO -> LM on whatever h->raw / h->n_pts point at; everything is enqueued, nothing waits.
+//
+// Two streams, like the reference's separate nodes: ImageProjection + LaserOdometry of sweep t on the main stream,
+// LaserMapping (local-map index build + scan-to-map) of sweep t on the side stream, so that mapping of sweep t overlaps
+// the front end of sweep t+1.  What crosses from the front end to mapping is double-buffered by sweep parity (the
+// less-sharp / less-flat clouds, the outlier cloud, LaserOdometry's pose); the front end of sweep t+2 waits for the
+// mapping of sweep t before it overwrites that parity.
 static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   int rc;
   bool any_ext = false;
   for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
   if (any_ext) {  // the pipeline feeds LaserMapping from LaserOdometry's device clouds
+    if ((rc = join_side(h)) != ALEGO_OK) return rc;
     CUDA_TRY(h, cudaMemsetAsync(h->lm_use_ext, 0, h->B * sizeof(int), h->stream));
     std::fill(h->lm_scan_is_external.begin(), h->lm_scan_is_external.end(), 0);
   }
   const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
-  // The local-map index does not depend on the sweep: rebuild it (the reference rebuilds its kd-trees every mapped
-  // frame, laserMapping.cpp:356-357) on the side stream while ImageProjection / LaserOdometry run on the main one.
-  cudaEvent_t map_ev = nullptr;
-  if (run_lm && h->overlap_map_build && !h->profiling && (h->rebuild_map_every_step || !h->map_index_valid)) {
-    CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));  // after the previous pass's associations (the index is rebuilt in place)
-    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    h->launch_stream = h->side_stream;
-    rc = lm_build_map_index(h);
-    h->launch_stream = nullptr;
-    if (rc != ALEGO_OK) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
-    map_ev = h->ev_join;
-  }
-  if ((rc = alego_ip_run(h)) != ALEGO_OK) return rc;
+  const bool overlap = h->overlap_lm && !h->profiling;
+  const int par = h->cur;  // buffer parity of this sweep's clouds
+  if (run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
+  // ---- front end (main stream)
+  if (overlap && h->lm_done_valid[par]) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_lm_done[par], 0));
+  if (!overlap && (rc = join_side(h)) != ALEGO_OK) return rc;
+  if ((rc = ip_run_internal(h)) != ALEGO_OK) return rc;
   // ImageProjection is the only reader of the raw sweep: its staging buffer may be refilled from here on
   if (consumed_ev) CUDA_TRY(h, cudaEventRecord(consumed_ev, h->stream));
-  if ((rc = alego_lo_extract(h)) != ALEGO_OK) return rc;
+  if ((rc = lo_extract_device(h)) != ALEGO_OK) return rc;
+  h->feat_buf = h->cur;
   if ((rc = lo_scan2scan_device(h)) != ALEGO_OK) return rc;
   h->stage_feat_done = false;
+  // ---- mapping (side stream when overlapped)
+  cudaStream_t ms = h->stream;
+  if (overlap) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_lo_done, h->stream));
+    ms = h->side_stream;
+    h->launch_stream = ms;
+  }
+  // The local-map index does not depend on the sweep: the reference rebuilds its kd-trees every mapped frame
+  // (laserMapping.cpp:356-357); on the side stream that happens before the wait for the front end.
+  if (run_lm && (h->rebuild_map_every_step || !h->map_index_valid)) {
+    rc = lm_build_map_index(h);
+    if (rc != ALEGO_OK) { h->launch_stream = nullptr; return rc; }
+  }
+  if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(ms, h->ev_lo_done, 0));
   if (run_lm) {
-    if ((rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
-    if ((rc = lm_scan2map_device(h, h->lm_guard, true, map_ev)) != ALEGO_OK) return rc;
+    rc = lm_scan2map_device(h, h->lm_guard, true, true);
   } else {
-    if (map_ev) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, map_ev, 0));
     LAUNCH(h, "pose_pack");
-    pose_pack_kernel<<<div_up(h->B, 128), 128, 0, h->stream>>>(h->m2l, h->lm_params, h->t_w, h->d_pose, h->B);
+    pose_pack_kernel<<<div_up(h->B, 128), 128, 0, ms>>>(h->m2l, h->lm_params, h->o2l_lo[par], h->d_pose, h->B);
+    rc = ALEGO_OK;
+  }
+  h->launch_stream = nullptr;
+  if (rc != ALEGO_OK) return rc;
+  if (overlap) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_lm_done[par], ms));
+    h->lm_done_valid[par] = true;
+    CUDA_TRY(h, cudaEventRecord(h->ev_side_tail, ms));
+    h->side_busy = true;
   }
   ++h->scan_count;
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }
+
+// stream that produced d_pose of the pass enqueued last
+static cudaStream_t pose_stream(AlegoHandle *h) { return (h->overlap_lm && !h->profiling) ? h->side_stream : h->stream; }
 
 int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out) {
   if (!h) return ALEGO_BAD_ARG;
@@ -695,8 +760,9 @@ int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n
   }
   if ((rc = pipeline_enqueue(h)) != ALEGO_OK) return rc;
   if (poses_out) {
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaStream_t ps = pose_stream(h);
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, ps));
+    CUDA_TRY(h, cudaStreamSynchronize(ps));
     std::memcpy(poses_out, h->h_pose, (size_t)h->B * 12 * sizeof(double));
   }
   return ALEGO_OK;
@@ -728,8 +794,10 @@ int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t 
   h->n_pts = h->n_pts_slot[slot];
   if ((rc = pipeline_enqueue(h, h->ev_consumed[slot])) != ALEGO_OK) return rc;
   h->consumed_valid[slot] = true;
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_pose_slot[slot], h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaEventRecord(h->ev_pose[slot], h->stream));
+  cudaStream_t ps = pose_stream(h);
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_pose_slot[slot], h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, ps));
+  CUDA_TRY(h, cudaEventRecord(h->ev_pose[slot], ps));
+  if (ps == h->side_stream) CUDA_TRY(h, cudaEventRecord(h->ev_side_tail, ps));
   ++h->n_submitted;
   return ALEGO_OK;
 }
@@ -755,6 +823,7 @@ int alego_voxel_grid(AlegoHandle *h, const float *xyzi, int32_t n, float leaf, f
 
 int alego_timer_mark(AlegoHandle *h, int slot) {
   if (!h || slot < 0 || slot >= 16) return ALEGO_BAD_ARG;
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;  // the mark covers both streams
   CUDA_TRY(h, cudaEventRecord(h->timer[slot], h->stream));
   return ALEGO_OK;
 }

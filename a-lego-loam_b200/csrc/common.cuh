@@ -41,10 +41,17 @@ struct AlegoHandle {
   int dev = 0, B = 0, Nmax = 0, R = 0, C = 0, RC = 0;
   int in_stride = 4;  // floats per input point: 4 = x,y,z,intensity; 3 = packed x,y,z (alego_set_point_stride)
   cudaStream_t stream = nullptr;
-  cudaStream_t side_stream = nullptr;    // map-index build overlapped with IP + LO (alego_pipeline_step)
+  cudaStream_t side_stream = nullptr;    // LaserMapping stage of the pipeline (map-index build + scan-to-map of sweep t) overlapped
+                                         // with ImageProjection + LaserOdometry of sweep t+1, like the reference's three nodes
   cudaStream_t copy_stream = nullptr;    // H2D of the next sweep overlapped with the current pass (alego_pipeline_submit)
   cudaStream_t launch_stream = nullptr;  // when set, LAUNCH() / grid_build() target this stream instead of `stream`
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_lo_done = nullptr;              // main stream: LaserOdometry of the sweep finished (its clouds are final)
+  cudaEvent_t ev_lm_done[2] = {nullptr, nullptr};  // side stream: LaserMapping has consumed the clouds of buffer parity k
+  bool lm_done_valid[2] = {false, false};
+  cudaEvent_t ev_side_tail = nullptr;            // side stream: everything enqueued there so far
+  bool side_busy = false;                        // work was enqueued on the side stream since the last join
+  bool overlap_lm = true;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_pose[2] = {nullptr, nullptr};
   bool consumed_valid[2] = {false, false};
   bool overlap_map_build = true;
@@ -93,7 +100,9 @@ struct AlegoHandle {
   int *start_ring = nullptr;   // [B][R]
   int *end_ring = nullptr;     // [B][R]
   int *M = nullptr;            // [B]
-  float4 *outlier = nullptr;   // [B][out_cap]
+  float4 *outlier = nullptr;   // [B][out_cap]  (points at outlier_buf[cur] of the sweep ImageProjection last processed)
+  float4 *outlier_buf[2] = {nullptr, nullptr};
+  int *n_outlier_buf[2] = {nullptr, nullptr};
   int out_cap = 0;
   int *n_outlier = nullptr;    // [B]
   float *orient = nullptr;     // [B][4] start, end, diff
@@ -157,6 +166,7 @@ struct AlegoHandle {
   int *lm_n = nullptr;         // [B][8] corner_ds, surf_ds, outlier_ds, surf_total, surf_total_ds
   double *lm_params = nullptr; // [B][6]
   Pose *m2o = nullptr, *o2l = nullptr, *m2l = nullptr;  // [B]
+  Pose *o2l_lo[2] = {nullptr, nullptr};  // [B] (t_w_cur_, r_w_cur_) of LaserOdometry after the sweep held in buffer parity k
   double *lm_edge = nullptr;   // [B][ds_cap_c][10]: valid, cp3, lpj3, lpl3
   double *lm_plane = nullptr;  // [B][ds_cap_s+o][8]: valid, cp3, n3, d
   int *lm_nn_c = nullptr, *lm_nn_s = nullptr;  // [B][cap][5] map indices of the gated 5-NN (first = -1: none)

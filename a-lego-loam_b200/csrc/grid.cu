@@ -61,12 +61,15 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict
 
 }  // namespace
 
-int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell) {
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2) {
   grid_free(g);
   g->cap = cap;
   g->cell = cell;
+  // buckets: next_pow2(cap / 2) << table_factor_log2.  A query reads whole buckets, so every point that merely collides
+  // with a neighbour cell is a wasted candidate: the big local-map grids use more buckets than points.
   int T = next_pow2(cap > 2048 ? cap / 2 : 1024);
   if (T < 1024) T = 1024;
+  T <<= table_factor_log2;
   g->table_size = T;
   CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)h->B * (T + 4) * sizeof(int)));
   CUDA_TRY(h, cudaMalloc(&g->sorted, (size_t)h->B * cap * sizeof(float4)));

@@ -21,7 +21,7 @@ __device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const f
   return r;
 }
 
-int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell);
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2 = 0);
 void grid_free(GridIndex *g);
 // pts: [B] clouds `pts_stride` points apart; point count of sequence b = n_ptr[b * n_stride]
 // pack_ring: store int(intensity) (the ring id of LaserOdometry's feature clouds) in bits 24..30 of the index word

@@ -50,13 +50,10 @@ __device__ __forceinline__ void mat3_mul_d(const double *A, const double *Bm, do
 }
 
 // transformAssociateToMap (:188-192); in pipeline mode odom2laser is LaserOdometry's (t_w_cur_, r_w_cur_)
-__global__ void lm_prepare_kernel(const int *use_ext, const double *t_w, const double *r_w, Pose *o2l, const Pose *m2o, Pose *m2l, int B) {
+__global__ void lm_prepare_kernel(const int *use_ext, const Pose *lo_pose, Pose *o2l, const Pose *m2o, Pose *m2l, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  if (!use_ext[b]) {
-    for (int q = 0; q < 3; ++q) o2l[b].t[q] = t_w[b * 3 + q];
-    for (int q = 0; q < 9; ++q) o2l[b].R[q] = r_w[b * 9 + q];
-  }
+  if (!use_ext[b]) o2l[b] = lo_pose[b];  // LaserOdometry's (t_w_cur_, r_w_cur_) after the sweep being mapped
   const Pose &mo = m2o[b];
   const Pose &ol = o2l[b];
   for (int r = 0; r < 3; ++r) m2l[b].t[r] = mo.R[r * 3] * ol.t[0] + mo.R[r * 3 + 1] * ol.t[1] + mo.R[r * 3 + 2] * ol.t[2] + mo.t[r];
@@ -398,7 +395,7 @@ __global__ void __launch_bounds__(256)
 lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restrict__ plane, int pcap, const int *__restrict__ lm_n,
                 const int *__restrict__ guard, double *lm_params, Pose *m2o, const Pose *o2l, Pose *m2l, AlegoSolveReport *report,
                 double *trace, int *trace_n, int trace_cap, int outer_iters, int max_iters, double huber_a, double *pose_out,
-                const double *t_w) {
+                const Pose *lo_pose) {
   const int b = blockIdx.x;
   __shared__ LmShared sh;
   __shared__ int s_red[34];
@@ -457,7 +454,7 @@ lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restr
       double *po = pose_out + b * 12;
       for (int q = 0; q < 3; ++q) po[q] = ml.t[q];
       for (int q = 0; q < 6; ++q) po[3 + q] = x[q];
-      for (int q = 0; q < 3; ++q) po[9 + q] = t_w ? t_w[b * 3 + q] : 0.0;
+      for (int q = 0; q < 3; ++q) po[9 + q] = lo_pose ? lo_pose[b].t[q] : 0.0;
     }
   }
 }
@@ -473,9 +470,9 @@ static LmInputs make_inputs(AlegoHandle *h) {
   in.ext_n = h->lm_in_n;
   in.use_ext = h->lm_use_ext;
   const int buf = 1 - h->cur;  // lo_scan2scan_device flipped the buffers: the sweep just processed is in 1-cur
-  in.lo_corner = h->less_sharp[buf]; in.lo_surf = h->less_flat[buf]; in.lo_outlier = h->outlier;
+  in.lo_corner = h->less_sharp[buf]; in.lo_surf = h->less_flat[buf]; in.lo_outlier = h->outlier_buf[buf];
   in.lo_cap_c = h->R * 120; in.lo_cap_s = h->RC; in.lo_cap_o = h->out_cap;
-  in.lo_n_corner = h->ls_ring_off[buf]; in.lo_n_surf = h->lf_ring_off[buf]; in.lo_n_outlier = h->n_outlier;
+  in.lo_n_corner = h->ls_ring_off[buf]; in.lo_n_surf = h->lf_ring_off[buf]; in.lo_n_outlier = h->n_outlier_buf[buf];
   in.R = h->R;
   return in;
 }
@@ -489,14 +486,14 @@ int lm_build_map_index(AlegoHandle *h) {
   return ALEGO_OK;
 }
 
-int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEvent_t map_index_event) {
+int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool index_ready) {
   const int B = h->B;
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->launch_stream ? h->launch_stream : h->stream;
   if (!h->map_corner || !h->map_surf) { h->err = "alego_lm_scan2map: no local map (call alego_lm_set_map)"; return ALEGO_NOT_READY; }
   int rc = lm_ensure_ds_buffers(h, 0, 0, 0);
   if (rc != ALEGO_OK) return rc;
   const LmInputs in = make_inputs(h);
-  { LAUNCH(h, "lm_prepare"); lm_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_use_ext, h->t_w, h->r_w, h->o2l, h->m2o, h->m2l, B); }
+  { LAUNCH(h, "lm_prepare"); lm_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_use_ext, h->o2l_lo[1 - h->cur], h->o2l, h->m2o, h->m2l, B); }
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(lm_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
@@ -512,9 +509,7 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEven
     lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_SMEM, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
         (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
         h->lm_n, sort_c, sort_s, sort_o, cc, cs + co, co); }
-  if (map_index_event) {  // built concurrently on the side stream (alego_pipeline_step)
-    CUDA_TRY(h, cudaStreamWaitEvent(s, map_index_event, 0));
-  } else if (h->rebuild_map_every_step || !h->map_index_valid) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
+  if (!index_ready && (h->rebuild_map_every_step || !h->map_index_valid)) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
     rc = lm_build_map_index(h);
     if (rc != ALEGO_OK) return rc;
   }
@@ -534,7 +529,7 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, cudaEven
   { LAUNCH(h, "lm_solve");
     lm_solve_kernel<<<B, 256, 0, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
         h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
-        write_pose ? h->d_pose : nullptr, h->t_w); }
+        write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur]); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

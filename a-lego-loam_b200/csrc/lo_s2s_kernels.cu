@@ -153,6 +153,15 @@ __device__ __forceinline__ void az_scan_ring(const float4 *__restrict__ az, cons
   }
 }
 
+// (t_w_cur_, r_w_cur_) after this sweep, kept per buffer parity: LaserMapping of sweep t reads it while LaserOdometry of
+// sweep t+1 already integrates the next step (laserMapping.cpp:154-164 receives it as the /odom/lidar message)
+__global__ void lo_snapshot_kernel(const double *__restrict__ t_w, const double *__restrict__ r_w, Pose *__restrict__ snap, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int q = 0; q < 3; ++q) snap[b].t[q] = t_w[b * 3 + q];
+  for (int q = 0; q < 9; ++q) snap[b].R[q] = r_w[b * 9 + q];
+}
+
 // params_ -> (R, t) of transformToStart, once per sequence instead of six double sin/cos per query
 __global__ void lo_pose_kernel(const double *__restrict__ lo_params, Pose *__restrict__ lo_pose, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,6 +419,7 @@ int lo_scan2scan_device(AlegoHandle *h) {
     lo_solve_kernel<<<B, 256, 0, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
                                       h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub); }
+  { LAUNCH(h, "lo_snapshot"); lo_snapshot_kernel<<<div_up(B, 128), 128, 0, s>>>(h->t_w, h->r_w, h->o2l_lo[cur], B); }
   // the current clouds become the targets of the next sweep (:531-534): index them, then flip the buffers
   int rc = grid_build(h, &h->g_surf_last, h->less_flat[cur], (size_t)RC, h->lf_ring_off[cur] + R, R + 1, "surf_last");
   if (rc != ALEGO_OK) return rc;
