@@ -187,6 +187,7 @@ _DEBUG_DTYPES = {
     "lm_params": np.float64, "lm_corner_ds": np.float32, "lm_surf_ds": np.float32, "lm_outlier_ds": np.float32,
     "lm_surf_total_ds": np.float32, "lm_edge": np.float64, "lm_plane": np.float64, "t_map2laser": np.float64,
     "r_map2laser": np.float64, "t_map2odom": np.float64, "r_map2odom": np.float64,
+    "lm_report": np.uint8, "lo_report": np.uint8,
 }
 _DEBUG_COLS = {"full_cloud": 4, "segmented_cloud": 4, "outlier_cloud": 4, "sharp": 4, "flat": 4, "less_sharp": 4, "less_flat": 4,
                "corner_last": 4, "surf_last": 4, "lo_surf_corr": 4, "lo_corner_corr": 3, "lo_trace": 7, "lm_trace": 7,
@@ -415,6 +416,11 @@ class Alego:
                 raise AlegoError("debug_get(%s) rc=%d: %s" % (name, got, self.L.alego_last_error(self.h).decode()))
         cols = _DEBUG_COLS.get(name)
         return a.reshape(-1, cols) if cols else a
+
+    def solve_report(self, stage, seq=0):
+        """AlegoSolveReport of the last LaserOdometry ("lo") / LaserMapping ("lm") solve of sequence seq, as a dict."""
+        raw = self.debug(stage + "_report", seq)
+        return AlegoSolveReport.from_buffer_copy(raw.tobytes()).as_dict()
 
 
 def pinned_empty(shape, dtype):

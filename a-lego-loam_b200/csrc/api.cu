@@ -917,6 +917,8 @@ int64_t alego_debug_get(AlegoHandle *h, const char *name, int seq, void *dst, si
     src = h->lm_trace + (size_t)seq * h->lm_trace_cap * 7; bytes = (size_t)n * 56;
   }
   else if (s == "lm_params") { src = h->lm_params + seq * 6; bytes = 48; }
+  else if (s == "lm_report") { src = h->lm_report + seq; bytes = sizeof(AlegoSolveReport); }  // of the last mapped sweep
+  else if (s == "lo_report") { src = h->lo_report + seq; bytes = sizeof(AlegoSolveReport); }
   else if (s == "lm_corner_ds") { src = h->lm_corner_ds + (size_t)seq * h->ds_cap_c; bytes = (size_t)lmn[0] * 16; }
   else if (s == "lm_surf_ds") { src = h->lm_surf_ds + (size_t)seq * h->ds_cap_s; bytes = (size_t)lmn[1] * 16; }
   else if (s == "lm_outlier_ds") { src = h->lm_outlier_ds + (size_t)seq * h->ds_cap_o; bytes = (size_t)lmn[2] * 16; }

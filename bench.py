@@ -49,11 +49,27 @@ def parse():
     ap.add_argument("--cpu-sweeps", type=int, default=40, help="bounded CPU sample: sweeps per sequence")
     ap.add_argument("--point-stride", type=int, default=3, choices=[3, 4],
                     help="floats per input point: 3 = packed x,y,z (the path never reads the sensor intensity), 4 = x,y,z,intensity")
+    ap.add_argument("--map-order", default="voxel", choices=["voxel", "generator"],
+                    help="order of the local-map clouds: 'voxel' = ascending PCL VoxelGrid index (x fastest), the order of the "
+                         "reference's corner_from_map_ds_ / surf_from_map_ds_ (VoxelGrid outputs, laserMapping.cpp:316-319); "
+                         "'generator' = the synthetic generator's structure-by-structure order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def make_sequences(alego, P, n_steps, n_corner, n_surf, rank=0):
+def voxel_order(cloud, leaf):
+    """Reorder a cloud the way pcl::VoxelGrid emits its output: ascending voxel index ijk0 + ijk1*dx + ijk2*dx*dy (stable)."""
+    if len(cloud) == 0:
+        return cloud
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(cloud[:, :3] * inv).astype(np.int64)
+    ijk -= ijk.min(axis=0)
+    d = ijk.max(axis=0) + 1
+    key = ijk[:, 0] + ijk[:, 1] * d[0] + ijk[:, 2] * d[0] * d[1]
+    return np.ascontiguousarray(cloud[np.argsort(key, kind="stable")])
+
+
+def make_sequences(alego, P, n_steps, n_corner, n_surf, rank=0, map_order="voxel"):
     """N_UNIQUE seeded sequences: n_steps consecutive sweeps each + a local map consistent with the world."""
     seqs = []
     for u in range(N_UNIQUE):
@@ -61,6 +77,8 @@ def make_sequences(alego, P, n_steps, n_corner, n_surf, rank=0):
         w = alego.SynthWorld(seed=seed)
         sweeps = [w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=1000 * seed + t) for t in range(n_steps)]
         corner, surf = w.make_map(n_corner, n_surf, seed=seed, radius=100.0)
+        if map_order == "voxel":
+            corner, surf = voxel_order(corner, P.lm_corner_leaf), voxel_order(surf, P.lm_surf_leaf)
         seqs.append({"sweeps": sweeps, "map_corner": corner, "map_surf": surf})
     return seqs
 
@@ -116,6 +134,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, n_seq, preset, stride):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this
+    same command line (profiles/*_ncu_traffic.json, newest first); None when no capture matches the configuration."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("n_seq") == n_seq and d.get("preset") == preset and d.get("point_stride") == stride:
+            v = d.get("dram_bytes_per_launch", {}).get(kernel)
+            if isinstance(v, (int, float)):
+                return float(v), os.path.basename(f)
+    return None, None
+
+
 def cpu_oracle_run(P_bytes, preset_id, sweeps, map_corner, map_surf, lm_every):
     """Time the oracle on one sequence (single thread). Returns seconds for len(sweeps) sweeps."""
     from oracle import binding as ob
@@ -142,7 +176,7 @@ def run_reference(args, alego, P, rank, world):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     n_sweeps = max(4, min(args.cpu_sweeps, 12))
-    seqs = make_sequences(alego, P, n_sweeps, args.map_corner, args.map_surf)
+    seqs = make_sequences(alego, P, n_sweeps, args.map_corner, args.map_surf, map_order=args.map_order)
     jobs = [(bytes(P), PRESETS[args.preset], seqs[c % N_UNIQUE]["sweeps"], seqs[c % N_UNIQUE]["map_corner"], seqs[c % N_UNIQUE]["map_surf"],
              args.lm_every) for c in range(cores)]
     ctx = mp.get_context("fork")
@@ -193,6 +227,25 @@ def algorithmic_bytes(name, st):
     return table.get(name)
 
 
+def lm_block(kernels, lm_reports, lo_reports, B):
+    """Second half of BASELINE.json's metric: scan-to-map LM ms/iter.  One LM iteration = one residual + Jacobian pass over the
+    sequence's correspondences + the 6x6 trust-region step; lm_solve runs the iterations of all B sequences of the batch in
+    lock-step (one CTA per sequence), so the per-launch time / iterations is the latency of ONE iteration of one sequence
+    while B of them are in flight, and / B its amortised cost."""
+    it = float(np.mean([r["iterations"] for r in lm_reports])) if lm_reports else 0.0
+    solve_ms = kernels.get("lm_solve", {}).get("ms_per_launch")
+    assoc_ms = sum(kernels[k]["ms_per_launch"] for k in ("lm_knn_corner", "lm_fit_corner", "lm_knn_surf", "lm_fit_surf") if k in kernels)
+    out = {"iters_per_scan2map": it, "edge_correspondences": float(np.mean([r["n_corner"] for r in lm_reports])) if lm_reports else 0.0,
+           "plane_correspondences": float(np.mean([r["n_surf"] for r in lm_reports])) if lm_reports else 0.0,
+           "lo_iters_per_scan": float(np.mean([r["iterations"] for r in lo_reports])) if lo_reports else 0.0}
+    if solve_ms and it > 0:
+        out["ms_per_iter"] = solve_ms / it
+        out["ms_per_iter_amortised_per_sequence"] = solve_ms / it / B
+        out["association_ms_per_batch"] = assoc_ms
+        out["unit"] = "ms per LM iteration (latency with %d sequences in lock-step); amortised = / %d" % (B, B)
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +275,7 @@ def main():
 
     K, W, B = args.steps, max(args.warmup, 3), args.n_seq
     n_steps = W + K
-    seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, rank=rank)
+    seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, rank=rank, map_order=args.map_order)
     g = alego.Alego(P, n_seq=B, device=local_rank)
     g.pipeline_config(lm_every=args.lm_every, rebuild_map_index_every_step=True)
     g.set_point_stride(args.point_stride)
@@ -322,6 +375,8 @@ def main():
     prof = g.profile()
     g.profile_enable(False)
     kept = float(np.mean([len(g.debug("segmentedCloudColInd", b)) for b in range(min(B, N_UNIQUE))])) * B
+    lm_reports = [g.solve_report("lm", b) for b in range(min(B, N_UNIQUE))]
+    lo_reports = [g.solve_report("lo", b) for b in range(min(B, N_UNIQUE))]
 
     times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -347,9 +402,12 @@ def main():
         dom_stream = next((k for k in kernels if kernels[k]["algorithmic_gbs"] is not None), None)
         ab = algorithmic_bytes(dom_stream, st)
         achieved = kernels[dom_stream]["algorithmic_gbs"]
+        traffic, traffic_src = ncu_traffic(dom_stream, B, args.preset, PS)
         roofline = {"bound": "hbm", "kernel": dom_stream, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "dominant_kernel_overall": dom,
-                    "named": {k: {"achieved": kernels[k]["algorithmic_gbs"], "frac": round(kernels[k]["algorithmic_gbs"] / peak, 4)}
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "dominant_kernel_overall": dom,
+                    "named": {k: {"achieved": kernels[k]["algorithmic_gbs"], "frac": round(kernels[k]["algorithmic_gbs"] / peak, 4),
+                                  "algorithmic_bytes_per_launch": algorithmic_bytes(k, st), "traffic": ncu_traffic(k, B, args.preset, PS)[0]}
                               for k in ("ip_project", "ip_gather", "lo_curv_occl") if k in kernels}}
         line = {
             "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -358,7 +416,7 @@ def main():
             "config": {"workload": "%s IP+LO+LM, local map %dk corner + %dk surf rebuilt-indexed every sweep, lm_every=%d" %
                                    (args.preset, args.map_corner // 1000, args.map_surf // 1000, args.lm_every),
                        "n_seq_per_gpu": B, "scans_per_step": B * world, "points_per_scan": st["points"] / B,
-                       "point_stride_floats": PS,
+                       "point_stride_floats": PS, "map_order": args.map_order,
                        "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 4 * PS / 1e6),
                        "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
             "clocks": clocks,
@@ -367,6 +425,7 @@ def main():
                     "h2d_probe_gbs": round(h2d_probe_gbs, 1),
                     "api": "alego_pipeline_submit/_collect, pinned host sweeps, 2 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
             "gpu_launches": int(launches),
+            "lm": lm_block(kernels, lm_reports, lo_reports, B),
             "roofline": roofline,
             "kernels": kernels,
             "kernel_ms_per_step": total_kernel_ms / K,

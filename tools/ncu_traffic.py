@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the uniquely named kernels of an
+`ncu --set full ... --page raw --csv` export -> JSON that bench.py reads for roofline.traffic.
+usage: ncu_traffic.py raw.csv n_seq preset point_stride > profiles/rNN_ncu_traffic.json"""
+import csv
+import json
+import re
+import sys
+
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units, data = rows[0], rows[1], rows[2:]
+idx = {h: i for i, h in enumerate(hdr)}
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def val(r, name):
+    return float(r[idx[name]].replace(",", "")) * scale.get(units[idx[name]], 1)
+
+
+acc = {}
+for r in data:
+    name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).split("::")[-1].replace("_kernel", "")
+    name = re.sub(r"<.*", "", name).replace("void ", "").strip()
+    t = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+    acc.setdefault(name, []).append(t)
+out = {"n_seq": int(sys.argv[2]), "preset": sys.argv[3], "point_stride": int(sys.argv[4]), "source": sys.argv[1],
+       "note": "kernels launched once per step: mean over the captured launches; others (grid_*, lm_knn, lm_fit, lm_voxel, lo_assoc, lo_solve) are listed per launch in order",
+       "dram_bytes_per_launch": {k: (sum(v) / len(v) if k in ("ip_project", "ip_gather", "ip_ground", "ccl_rows", "ccl_merge", "ccl_flatten", "ip_rowcount", "ip_compact", "lo_curv_occl", "lo_sort_segments", "lo_select", "lo_less_flat_voxel", "lo_finalize", "lm_solve") else v) for k, v in acc.items()}}
+print(json.dumps(out, indent=1))
