@@ -151,7 +151,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lo_done, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side_tail, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lm_done[k], cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < ALEGO_INFLIGHT; ++k) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_consumed[k], cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pose[k], cudaEventDisableTiming));
@@ -284,9 +284,11 @@ void alego_destroy(AlegoHandle *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->side_stream) cudaStreamSynchronize(h->side_stream);
-  if (h->raw_slot[1]) cudaFree(h->raw_slot[1]);
-  if (h->n_pts_slot[1]) cudaFree(h->n_pts_slot[1]);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 1; k < ALEGO_INFLIGHT; ++k) {  // slot 0 aliases raw_own / n_pts_own
+    if (h->raw_slot[k]) cudaFree(h->raw_slot[k]);
+    if (h->n_pts_slot[k]) cudaFree(h->n_pts_slot[k]);
+  }
+  for (int k = 0; k < ALEGO_INFLIGHT; ++k) {
     if (h->h_n_pts_slot[k]) cudaFreeHost(h->h_n_pts_slot[k]);
     if (h->h_pose_slot[k]) cudaFreeHost(h->h_pose_slot[k]);
     if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
@@ -769,17 +771,17 @@ int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n
 }
 
 // Asynchronous form: the H2D copy of sweep t+1 (copy stream, second device staging buffer) overlaps the pass over
-// sweep t.  At most two steps in flight; alego_pipeline_collect returns them in submission order.
+// sweep t.  At most ALEGO_INFLIGHT (3) steps in flight; alego_pipeline_collect returns them in submission order.
 int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points) {
   if (!h || !xyzi_host || !n_points) return ALEGO_BAD_ARG;
-  if (h->n_submitted - h->n_collected >= 2) { h->err = "alego_pipeline_submit: two steps already in flight (collect first)"; return ALEGO_NOT_READY; }
+  if (h->n_submitted - h->n_collected >= ALEGO_INFLIGHT) { h->err = "alego_pipeline_submit: three steps already in flight (collect first)"; return ALEGO_NOT_READY; }
   CUDA_TRY(h, cudaSetDevice(h->dev));
-  const int slot = (int)(h->n_submitted & 1);
+  const int slot = (int)(h->n_submitted % ALEGO_INFLIGHT);
   if (!h->raw_slot[slot]) {
     CUDA_TRY(h, cudaMalloc(&h->raw_slot[slot], (size_t)h->B * h->Nmax * sizeof(float4)));
     CUDA_TRY(h, cudaMalloc(&h->n_pts_slot[slot], (size_t)h->B * sizeof(int)));
   }
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < ALEGO_INFLIGHT; ++k) {
     if (!h->h_n_pts_slot[k]) CUDA_TRY(h, cudaMallocHost((void **)&h->h_n_pts_slot[k], (size_t)h->B * sizeof(int32_t)));
     if (!h->h_pose_slot[k]) CUDA_TRY(h, cudaMallocHost((void **)&h->h_pose_slot[k], (size_t)h->B * 12 * sizeof(double)));
   }
@@ -806,7 +808,7 @@ int alego_pipeline_collect(AlegoHandle *h, double *poses_out) {
   if (!h) return ALEGO_BAD_ARG;
   if (h->n_submitted == h->n_collected) { h->err = "alego_pipeline_collect: nothing in flight"; return ALEGO_NOT_READY; }
   CUDA_TRY(h, cudaSetDevice(h->dev));
-  const int slot = (int)(h->n_collected & 1);
+  const int slot = (int)(h->n_collected % ALEGO_INFLIGHT);
   CUDA_TRY(h, cudaEventSynchronize(h->ev_pose[slot]));
   if (poses_out) std::memcpy(poses_out, h->h_pose_slot[slot], (size_t)h->B * 12 * sizeof(double));
   ++h->n_collected;

@@ -12,6 +12,7 @@
 #include "../../include/alego_b200.h"
 
 #define ALEGO_MAX_RINGS 128
+#define ALEGO_INFLIGHT 3  // steps alego_pipeline_submit keeps in flight (device staging buffers, pinned result slots)
 #define ALEGO_EMPTY_RANGE 3.402823466e+38f  // FLT_MAX: "no return" marker of the range image (reference: DBL_MAX, imageProjection.cpp:33)
 #define ALEGO_LABEL_INVALID 999999          // imageProjection.cpp:311
 
@@ -52,8 +53,8 @@ struct AlegoHandle {
   cudaEvent_t ev_side_tail = nullptr;            // side stream: everything enqueued there so far
   bool side_busy = false;                        // work was enqueued on the side stream since the last join
   bool overlap_lm = true;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_pose[2] = {nullptr, nullptr};
-  bool consumed_valid[2] = {false, false};
+  cudaEvent_t ev_copied[ALEGO_INFLIGHT] = {}, ev_consumed[ALEGO_INFLIGHT] = {}, ev_pose[ALEGO_INFLIGHT] = {};
+  bool consumed_valid[ALEGO_INFLIGHT] = {};
   bool overlap_map_build = true;
   long long n_submitted = 0, n_collected = 0;
   std::string err;
@@ -79,9 +80,9 @@ struct AlegoHandle {
   int *n_pts = nullptr;        // [B]
   float4 *raw_own = nullptr;
   int *n_pts_own = nullptr;
-  float4 *raw_slot[2] = {nullptr, nullptr};  // device staging of alego_pipeline_submit (slot 0 aliases raw_own)
-  int *n_pts_slot[2] = {nullptr, nullptr};
-  int32_t *h_n_pts_slot[2] = {nullptr, nullptr};  // pinned copies of the caller's n_points
+  float4 *raw_slot[ALEGO_INFLIGHT] = {};  // device staging of alego_pipeline_submit (slot 0 aliases raw_own)
+  int *n_pts_slot[ALEGO_INFLIGHT] = {};
+  int32_t *h_n_pts_slot[ALEGO_INFLIGHT] = {};  // pinned copies of the caller's n_points
   std::vector<float4 *> stage_raw;  // sweeps pre-staged in HBM (alego_stage_*)
   std::vector<int *> stage_n;
   int *winner = nullptr;       // [B][RC]  index of the last input point that fell in the cell (-1 none)
@@ -178,7 +179,7 @@ struct AlegoHandle {
 
   // host staging for small D2H results
   double *h_pose = nullptr;  // pinned [B][12]
-  double *h_pose_slot[2] = {nullptr, nullptr};  // pinned, per in-flight step
+  double *h_pose_slot[ALEGO_INFLIGHT] = {};  // pinned, per in-flight step
   double *d_pose = nullptr;  // [B][12]
 };
 

@@ -345,11 +345,12 @@ def main():
     barrier()
     t_host0 = time.perf_counter()
     g.timer_mark(2)
+    DEPTH = 3  # steps in flight (alego_pipeline_submit allows three)
     for t in range(W, W + K):
-        if t - W >= 2:
+        if t - W >= DEPTH:
             poses = g.pipeline_collect()
         g.pipeline_submit(host[t], host_n[t])
-    for _ in range(min(K, 2)):
+    for _ in range(min(K, DEPTH)):
         poses = g.pipeline_collect()
     g.timer_mark(3)
     barrier()
@@ -423,7 +424,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 4 * PS + B * 4), "d2h_bytes_per_step": B * 12 * 8,
                     "ms_per_step": ms_e2e / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
                     "h2d_probe_gbs": round(h2d_probe_gbs, 1),
-                    "api": "alego_pipeline_submit/_collect, pinned host sweeps, 2 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
+                    "api": "alego_pipeline_submit/_collect, pinned host sweeps, 3 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
             "gpu_launches": int(launches),
             "lm": lm_block(kernels, lm_reports, lo_reports, B),
             "roofline": roofline,

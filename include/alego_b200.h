@@ -185,9 +185,9 @@ int alego_lm_get_downsampled(AlegoHandle *h, int seq, float *corner_ds, int32_t 
 int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out);
 /* Asynchronous form of alego_pipeline_step for streaming ingestion (a rosbag / sensor thread feeding the nodelets,
  * imageProjection.cpp:45 subscriber queue): submit enqueues the H2D copy of the sweeps on a copy stream into one of
- * two device staging buffers and the whole IP -> LO -> LM pass behind it, and returns without waiting, so the copy
+ * three device staging buffers and the whole IP -> LO -> LM pass behind it, and returns without waiting, so the copy
  * of sweep t+1 overlaps the pass over sweep t.  xyzi_host must be pinned (alego_host_alloc) and stay untouched until
- * the step is collected.  At most two steps may be in flight; collect waits for the OLDEST one and returns its
+ * the step is collected.  At most three steps may be in flight; collect waits for the OLDEST one and returns its
  * poses (layout as alego_pipeline_step; poses_out may be NULL). */
 int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
 int alego_pipeline_collect(AlegoHandle *h, double *poses_out);

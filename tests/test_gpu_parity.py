@@ -473,20 +473,21 @@ def test_async_submit_collect_matches_sync(alego):
         ref.append(g.pipeline_step(buf, n))
     g.close()
     g = fresh(True)
-    bufs = [alego.pinned_empty((len(seeds), g.max_points, 4), np.float32) for _ in range(2)]
-    ns = [np.zeros(len(seeds), np.int32) for _ in range(2)]
+    D = 3  # steps alego_pipeline_submit keeps in flight
+    bufs = [alego.pinned_empty((len(seeds), g.max_points, 4), np.float32) for _ in range(D)]
+    ns = [np.zeros(len(seeds), np.int32) for _ in range(D)]
     got = []
     for t in range(T):
-        if t >= 2:
-            got.append(g.pipeline_collect())     # frees the pinned buffer of step t-2
+        if t >= D:
+            got.append(g.pipeline_collect())     # frees the pinned buffer of step t-D
         b_, n_ = g.pack_scans(sweeps[t])
-        bufs[t % 2][:] = b_
-        ns[t % 2][:] = n_
-        g.pipeline_submit(bufs[t % 2], ns[t % 2])
+        bufs[t % D][:] = b_
+        ns[t % D][:] = n_
+        g.pipeline_submit(bufs[t % D], ns[t % D])
     with pytest.raises(alego.AlegoError):
-        g.pipeline_submit(bufs[0], ns[0])        # two steps already in flight
-    got.append(g.pipeline_collect())
-    got.append(g.pipeline_collect())
+        g.pipeline_submit(bufs[0], ns[0])        # three steps already in flight
+    for _ in range(D):
+        got.append(g.pipeline_collect())
     with pytest.raises(alego.AlegoError):
         g.pipeline_collect()                     # nothing in flight
     for t in range(T):
