@@ -120,43 +120,70 @@ __global__ void __launch_bounds__(256) ip_project_kernel(const float *__restrict
   }
 }
 
-__global__ void __launch_bounds__(256) ip_gather_kernel(const float *__restrict__ raw, int stride, int *__restrict__ winner,
-                                                        float4 *__restrict__ cloud, float *__restrict__ range,
-                                                        uint8_t *__restrict__ ground, int Nmax, IpDev P) {
-  const int b = blockIdx.y;
-  const size_t base = (size_t)b * P.RC;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
-    const int w = winner[base + cell];
-    float4 o = make_float4(0.f, 0.f, 0.f, -1.f);  // nan_p (:24-27)
-    float r = ALEGO_EMPTY_RANGE;
-    if (w >= 0) {
-      winner[base + cell] = -1;  // ready for the next sweep
-      const float4 p = load_point(raw + (size_t)b * Nmax * stride, w, stride);
-      const int row = cell / P.C, col = cell - row * P.C;
-      r = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);                      // (:99) float sum, float sqrt
-      o = make_float4(p.x, p.y, p.z, (float)((double)row + (double)col / 10000.0));  // (:101)
-    }
-    cloud[base + cell] = o;
-    range[base + cell] = r;
-    ground[base + cell] = 0;
-  }
+// range-angle criterion (:255-270): atan2(d2*sin(alpha), d1 - d2*cos(alpha)) > seg_theta
+__device__ __forceinline__ bool seg_join(float ra, float rb, bool horizontal, const IpDev &P) {
+  const float d1f = fmaxf(ra, rb), d2f = fminf(ra, rb);
+  const float sf = horizontal ? (float)P.sin_x : (float)P.sin_y, cf = horizontal ? (float)P.cos_x : (float)P.cos_y;
+  float af = 0.f;  // approximate angle (1e-6 rad) decides unless it is within 1e-4 rad of the threshold
+  if (fast_atan2(d2f * sf, d1f - d2f * cf, af) && fabsf(af - (float)P.seg_theta) > 1e-4f) return af > (float)P.seg_theta;
+  const double d1 = d1f, d2 = d2f;
+  const double angle = atan2(d2 * (horizontal ? P.sin_x : P.sin_y), d1 - d2 * (horizontal ? P.cos_x : P.cos_y));
+  return angle > P.seg_theta;
 }
 
-// (:106-132) one thread per vertical pair (i, i+1), i < ground_scan_id
-__global__ void __launch_bounds__(256) ip_ground_kernel(const float4 *__restrict__ cloud, uint8_t *__restrict__ ground, IpDev P) {
-  const int b = blockIdx.y;
+// cell flags written by ip_image, read by the connected-component kernels
+#define CELL_VALID 1      // has a return and is not ground: a segmentation candidate (label_mat_ == 0, :134-143)
+#define CELL_GROUND 2
+#define CELL_JOIN_LEFT 4  // joined with the cell one column to the left (column 0: with column C-1, :241-248)
+#define CELL_JOIN_DOWN 8  // joined with the cell one row up in the image (row + 1)
+
+// K1b + K2 + the join tests of K3 in one pass over the image.  A CTA owns a strip of IMG_W columns x all rows, staged in
+// shared memory together with the column to its left:
+//   * per cell: the winner of ip_project -> organised cloud + range image (:99-103, fill values :24-33);
+//   * per column: ground test of every vertical pair below ground_scan_id (:106-132) — a cell's ground flag depends only on
+//     its own column, which the CTA holds completely;
+//   * per cell: validity and the two range-angle join tests (:255-270) towards the left and the upper neighbour, kept as
+//     one flag byte, so that the union-find kernels touch 1 byte per cell and evaluate no atan2.
+#define IMG_W 32
+__global__ void __launch_bounds__(256) ip_image_kernel(const float *__restrict__ raw, int stride, const int *__restrict__ winner,
+                                                       float4 *__restrict__ cloud, float *__restrict__ range,
+                                                       uint8_t *__restrict__ ground, uint8_t *__restrict__ flags, int Nmax, IpDev P) {
+  extern __shared__ float4 s_pt[];  // [R][IMG_W + 1]: x, y, z, range (ALEGO_EMPTY_RANGE: no return); column 0 = left neighbour strip
+  const int SW = IMG_W + 1;
+  uint8_t *s_ground = reinterpret_cast<uint8_t *>(s_pt + (size_t)P.R * SW);  // [R][SW]
+  const int b = blockIdx.y, col0 = blockIdx.x * IMG_W;
   const size_t base = (size_t)b * P.RC;
-  const int rows = min(P.ground_scan_id, P.R - 1);
-  const int total = rows * P.C;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const float4 lo = cloud[base + t], up = cloud[base + t + P.C];
-    if (lo.w == -1.f || up.w == -1.f) continue;
+  const float *sweep = raw + (size_t)b * Nmax * stride;
+  const int ncell = P.R * SW;
+  for (int t = threadIdx.x; t < ncell; t += blockDim.x) {
+    const int row = t / SW, c = t - row * SW;
+    int col = col0 + c - 1;
+    if (col < 0) col += P.C;
+    float4 v = make_float4(0.f, 0.f, 0.f, ALEGO_EMPTY_RANGE);
+    if (col < P.C) {
+      const int w = winner[base + (size_t)row * P.C + col];
+      if (w >= 0) {
+        const float4 p = load_point(sweep, w, stride);
+        v = make_float4(p.x, p.y, p.z, sqrtf(p.x * p.x + p.y * p.y + p.z * p.z));  // (:99) float sum, float sqrt
+      }
+    }
+    s_pt[t] = v;
+    s_ground[t] = 0;
+  }
+  __syncthreads();
+  // ---- ground (:106-132): one thread per vertical pair (i, i+1), i < ground_scan_id
+  const int grows = min(P.ground_scan_id, P.R - 1);
+  for (int t = threadIdx.x; t < grows * SW; t += blockDim.x) {
+    const float4 lo = s_pt[t], up = s_pt[t + SW];
+    if (lo.w == ALEGO_EMPTY_RANGE || up.w == ALEGO_EMPTY_RANGE) continue;
     const float fx = up.x - lo.x, fy = up.y - lo.y, fz = up.z - lo.z;  // float differences, then widened
     // fast float estimate; the exact double evaluation only near the 10 degree threshold
-    const float af = atan2f(fz, sqrtf(fx * fx + fy * fy)) * 57.29577951f;
+    float af = 0.f;
+    const float h2 = fx * fx + fy * fy;
+    const bool fast = fast_atan2(fz, h2 * rsqrtf(fmaxf(h2, 1e-30f)), af);
     bool is_ground;
-    const float da = fabsf(af - (float)P.sensor_mount_ang);
-    if (fabsf(da - 10.f) > 1e-2f) {
+    const float da = fabsf(af * 57.29577951f - (float)P.sensor_mount_ang);
+    if (fast && fabsf(da - 10.f) > 1e-2f) {
       is_ground = da < 10.f;
     } else {
       const double dx = fx, dy = fy, dz = fz;
@@ -164,9 +191,34 @@ __global__ void __launch_bounds__(256) ip_ground_kernel(const float4 *__restrict
       is_ground = fabs(angle - P.sensor_mount_ang) < 10.;
     }
     if (is_ground) {
-      ground[base + t] = 1;
-      ground[base + t + P.C] = 1;
+      s_ground[t] = 1;
+      s_ground[t + SW] = 1;
     }
+  }
+  __syncthreads();
+  // ---- outputs + flags of the strip's own columns
+  for (int t = threadIdx.x; t < P.R * IMG_W; t += blockDim.x) {
+    const int row = t / IMG_W, c = (t & (IMG_W - 1)) + 1, col = col0 + c - 1;
+    if (col >= P.C) continue;
+    const int si = row * SW + c;
+    const float4 v = s_pt[si];
+    const bool has = v.w != ALEGO_EMPTY_RANGE, g = s_ground[si] != 0;
+    const bool valid = has && !g;
+    int f = (valid ? CELL_VALID : 0) | (g ? CELL_GROUND : 0);
+    if (valid) {
+      const float4 l = s_pt[si - 1];
+      if (P.C > 1 && l.w != ALEGO_EMPTY_RANGE && s_ground[si - 1] == 0 && seg_join(l.w, v.w, true, P)) f |= CELL_JOIN_LEFT;
+      if (row + 1 < P.R) {
+        const float4 u = s_pt[si + SW];
+        if (u.w != ALEGO_EMPTY_RANGE && s_ground[si + SW] == 0 && seg_join(v.w, u.w, false, P)) f |= CELL_JOIN_DOWN;
+      }
+    }
+    const size_t cell = base + (size_t)row * P.C + col;
+    // nan_p (:24-27) for cells without a return; intensity = row + col/10000 (:101)
+    cloud[cell] = has ? make_float4(v.x, v.y, v.z, (float)((double)row + (double)col / 10000.0)) : make_float4(0.f, 0.f, 0.f, -1.f);
+    range[cell] = v.w;
+    ground[cell] = g ? 1 : 0;
+    flags[cell] = (uint8_t)f;
   }
 }
 
@@ -213,17 +265,6 @@ __device__ __forceinline__ void uf_unite(int *L, int a, int b) {
   } while (!done);
 }
 
-// range-angle criterion (:255-270): atan2(d2*sin(alpha), d1 - d2*cos(alpha)) > seg_theta
-__device__ __forceinline__ bool seg_join(float ra, float rb, bool horizontal, const IpDev &P) {
-  const float d1f = fmaxf(ra, rb), d2f = fminf(ra, rb);
-  const float sf = horizontal ? (float)P.sin_x : (float)P.sin_y, cf = horizontal ? (float)P.cos_x : (float)P.cos_y;
-  const float af = atan2f(d2f * sf, d1f - d2f * cf);
-  if (fabsf(af - (float)P.seg_theta) > 1e-4f) return af > (float)P.seg_theta;
-  const double d1 = d1f, d2 = d2f;
-  const double angle = atan2(d2 * (horizontal ? P.sin_x : P.sin_y), d1 - d2 * (horizontal ? P.cos_x : P.cos_y));
-  return angle > P.seg_theta;
-}
-
 // inclusive block-wide max scan of one int per thread (smem: >= 33 ints); all threads must call
 __device__ __forceinline__ int block_incl_max_scan(int v, int *smem) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -251,24 +292,20 @@ __device__ __forceinline__ int block_incl_max_scan(int v, int *smem) {
 // Horizontal pass, one CTA per (ring, sequence): candidate mask (:134-143) and the horizontal joins of the ring.  A
 // ring decomposes into runs of cells each joined to its left neighbour; every cell is pointed at the first cell of its
 // run by a max-scan of the run-start columns — no atomics.  The column wrap (:241-248) links the last run to the first.
-__global__ void __launch_bounds__(256) ccl_rows_kernel(const float *__restrict__ range, const uint8_t *__restrict__ ground,
-                                                       int *__restrict__ parent, int2 *__restrict__ comp_stat, IpDev P) {
+__global__ void __launch_bounds__(256) ccl_rows_kernel(const uint8_t *__restrict__ flags, int *__restrict__ parent,
+                                                       int2 *__restrict__ comp_stat, IpDev P) {
   const int b = blockIdx.y, row = blockIdx.x;
   const size_t base = (size_t)b * P.RC + (size_t)row * P.C;
-  const float *rg = range + base;
-  const uint8_t *gr = ground + base;
+  const uint8_t *fl = flags + base;
   __shared__ int s_scan[34];
   int carry = -1;  // run-start column inherited from the columns left of this chunk
   for (int c0 = 0; c0 < P.C; c0 += blockDim.x) {
     const int col = c0 + threadIdx.x;
     bool valid = false, join_left = false;
     if (col < P.C) {
-      const float r0 = rg[col];
-      valid = gr[col] == 0 && r0 != ALEGO_EMPTY_RANGE;
-      if (valid && col > 0) {
-        const float rl = rg[col - 1];
-        join_left = gr[col - 1] == 0 && rl != ALEGO_EMPTY_RANGE && seg_join(rl, r0, true, P);
-      }
+      const int f = fl[col];
+      valid = (f & CELL_VALID) != 0;
+      join_left = col > 0 && (f & CELL_JOIN_LEFT) != 0;
       comp_stat[base + col] = make_int2(0, 0);
     }
     const int start = (valid && !join_left) ? col : -1;
@@ -280,28 +317,21 @@ __global__ void __launch_bounds__(256) ccl_rows_kernel(const float *__restrict__
     __syncthreads();
     carry = s_scan[33];
   }
-  if (threadIdx.x == 0 && P.C > 1) {
-    const float rf = rg[0], rl = rg[P.C - 1];
-    const bool vf = gr[0] == 0 && rf != ALEGO_EMPTY_RANGE, vl = gr[P.C - 1] == 0 && rl != ALEGO_EMPTY_RANGE;
-    if (vf && vl && seg_join(rl, rf, true, P)) {
-      const int last_root = parent[base + P.C - 1];  // written by this CTA (same thread block: visible after the barrier)
-      if (last_root != row * P.C) parent[(size_t)b * P.RC + last_root] = row * P.C;
-    }
+  if (threadIdx.x == 0 && P.C > 1 && (fl[0] & CELL_JOIN_LEFT)) {  // column wrap: the last run of the ring joins the first
+    const int last_root = parent[base + P.C - 1];  // written by this CTA (same thread block: visible after the barrier)
+    if (last_root != row * P.C) parent[(size_t)b * P.RC + last_root] = row * P.C;
   }
 }
 
 // Vertical pass: joins between a cell and the cell below it (rows do not wrap, :237) on the union-find forest
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const float *__restrict__ range, int *parent, IpDev P) {
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t *__restrict__ flags, int *parent, IpDev P) {
   const int b = blockIdx.y;
   const size_t base = (size_t)b * P.RC;
   int *L = parent + base;
-  const float *rg = range + base;
+  const uint8_t *fl = flags + base;
   const int n = P.RC - P.C;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x) {
-    const int nb = cell + P.C;
-    if (L[cell] < 0 || L[nb] < 0) continue;
-    if (seg_join(rg[cell], rg[nb], false, P)) uf_unite(L, cell, nb);
-  }
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x)
+    if (fl[cell] & CELL_JOIN_DOWN) uf_unite(L, cell, cell + P.C);
 }
 
 // flatten + per-component size and highest row (rows of a 4-connected component are contiguous, so the
@@ -437,30 +467,36 @@ ip_compact_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_
     }
   }
   __syncthreads();
-  int run_k = s_base[0], run_o = s_base[1], run_r = s_base[2];
-  for (int c0 = 0; c0 < P.C; c0 += blockDim.x) {
-    const int col = c0 + threadIdx.x;
-    CellClass c{false, false, false, false, false};
+  // every thread owns `per` consecutive columns: count, ONE block scan for the whole ring, then the ordered writes (the
+  // classification is evaluated twice — cached loads — instead of scanning the ring in eight 256-column chunks)
+  const int per = (P.C + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int c_lo = min((int)threadIdx.x * per, P.C), c_hi = min(c_lo + per, P.C);
+  int nk = 0, no = 0, nr = 0;
+  for (int col = c_lo; col < c_hi; ++col) {
+    const CellClass c = classify(row * P.C + col, row, col, parent + base, comp_stat + base, ground + base, P);
+    nk += c.keep;
+    no += c.outl;
+    nr += c.rootflag;
+  }
+  int total;
+  const int ex_ko = block_excl_scan(nk | (no << 16), s_scan, &total);  // a ring holds < 65536 cells
+  const int ex_r = block_excl_scan(nr, s_scan, &total);
+  int dk = s_base[0] + (ex_ko & 0xffff), dout = s_base[1] + (ex_ko >> 16), dr = s_base[2] + ex_r;
+  for (int col = c_lo; col < c_hi; ++col) {
     const int cell = row * P.C + col;
-    if (col < P.C) c = classify(cell, row, col, parent + base, comp_stat + base, ground + base, P);
-    const int packed = (int)c.keep | ((int)c.outl << 10) | ((int)c.rootflag << 20);
-    int total;
-    const int ex = block_excl_scan(packed, s_scan, &total);
+    const CellClass c = classify(cell, row, col, parent + base, comp_stat + base, ground + base, P);
     if (c.keep) {
-      const int dst = run_k + (ex & 1023);
-      seg_cloud[base + dst] = cloud[base + cell];
-      seg_ground[base + dst] = ground[base + cell] == 1;  // (:183)
-      seg_col[base + dst] = col;                          // (:184)
-      seg_range[base + dst] = range[base + cell];         // (:185)
+      seg_cloud[base + dk] = cloud[base + cell];
+      seg_ground[base + dk] = ground[base + cell] == 1;  // (:183)
+      seg_col[base + dk] = col;                          // (:184)
+      seg_range[base + dk] = range[base + cell];         // (:185)
+      ++dk;
     }
     if (c.outl) {
-      const int dst = run_o + ((ex >> 10) & 1023);
-      if (dst < out_cap) outlier[(size_t)b * out_cap + dst] = cloud[base + cell];
+      if (dout < out_cap) outlier[(size_t)b * out_cap + dout] = cloud[base + cell];
+      ++dout;
     }
-    if (c.rootflag) comp_id[base + cell] = run_r + ((ex >> 20) & 1023) + 1;  // label_cnt_ in raster-seed order (:303-306)
-    run_k += total & 1023;
-    run_o += (total >> 10) & 1023;
-    run_r += (total >> 20) & 1023;
+    if (c.rootflag) comp_id[base + cell] = ++dr;  // label_cnt_ in raster-seed order (:303-306)
   }
 }
 
@@ -514,19 +550,21 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   if (!proj_attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(ip_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(32 * (ALEGO_MAX_RINGS + 1) * sizeof(float4))));
+    CUDA_TRY(h, cudaFuncSetAttribute(ip_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(ALEGO_MAX_RINGS * (IMG_W + 1) * (sizeof(float4) + 1))));
     proj_attr_set = true;
   }
   { LAUNCH(h, "ip_project");
     ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(reinterpret_cast<const float *>(h->raw), h->n_pts, h->winner, h->Nmax, h->in_stride, P); }
-  { LAUNCH(h, "ip_gather");
-    ip_gather_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(reinterpret_cast<const float *>(h->raw), h->in_stride, h->winner, h->cloud, h->range, h->ground, h->Nmax, P); }
-  const int gpairs = min(P.ground_scan_id, P.R - 1) * P.C;
-  if (gpairs > 0) {
-    LAUNCH(h, "ip_ground");
-    ip_ground_kernel<<<dim3(min(div_up(gpairs, 256), 4096), B), 256, 0, s>>>(h->cloud, h->ground, P);
-  }
-  { LAUNCH(h, "ccl_rows"); ccl_rows_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->range, h->ground, h->parent, h->comp_stat, P); }
-  { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->range, h->parent, P); }
+  const size_t img_smem = (size_t)P.R * (IMG_W + 1) * (sizeof(float4) + 1);
+  { LAUNCH(h, "ip_image");
+    ip_image_kernel<<<dim3(div_up(P.C, IMG_W), B), 256, img_smem, s>>>(reinterpret_cast<const float *>(h->raw), h->in_stride, h->winner,
+                                                                   h->cloud, h->range, h->ground, h->cell_flags, h->Nmax, P); }
+  // the winner image is consumed: empty it for the next sweep (a cell is reset by memset rather than by its reader because the
+  // neighbouring strip reads it too)
+  CUDA_TRY(h, cudaMemsetAsync(h->winner, 0xFF, (size_t)B * h->RC * sizeof(int), s));
+  { LAUNCH(h, "ccl_rows"); ccl_rows_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->cell_flags, h->parent, h->comp_stat, P); }
+  { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->cell_flags, h->parent, P); }
   { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ip_rowcount");
     ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, reinterpret_cast<const float *>(h->raw), h->in_stride, h->n_pts, h->orient,

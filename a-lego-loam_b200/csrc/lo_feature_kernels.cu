@@ -27,6 +27,7 @@ lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__
   const size_t base = (size_t)b * RC;
   __shared__ float sr[CURV_TILE + 12];
   __shared__ int sc[CURV_TILE + 12];
+  __shared__ uint8_t sf[CURV_TILE + 12];  // per loop iteration j of markOccludedPoints: 1 = marks j-5..j, 2 = marks j+1..j+5
   for (int t = threadIdx.x; t < CURV_TILE + 12; t += CURV_TILE) {
     const int g = tile_lo - 6 + t;
     const bool ok = g >= 0 && g < M;
@@ -34,37 +35,34 @@ lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__
     sc[t] = ok ? seg_col[base + g] : 0;
   }
   __syncthreads();
+  const int lo = 5, hi = M - 5;  // loop bounds of both reference loops: i in [5, M-5)
+  // the occlusion test of iteration j (:134-150) is evaluated once, by the thread that stages j, and shared
+  for (int t = threadIdx.x; t < CURV_TILE + 11; t += CURV_TILE) {
+    const int j = tile_lo - 6 + t;
+    int f = 0;
+    if (j >= lo && j < hi && abs(sc[t] - sc[t + 1]) < 10) {
+      const double d1 = sr[t], d2 = sr[t + 1];
+      if (d1 - d2 > 0.5) f = 1;        // (:140-145), `continue`s past the parallel-beam test
+      else if (d2 - d1 > 0.5) f = 2;   // (:146-150)
+    }
+    sf[t] = (uint8_t)f;
+  }
+  __syncthreads();
   const int i = tile_lo + threadIdx.x;
   if (i >= M) return;
   const int li = threadIdx.x + 6;
   float c = 0.f;
-  bool pk = false;
-  const int lo = 5, hi = M - 5;  // loop bounds of both reference loops: i in [5, M-5)
+  // markOccludedPoints as a gather: iteration j = i..i+5 with f == 1 marks i, iteration j = i-5..i-1 with f == 2 marks i
+  bool pk = ((sf[li] | sf[li + 1] | sf[li + 2] | sf[li + 3] | sf[li + 4] | sf[li + 5]) & 1) != 0 ||
+            ((sf[li - 1] | sf[li - 2] | sf[li - 3] | sf[li - 4] | sf[li - 5]) & 2) != 0;
   if (i >= lo && i < hi) {
     // (:124) float sum, strictly left to right, r[i]*10 is a float product; compiled without FMA contraction
     const float d = sr[li - 5] + sr[li - 4] + sr[li - 3] + sr[li - 2] + sr[li - 1] - sr[li] * 10 + sr[li + 1] + sr[li + 2] +
                     sr[li + 3] + sr[li + 4] + sr[li + 5];
     c = fabsf(d);  // cloud_curvature_ = double(d)*double(d) is recovered exactly as (double)c*(double)c
-  }
-  // markOccludedPoints as a gather: which iterations j of the reference loop mark position i?
-#pragma unroll
-  for (int o = 0; o <= 5; ++o) {  // j = i+o marks j-5..j when depth1 - depth2 > 0.5 (:140-145)
-    const int j = i + o, lj = li + o;
-    if (j >= lo && j < hi && abs(sc[lj] - sc[lj + 1]) < 10 && (double)sr[lj] - (double)sr[lj + 1] > 0.5) pk = true;
-  }
-#pragma unroll
-  for (int o = 1; o <= 5; ++o) {  // j = i-o marks j+1..j+5 when depth2 - depth1 > 0.5 (:146-150)
-    const int j = i - o, lj = li - o;
-    if (j >= lo && j < hi && abs(sc[lj] - sc[lj + 1]) < 10) {
-      const double d1 = sr[lj], d2 = sr[lj + 1];
-      if (!(d1 - d2 > 0.5) && d2 - d1 > 0.5) pk = true;
-    }
-  }
-  if (i >= lo && i < hi) {  // parallel-beam test, skipped by the `continue` of the first branch (:144,152-158)
-    const double d1 = sr[li], d2 = sr[li + 1];
-    const bool first_branch = abs(sc[li] - sc[li + 1]) < 10 && d1 - d2 > 0.5;
-    if (!first_branch) {
-      const double diff1 = fabs((double)sr[li - 1] - d1), diff2 = fabs(d2 - d1), thr = 0.02 * (double)sr[li];
+    if (sf[li] != 1) {  // parallel-beam test, skipped by the `continue` of the first branch (:144,152-158)
+      const double d1 = sr[li], d2 = sr[li + 1];
+      const double diff1 = fabs((double)sr[li - 1] - d1), diff2 = fabs(d2 - d1), thr = 0.02 * d1;
       if (diff1 > thr && diff2 > thr) pk = true;
     }
   }

@@ -214,10 +214,10 @@ def algorithmic_bytes(name, st):
     gfrac = st["ground_rows"] / st["R"]
     table = {
         "ip_project": (pb + 4.0) * pts,                # read the point + 4 B winner atomic
-        "ip_gather": 4.0 * cells + pb * pts + 21.0 * cells,  # winner + gathered point -> cloud(16) + range(4) + ground(1)
-        "ip_ground": (2 * 16.0 + 1.0) * cells * gfrac,
-        "ccl_init": (4 + 1 + 4 + 8) * cells,
-        "ccl_merge": 12.0 * cells,
+        # winner + gathered point -> cloud(16) + range(4) + ground(1) + cell flags(1)
+        "ip_image": 4.0 * cells + pb * pts + 22.0 * cells,
+        "ccl_rows": (1 + 4 + 8) * cells,               # flags -> parent + zeroed component statistics
+        "ccl_merge": 5.0 * cells,                      # flags + the parent entries of joined cells (minimum)
         "ccl_flatten": 8.0 * cells,
         "ip_rowcount": 13.0 * cells,
         "ip_compact": 13.0 * cells + (16 + 4 + 25.0) * kept,
@@ -409,7 +409,7 @@ def main():
                     "dominant_kernel_overall": dom,
                     "named": {k: {"achieved": kernels[k]["algorithmic_gbs"], "frac": round(kernels[k]["algorithmic_gbs"] / peak, 4),
                                   "algorithmic_bytes_per_launch": algorithmic_bytes(k, st), "traffic": ncu_traffic(k, B, args.preset, PS)[0]}
-                              for k in ("ip_project", "ip_gather", "lo_curv_occl") if k in kernels}}
+                              for k in ("ip_project", "ip_image", "lo_curv_occl") if k in kernels}}
         line = {
             "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
