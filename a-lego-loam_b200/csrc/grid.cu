@@ -90,7 +90,7 @@ int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_strid
   const int B = h->B, T = g->table_size;
   cudaStream_t s = h->launch_stream ? h->launch_stream : h->stream;
   const float inv = 1.0f / g->cell;
-  const int blocks = min(div_up(g->cap, 256), 1024);
+  const int blocks = min(div_up(g->cap, 256), 128);  // capacity-sized clouds are mostly far from full: bounded grid, stride loops
   std::string t0 = std::string("grid_count_") + tag, t1 = std::string("grid_scan_") + tag, t2 = std::string("grid_fill_") + tag;
   CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)B * (T + 4) * sizeof(int), s));
   { LAUNCH(h, t0.c_str());

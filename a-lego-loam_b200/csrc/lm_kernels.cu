@@ -283,33 +283,43 @@ __global__ void __launch_bounds__(256, 4)
 lm_knn_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, GridIndex g,
               const Pose *__restrict__ m2l, const int *__restrict__ guard, int *__restrict__ nn) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(lm_n[b * 8 + n_slot], qcap);
-  if (i >= nq) return;
-  int *o = nn + ((size_t)b * qcap + i) * 5;
-  if (!guard[b]) { o[0] = -1; return; }
-  const float4 cp = query[(size_t)b * qcap + i];
+  const bool ok = guard[b] != 0;
   const Pose &P = m2l[b];
-  // pointAssociateToMap (laserMapping.h:187-194): double transform, float result
-  const float sx = (float)(P.R[0] * cp.x + P.R[1] * cp.y + P.R[2] * cp.z + P.t[0]);
-  const float sy = (float)(P.R[3] * cp.x + P.R[4] * cp.y + P.R[5] * cp.z + P.t[1]);
-  const float sz = (float)(P.R[6] * cp.x + P.R[7] * cp.y + P.R[8] * cp.z + P.t[2]);
-  float bd[5];
-  int bi[5];
-  if (knn5_gate(g, b, sx, sy, sz, bd, bi) < 5) { o[0] = -1; return; }  // point_dist_[4] < 1.0 (:376, :426)
+  // the buffers are sized for the largest possible cloud, the queries that exist are a few thousand: bounded grid + stride
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+    int *o = nn + ((size_t)b * qcap + i) * 5;
+    if (!ok) { o[0] = -1; continue; }
+    const float4 cp = query[(size_t)b * qcap + i];
+    // pointAssociateToMap (laserMapping.h:187-194): double transform, float result
+    const float sx = (float)(P.R[0] * cp.x + P.R[1] * cp.y + P.R[2] * cp.z + P.t[0]);
+    const float sy = (float)(P.R[3] * cp.x + P.R[4] * cp.y + P.R[5] * cp.z + P.t[1]);
+    const float sz = (float)(P.R[6] * cp.x + P.R[7] * cp.y + P.R[8] * cp.z + P.t[2]);
+    float bd[5];
+    int bi[5];
+    if (knn5_gate(g, b, sx, sy, sz, bd, bi) < 5) { o[0] = -1; continue; }  // point_dist_[4] < 1.0 (:376, :426)
 #pragma unroll
-  for (int t = 0; t < 5; ++t) o[t] = bi[t];
+    for (int t = 0; t < 5; ++t) o[t] = bi[t];
+  }
 }
 
 // K14b/K15b: per query with 5 neighbours — line test (PCA) or plane fit in double; writes the residual block
+template <bool EDGE>
+__device__ __forceinline__ void lm_fit_one(const float4 *__restrict__ query, int qcap, const float4 *__restrict__ map, int map_cap,
+                                           const int *__restrict__ nn, double *__restrict__ out, int out_w, int b, int i);
 template <bool EDGE>
 __global__ void __launch_bounds__(128)
 lm_fit_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, const float4 *__restrict__ map,
               int map_cap, const int *__restrict__ nn, double *__restrict__ out, int out_w) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(lm_n[b * 8 + n_slot], qcap);
-  if (i >= nq) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x)
+    lm_fit_one<EDGE>(query, qcap, map, map_cap, nn, out, out_w, b, i);
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void lm_fit_one(const float4 *__restrict__ query, int qcap, const float4 *__restrict__ map, int map_cap,
+                                           const int *__restrict__ nn, double *__restrict__ out, int out_w, int b, int i) {
   double *o = out + ((size_t)b * qcap + i) * out_w;
   o[0] = 0.0;
   const int *bi = nn + ((size_t)b * qcap + i) * 5;
@@ -516,15 +526,15 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   { LAUNCH(h, "lm_guard"); lm_guard_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_n, h->n_map_corner, guard_dev, B); }
   // query slots actually populated are far fewer than the capacities: size the grids from the LO feature capacities
   { LAUNCH(h, "lm_knn_corner");
-    lm_knn_kernel<<<dim3(div_up(cc, 256), B), 256, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->g_map_corner, h->m2l, guard_dev, h->lm_nn_c); }
+    lm_knn_kernel<<<dim3(min(div_up(cc, 256), 32), B), 256, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->g_map_corner, h->m2l, guard_dev, h->lm_nn_c); }
   { LAUNCH(h, "lm_fit_corner");
-    lm_fit_kernel<true><<<dim3(div_up(cc, 128), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
+    lm_fit_kernel<true><<<dim3(min(div_up(cc, 128), 64), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
                                                                   h->lm_nn_c, h->lm_edge, 10); }
   { LAUNCH(h, "lm_knn_surf");
-    lm_knn_kernel<<<dim3(div_up(cs + co, 256), B), 256, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->g_map_surf, h->m2l, guard_dev,
+    lm_knn_kernel<<<dim3(min(div_up(cs + co, 256), 32), B), 256, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->g_map_surf, h->m2l, guard_dev,
                                                                 h->lm_nn_s); }
   { LAUNCH(h, "lm_fit_surf");
-    lm_fit_kernel<false><<<dim3(div_up(cs + co, 128), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
+    lm_fit_kernel<false><<<dim3(min(div_up(cs + co, 128), 64), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
                                                                        h->lm_nn_s, h->lm_plane, 8); }
   { LAUNCH(h, "lm_solve");
     lm_solve_kernel<<<B, 256, 0, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,

@@ -22,12 +22,13 @@ lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__
                     int *__restrict__ sort_idx, int RC) {
   const int b = blockIdx.y;
   const int M = Mdev[b];
-  const int tile_lo = blockIdx.x * CURV_TILE;
-  if (tile_lo >= M) return;
   const size_t base = (size_t)b * RC;
   __shared__ float sr[CURV_TILE + 12];
   __shared__ int sc[CURV_TILE + 12];
   __shared__ uint8_t sf[CURV_TILE + 12];  // per loop iteration j of markOccludedPoints: 1 = marks j-5..j, 2 = marks j+1..j+5
+  // the segmented cloud holds M of the R*C cells (about a third): bounded grid, tiles taken with a stride
+  for (int tile_lo = blockIdx.x * CURV_TILE; tile_lo < M; tile_lo += gridDim.x * CURV_TILE) {
+  __syncthreads();
   for (int t = threadIdx.x; t < CURV_TILE + 12; t += CURV_TILE) {
     const int g = tile_lo - 6 + t;
     const bool ok = g >= 0 && g < M;
@@ -49,7 +50,7 @@ lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__
   }
   __syncthreads();
   const int i = tile_lo + threadIdx.x;
-  if (i >= M) return;
+  if (i >= M) continue;
   const int li = threadIdx.x + 6;
   float c = 0.f;
   // markOccludedPoints as a gather: iteration j = i..i+5 with f == 1 marks i, iteration j = i-5..i-1 with f == 2 marks i
@@ -70,6 +71,7 @@ lo_curv_occl_kernel(const float *__restrict__ seg_range, const int *__restrict__
   picked0[base + i] = pk ? 1 : 0;
   flabel[base + i] = 0;
   sort_idx[base + i] = i;
+  }
 }
 
 // segment bounds (:177-178)
@@ -448,7 +450,7 @@ int lo_extract_device(AlegoHandle *h) {
   const int B = h->B, R = h->R, C = h->C, RC = h->RC;
   cudaStream_t s = h->stream;
   { LAUNCH(h, "lo_curv_occl");
-    lo_curv_occl_kernel<<<dim3(div_up(RC, CURV_TILE), B), CURV_TILE, 0, s>>>(h->seg_range, h->seg_col, h->M, h->curv, h->picked0,
+    lo_curv_occl_kernel<<<dim3(min(div_up(RC, CURV_TILE), 192), B), CURV_TILE, 0, s>>>(h->seg_range, h->seg_col, h->M, h->curv, h->picked0,
                                                                              h->flabel, h->sort_idx, RC); }
   const int sort_cap = ((C / 6 + 8) + 3) & ~3;
   const size_t sort_smem = (size_t)SORT_WARPS * ((size_t)sort_cap * 14 + 16);
