@@ -377,6 +377,7 @@ __global__ void lm_guard_kernel(const int *lm_n, const int *n_map_corner, int *g
   guard[b] = !(lm_n[b * 8 + 0] < 10 || lm_n[b * 8 + 3] < 100 || n_map_corner[b] < 10);
 }
 
+#define LM_STAGE_BYTES (200 * 1024)  // shared-memory staging of the residual blocks (one CTA per SM: the solver takes the register file)
 struct LmResidSet {
   const double *edge;
   int n_edge_slots;
@@ -401,11 +402,35 @@ struct LmResidSet {
   }
 };
 
+// the same residuals, compacted into shared memory by stage_blocks (edge blocks of 9 doubles, then plane blocks of 7)
+struct LmStagedSet {
+  const double *edge;
+  int n_edge;
+  const double *plane;
+  int n_plane;
+  __device__ int slots() const { return n_edge + n_plane; }
+  __device__ bool load(int i, int &kind, double cp[3], double a[3], double b[3], double c[3], double &d) const {
+    if (i < n_edge) {
+      const double *e = edge + (size_t)i * 9;
+      kind = 2;
+      for (int q = 0; q < 3; ++q) { cp[q] = e[q]; a[q] = e[3 + q]; b[q] = e[6 + q]; c[q] = 0; }
+      d = 0;
+      return true;
+    }
+    const double *p = plane + (size_t)(i - n_edge) * 7;
+    kind = 3;
+    for (int q = 0; q < 3; ++q) { cp[q] = p[q]; a[q] = p[3 + q]; b[q] = 0; c[q] = 0; }
+    d = p[6];
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(256)
 lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restrict__ plane, int pcap, const int *__restrict__ lm_n,
                 const int *__restrict__ guard, double *lm_params, Pose *m2o, const Pose *o2l, Pose *m2l, AlegoSolveReport *report,
                 double *trace, int *trace_n, int trace_cap, int outer_iters, int max_iters, double huber_a, double *pose_out,
-                const Pose *lo_pose) {
+                const Pose *lo_pose, int stage_doubles) {
+  extern __shared__ __align__(16) double lm_stage[];
   const int b = blockIdx.x;
   __shared__ LmShared sh;
   __shared__ int s_red[34];
@@ -439,9 +464,21 @@ lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restr
   __syncthreads();
   if (ok && ne + np > 0) {
     double *tr = trace ? trace + (size_t)b * trace_cap * 7 : nullptr;
+    // staged copy of the valid blocks when they fit (a few thousand correspondences do); otherwise the global arrays are swept
+    LmStagedSet ss{lm_stage, 0, lm_stage, 0};
+    const bool staged = ne * 9 + np * 7 <= stage_doubles;
+    if (staged) {
+      const double *ge = rs.edge, *gp = rs.plane;
+      ss.n_edge = stage_blocks<double, 9>(rs.n_edge_slots, lm_stage, [&](int i) { return ge[(size_t)i * 10] != 0.0; },
+                                          [&](int i, double *d) { for (int q = 0; q < 9; ++q) d[q] = ge[(size_t)i * 10 + 1 + q]; }, s_red);
+      ss.plane = lm_stage + (size_t)ss.n_edge * 9;
+      ss.n_plane = stage_blocks<double, 7>(rs.n_plane_slots, lm_stage + (size_t)ss.n_edge * 9, [&](int i) { return gp[(size_t)i * 8] != 0.0; },
+                                           [&](int i, double *d) { for (int q = 0; q < 7; ++q) d[q] = gp[(size_t)i * 8 + 1 + q]; }, s_red);
+    }
     for (int outer = 0; outer < outer_iters; ++outer) {  // (:360) the association pose is frozen, so both outer
       // iterations see the same correspondences; the second Solve continues from the first
-      const LmResult r = block_lm_solve(rs, x, max_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
+      const LmResult r = staged ? block_lm_solve(ss, x, max_iters, huber_a, &sh, tr, trace_n + b, trace_cap)
+                                : block_lm_solve(rs, x, max_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
       if (threadIdx.x == 0) {
         if (outer == 0) rep->initial_cost = r.initial_cost;
         rep->iterations += r.iterations;
@@ -536,10 +573,15 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   { LAUNCH(h, "lm_fit_surf");
     lm_fit_kernel<false><<<dim3(min(div_up(cs + co, 128), 64), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
                                                                        h->lm_nn_s, h->lm_plane, 8); }
+  static bool solve_attr_set = false;
+  if (!solve_attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_STAGE_BYTES));
+    solve_attr_set = true;
+  }
   { LAUNCH(h, "lm_solve");
-    lm_solve_kernel<<<B, 256, 0, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
+    lm_solve_kernel<<<B, 256, LM_STAGE_BYTES, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
         h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
-        write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur]); }
+        write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur], (int)(LM_STAGE_BYTES / sizeof(double))); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

@@ -8,6 +8,8 @@
 // K11/K12 lo_solve    : one CTA per sequence — Corner/Surf residuals, Huber, 6x6 reduction, LM (solver.cuh);
 //                       phase 1 = surf blocks only (:410-421), phase 2 = surf + corner blocks (:484-495) and
 //                       the pose integration (:504-508)
+#include <algorithm>
+
 #include "common.cuh"
 #include "grid.cuh"
 #include "lo_kernels.cuh"
@@ -310,11 +312,34 @@ struct LoResidSet {
   }
 };
 
+// the same residuals, compacted into shared memory by stage_blocks (surf blocks of 12 floats, then corner blocks of 9)
+struct LoStagedSet {
+  const float *surf;
+  int n_surf;
+  const float *corner;
+  int n_corner;
+  __device__ int slots() const { return n_surf + n_corner; }
+  __device__ bool load(int i, int &kind, double cp[3], double a[3], double b[3], double c[3], double &d) const {
+    d = 0;
+    if (i < n_surf) {
+      const float *r = surf + (size_t)i * 12;
+      kind = 1;
+      for (int q = 0; q < 3; ++q) { cp[q] = r[q]; a[q] = r[3 + q]; b[q] = r[6 + q]; c[q] = r[9 + q]; }
+      return true;
+    }
+    const float *r = corner + (size_t)(i - n_surf) * 9;
+    kind = 0;
+    for (int q = 0; q < 3; ++q) { cp[q] = r[q]; a[q] = r[3 + q]; b[q] = r[6 + q]; c[q] = 0; }
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(256)
 lo_solve_kernel(int phase, const float *__restrict__ surf_res, const int *__restrict__ surf_corr, const float *__restrict__ corner_res,
                 const int *__restrict__ corner_corr, const int *__restrict__ n_feat, double *lo_params, double *t_w, double *r_w,
                 int *lo_init, AlegoSolveReport *report, double *trace, int *trace_n, int trace_cap, int R, int surf_iters,
-                int corner_iters, double huber_a) {
+                int corner_iters, double huber_a, int stage_floats) {
+  extern __shared__ __align__(16) float lo_stage[];
   const int b = blockIdx.x;
   __shared__ LmShared sh;
   __shared__ int s_cnt[2];
@@ -354,6 +379,18 @@ lo_solve_kernel(int phase, const float *__restrict__ surf_res, const int *__rest
   rs.n_corner_slots = phase == 2 ? cslots : 0;
   double *x = lo_params + b * 6;
   double *tr = trace ? trace + (size_t)b * trace_cap * 7 : nullptr;
+  // staged copy of the valid blocks (always fits for the supported ring counts; otherwise the global arrays are swept)
+  LoStagedSet ss{lo_stage, 0, lo_stage, 0};
+  const bool staged = ns * 12 + nc * 9 <= stage_floats && (phase == 1 ? ns >= 10 : nc >= 10);
+  if (staged) {
+    const float *gs = rs.surf, *gc = rs.corner;
+    ss.n_surf = stage_blocks<float, 12>(sslots, lo_stage, [&](int i) { return sc[i * 4 + 1] >= 0; },
+                                        [&](int i, float *d) { for (int q = 0; q < 12; ++q) d[q] = gs[(size_t)i * 12 + q]; }, s_red);
+    ss.corner = lo_stage + (size_t)ss.n_surf * 12;
+    if (phase == 2)
+      ss.n_corner = stage_blocks<float, 9>(cslots, lo_stage + (size_t)ss.n_surf * 12, [&](int i) { return cc[i * 3 + 1] >= 0; },
+                                           [&](int i, float *d) { for (int q = 0; q < 9; ++q) d[q] = gc[(size_t)i * 9 + q]; }, s_red);
+  }
   if (phase == 1) {
     if (threadIdx.x == 0) {
       trace_n[b] = 0;
@@ -362,14 +399,16 @@ lo_solve_kernel(int phase, const float *__restrict__ surf_res, const int *__rest
     }
     __syncthreads();
     if (ns >= 10) {  // (:410)
-      const LmResult r = block_lm_solve(rs, x, surf_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
+      const LmResult r = staged ? block_lm_solve(ss, x, surf_iters, huber_a, &sh, tr, trace_n + b, trace_cap)
+                                : block_lm_solve(rs, x, surf_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
       if (threadIdx.x == 0) { rep->iterations = r.iterations; rep->initial_cost = r.initial_cost; rep->final_cost = r.final_cost; }
     }
     return;
   }
   // phase 2
   if (nc >= 10) {  // (:484)
-    const LmResult r = block_lm_solve(rs, x, corner_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
+    const LmResult r = staged ? block_lm_solve(ss, x, corner_iters, huber_a, &sh, tr, trace_n + b, trace_cap)
+                              : block_lm_solve(rs, x, corner_iters, huber_a, &sh, tr, trace_n + b, trace_cap);
     if (threadIdx.x == 0) {
       if (rep->iterations == 0 && ns < 10) rep->initial_cost = r.initial_cost;
       rep->iterations += r.iterations;
@@ -401,24 +440,31 @@ int lo_scan2scan_device(AlegoHandle *h) {
   cudaStream_t s = h->stream;
   const int cur = h->cur, prev = 1 - cur;
   const double gate = h->P.nearest_feature_dist, hub = h->P.huber_delta;
+  // shared-memory staging of the residual blocks: every surf (12 floats) and corner (9 floats) slot, capped at 200 KB
+  const size_t lo_stage_bytes = std::min<size_t>((size_t)R * (24 * 12 + 12 * 9) * sizeof(float), 200 * 1024);
+  static bool lo_attr_set = false;
+  if (!lo_attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(lo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    lo_attr_set = true;
+  }
   { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
   { LAUNCH(h, "lo_assoc_surf");
     lo_assoc_kernel<true, LO_G_SURF><<<dim3(div_up(R * 24, ASSOC_THREADS / LO_G_SURF), B), ASSOC_THREADS, 0, s>>>(
         h->flat, R * 24, h->n_feat, h->less_flat[prev], (size_t)RC, h->lf_ring_off[prev], h->g_surf_last, h->lo_pose, h->lo_init,
         h->lo_surf_res, h->lo_surf_corr, R, gate, h->az_pts[prev], h->az_off[prev]); }
   { LAUNCH(h, "lo_solve_surf");
-    lo_solve_kernel<<<B, 256, 0, s>>>(1, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
+    lo_solve_kernel<<<B, 256, lo_stage_bytes, s>>>(1, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
-                                      h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub); }
+                                      h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub, (int)(lo_stage_bytes / sizeof(float))); }
   { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
   { LAUNCH(h, "lo_assoc_corner");
     lo_assoc_kernel<false, LO_G_CORNER><<<dim3(div_up(R * 12, ASSOC_THREADS / LO_G_CORNER), B), ASSOC_THREADS, 0, s>>>(
         h->sharp, R * 12, h->n_feat, h->less_sharp[prev], (size_t)R * 120, h->ls_ring_off[prev], h->g_corner_last, h->lo_pose,
         h->lo_init, h->lo_corner_res, h->lo_corner_corr, R, gate, nullptr, nullptr); }
   { LAUNCH(h, "lo_solve_corner");
-    lo_solve_kernel<<<B, 256, 0, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
+    lo_solve_kernel<<<B, 256, lo_stage_bytes, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
-                                      h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub); }
+                                      h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub, (int)(lo_stage_bytes / sizeof(float))); }
   { LAUNCH(h, "lo_snapshot"); lo_snapshot_kernel<<<div_up(B, 128), 128, 0, s>>>(h->t_w, h->r_w, h->o2l_lo[cur], B); }
   // the current clouds become the targets of the next sweep (:531-534): index them, then flip the buffers
   int rc = grid_build(h, &h->g_surf_last, h->less_flat[cur], (size_t)RC, h->lf_ring_off[cur] + R, R + 1, "surf_last");

@@ -180,6 +180,25 @@ __device__ __forceinline__ bool chol6_solve(double A[6][6], const double *g, dou
   return true;
 }
 
+// Ordered compaction of the valid residual blocks of one sequence into shared memory: the trust-region loop sweeps the
+// residuals once per iteration, and with one CTA per sequence each global-memory round trip of that sweep is exposed
+// latency — staged blocks are read at shared-memory latency and the threads no longer idle on empty slots.
+// valid(i) / copy(i, dst): slot i of n_slots; W words of type T per block.  smem: >= 33 ints.  Returns the number staged.
+template <typename T, int W, class Valid, class Copy>
+__device__ __forceinline__ int stage_blocks(int n_slots, T *dst, Valid valid, Copy copy, int *smem) {
+  int run = 0;
+  for (int c0 = 0; c0 < n_slots; c0 += blockDim.x) {
+    const int i = c0 + threadIdx.x;
+    const bool v = i < n_slots && valid(i);
+    int total;
+    const int ex = block_excl_scan(v ? 1 : 0, smem, &total);
+    if (v) copy(i, dst + (size_t)(run + ex) * W);
+    run += total;
+  }
+  __syncthreads();
+  return run;
+}
+
 struct LmResult {
   int iterations;
   double initial_cost, final_cost;
