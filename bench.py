@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default="hdl64_1800", choices=sorted(PRESETS))
-    ap.add_argument("--n-seq", type=int, default=128, help="independent sequences per GPU")
+    ap.add_argument("--n-seq", type=int, default=256, help="independent sequences per GPU")
     ap.add_argument("--lm-every", type=int, default=1, help="LaserMapping on every k-th sweep (reference: 2)")
     ap.add_argument("--map-corner", type=int, default=50000)
     ap.add_argument("--map-surf", type=int, default=200000)
