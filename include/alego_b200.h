@@ -193,8 +193,9 @@ int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t 
 int alego_pipeline_collect(AlegoHandle *h, double *poses_out);
 /* lm_every: run LM on every k-th sweep (reference: 2, laserMapping.cpp:112); 0 disables LM.
  * rebuild_map_index_every_step: rebuild the local-map search index on every mapped sweep, like the reference's kd-tree
- * builds (laserMapping.cpp:356-357), instead of only after alego_lm_set_map.  options: 0 default; a negative value
- * disables the side-stream overlap of that rebuild (debugging). */
+ * builds (laserMapping.cpp:356-357), instead of only after alego_lm_set_map.  options: 0 default — the LaserMapping stage
+ * of sweep t (index build + scan-to-map) runs on a second stream and overlaps ImageProjection + LaserOdometry of sweep
+ * t+1, like the reference's separate nodes; a negative value keeps everything on one stream (debugging). */
 int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_every_step, int options);
 
 /* ---- stand-alone operators (used by LO/LM internally, exposed for tests and callers) ------------- */
