@@ -369,8 +369,8 @@ __device__ __forceinline__ CellClass classify(int cell, int row, int col, const 
   c.feasible = false;
   if (c.valid) {
     const int2 s = stat[root];
-    const int rows = s.y - root / P.C + 1;
-    c.feasible = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && rows >= P.seg_valid_line_num);  // (:282-301)
+    // (:282-301) the distinct-row count (an integer division) only matters for the small clusters
+    c.feasible = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && s.y - root / P.C + 1 >= P.seg_valid_line_num);
   }
   const bool g = gr[cell] == 1;
   // (:164-181) kept: feasible cluster cells, and ground cells on every 5th column or the 5-column borders
@@ -509,8 +509,7 @@ __global__ void __launch_bounds__(256) ip_label_kernel(const int *__restrict__ p
     int lab = -1;
     if (root >= 0) {
       const int2 s = comp_stat[base + root];
-      const int rows = s.y - root / P.C + 1;
-      const bool feas = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && rows >= P.seg_valid_line_num);
+      const bool feas = s.x >= P.seg_min_cluster || (s.x >= P.seg_valid_point_num && s.y - root / P.C + 1 >= P.seg_valid_line_num);
       lab = feas ? comp_id[base + root] : ALEGO_LABEL_INVALID;
     }
     label[base + cell] = lab;

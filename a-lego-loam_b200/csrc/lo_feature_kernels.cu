@@ -94,6 +94,69 @@ __device__ __forceinline__ void segment_bounds(int start, int end, int j, int &s
 //  * depth-limit heapsort (never reached on non-adversarial data) runs on lane 0 with the sequential clone.
 // tools/proto_parallel_introsort.py checks this formulation against the real std::sort; tests/test_gpu_parity.py
 // checks the kernel's cloud_sort_idx_ against the oracle's on tie-heavy sweeps.
+// Fast path of K8a: when all curvatures of a segment are distinct the permutation std::sort leaves is simply the ascending
+// order, which a register bitonic network over (key, position) produces in a quarter of the instructions of the introsort
+// clone (NR elements per lane, partners >= 32 apart live in the same lane).  Returns false — nothing written — when two
+// equal keys meet, i.e. when the result depends on introsort's tie behaviour.
+template <int NR>
+__device__ __forceinline__ bool warp_sort_distinct(const float *__restrict__ keys_in, int n, int *__restrict__ out, int out_base) {
+  const int lane = threadIdx.x & 31;
+  unsigned key[NR];
+  int idx[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int e = lane + 32 * r;
+    key[r] = e < n ? __float_as_uint(keys_in[e]) : 0xffffffffu;
+    idx[r] = e < n ? e : 0x7fffffff;
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * NR; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int e = lane + 32 * r;
+        unsigned ok;
+        int oi;
+        if (j >= 32) {
+          if ((r & (j >> 5)) != 0) continue;  // handled together with the partner register below
+          const int r2 = r | (j >> 5);
+          const bool up = (e & k) == 0;
+          const bool gt = key[r] > key[r2] || (key[r] == key[r2] && idx[r] > idx[r2]);
+          if (gt == up) {
+            const unsigned tk = key[r]; key[r] = key[r2]; key[r2] = tk;
+            const int ti = idx[r]; idx[r] = idx[r2]; idx[r2] = ti;
+          }
+          continue;
+        }
+        ok = __shfl_xor_sync(0xffffffffu, key[r], j);
+        oi = __shfl_xor_sync(0xffffffffu, idx[r], j);
+        const bool up = (e & k) == 0, lower = (e & j) == 0;
+        const bool other_less = ok < key[r] || (ok == key[r] && oi < idx[r]);
+        // the lower element of an ascending pair keeps the minimum, the upper one the maximum (reversed when descending)
+        if ((up == lower) == other_less) { key[r] = ok; idx[r] = oi; }
+      }
+    }
+  }
+  // ties between real elements?  (element e+1 lives in lane+1, or in lane 0 of the next register)
+  bool tie = false;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    unsigned nk = __shfl_down_sync(0xffffffffu, key[r], 1);
+    const unsigned wrap = r + 1 < NR ? __shfl_sync(0xffffffffu, key[r + 1 < NR ? r + 1 : r], 0) : 0xffffffffu;
+    if (lane == 31) nk = wrap;
+    const int e = lane + 32 * r;
+    tie |= e + 1 < n && nk == key[r];
+  }
+  if (__any_sync(0xffffffffu, tie)) return false;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int e = lane + 32 * r;
+    if (e < n) out[e] = out_base + idx[r];
+  }
+  return true;
+}
+
 #define SORT_WARPS 8
 __device__ __forceinline__ unsigned ss_key(unsigned long long e) { return (unsigned)(e >> 32); }
 __device__ __forceinline__ unsigned ss_pack(int f, int l, int depth) { return (unsigned)f | ((unsigned)l << 11) | ((unsigned)depth << 22); }
@@ -119,6 +182,15 @@ lo_sort_segments_kernel(const float *__restrict__ curv, const int *__restrict__ 
       for (int k = 0; k < n; ++k) sort_idx[base + sp + k] = (int)(e[k] & 0xffffffffu);
     }
     return;
+  }
+  {  // distinct keys (the common case): plain ascending order
+    const float *kin = curv + base + sp;
+    int *o = sort_idx + base + sp;
+    bool done = false;
+    if (n <= 32) done = warp_sort_distinct<1>(kin, n, o, sp);
+    else if (n <= 64) done = warp_sort_distinct<2>(kin, n, o, sp);
+    else if (n <= 128) done = warp_sort_distinct<4>(kin, n, o, sp);
+    if (done) return;
   }
   const size_t per_warp = (size_t)cap * 14 + 16;
   unsigned long long *e = reinterpret_cast<unsigned long long *>(ss_smem + warp * per_warp);
