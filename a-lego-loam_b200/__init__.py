@@ -117,6 +117,9 @@ def lib():
         "alego_get_params": (C.c_int, [H, C.POINTER(AlegoParams)]),
         "alego_n_seq": (C.c_int, [H]),
         "alego_set_point_stride": (C.c_int, [H, C.c_int]),
+        "alego_lm_assemble_map": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
+        "alego_lm_get_map": (C.c_int, [H, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
         "alego_host_alloc": (C.c_void_p, [C.c_size_t]),
         "alego_host_free": (None, [C.c_void_p]),
         "alego_ip_process": (C.c_int, [H, C.c_void_p, C.c_void_p]),
@@ -161,7 +164,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "alego_default_params", "alego_create", "alego_destroy", "alego_last_error", "alego_synchronize", "alego_get_params",
-    "alego_n_seq", "alego_set_point_stride", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
+    "alego_n_seq", "alego_set_point_stride", "alego_lm_assemble_map", "alego_lm_get_map", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
     "alego_lo_get_features", "alego_lo_scan2scan", "alego_lo_get_state", "alego_lo_set_params", "alego_lm_set_map",
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
     "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
@@ -416,6 +419,29 @@ class Alego:
                 raise AlegoError("debug_get(%s) rc=%d: %s" % (name, got, self.L.alego_last_error(self.h).decode()))
         cols = _DEBUG_COLS.get(name)
         return a.reshape(-1, cols) if cols else a
+
+    def lm_assemble_map(self, seq, corner_kfs, surf_kfs, outlier_kfs, poses6):
+        """Local map of sequence seq from keyframe clouds (lists of (n,4) arrays) and their poses [K][6] (x,y,z,roll,pitch,yaw):
+        alego_lm_assemble_map (laserMapping.cpp:194-323)."""
+        def pack(clouds):
+            clouds = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+            ptrs = (C.c_void_p * max(len(clouds), 1))(*[c.ctypes.data for c in clouds])
+            return clouds, ptrs, np.array([len(c) for c in clouds], np.int32)
+        ck, cp, cn = pack(corner_kfs)
+        sk, sp, sn = pack(surf_kfs)
+        ok, op, on = pack(outlier_kfs)
+        poses6 = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+        self._cap_map = (int(cn.sum()), int(sn.sum() + on.sum()))
+        return self._chk(self.L.alego_lm_assemble_map(self.h, seq, len(ck), cp, _ptr(cn), sp, _ptr(sn), op, _ptr(on), _ptr(poses6)))
+
+    def lm_get_map(self, seq=0):
+        """(corner_from_map_ds_, surf_from_map_ds_) of sequence seq as (n,4) arrays."""
+        nc, ns = C.c_int32(0), C.c_int32(0)
+        self._chk(self.L.alego_lm_get_map(self.h, seq, None, C.byref(nc), None, C.byref(ns)))
+        c = np.zeros((max(nc.value, 1), 4), np.float32)
+        s = np.zeros((max(ns.value, 1), 4), np.float32)
+        self._chk(self.L.alego_lm_get_map(self.h, seq, _ptr(c), C.byref(nc), _ptr(s), C.byref(ns)))
+        return c[:nc.value], s[:ns.value]
 
     def solve_report(self, stage, seq=0):
         """AlegoSolveReport of the last LaserOdometry ("lo") / LaserMapping ("lm") solve of sequence seq, as a dict."""

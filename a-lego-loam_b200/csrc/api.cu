@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <vector>
 
 #include "common.cuh"
 #include "grid.cuh"
@@ -577,6 +578,90 @@ int alego_lm_set_map(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t 
   CUDA_TRY(h, cudaMemcpyAsync(h->n_map_surf + seq, &n_surf, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->map_index_valid = false;
+  return ALEGO_OK;
+}
+
+// Rotation of a keyframe pose the way transformPointCloud builds it (laserMapping.h:163-177):
+// (AngleAxisf(yaw, Z) * AngleAxisf(pitch, Y) * AngleAxisf(roll, X)).toRotationMatrix() — Eigen turns every AngleAxis into a
+// quaternion (w = cos(a/2), axis * sin(a/2)), multiplies the quaternions and expands the product; all in float, evaluated
+// on the host like the reference does.  M: row-major 3x4 (rotation | translation).
+static void keyframe_matrix(const float pose6[6], float M[12]) {
+  auto quat = [](float angle, int axis, float q[4]) {
+    const float ha = 0.5f * angle;
+    q[0] = std::cos(ha); q[1] = q[2] = q[3] = 0.f;
+    q[1 + axis] = std::sin(ha);
+  };
+  auto mul = [](const float a[4], const float b[4], float o[4]) {
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+  };
+  float qz[4], qy[4], qx[4], qzy[4], q[4];
+  quat(pose6[5], 2, qz); quat(pose6[4], 1, qy); quat(pose6[3], 0, qx);
+  mul(qz, qy, qzy);
+  mul(qzy, qx, q);
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M[0] = 1.f - (tyy + tzz); M[1] = txy - twz;         M[2] = txz + twy;          M[3] = pose6[0];
+  M[4] = txy + twz;         M[5] = 1.f - (txx + tzz); M[6] = tyz - twx;          M[7] = pose6[1];
+  M[8] = txz - twy;         M[9] = tyz + twx;         M[10] = 1.f - (txx + tyy); M[11] = pose6[2];
+}
+
+int alego_lm_assemble_map(AlegoHandle *h, int seq, int n_keyframes, const float *const *corner_xyzi, const int32_t *n_corner,
+                          const float *const *surf_xyzi, const int32_t *n_surf, const float *const *outlier_xyzi,
+                          const int32_t *n_outlier, const float *poses6) {
+  int rc = check(h, seq);
+  if (rc != ALEGO_OK) return rc;
+  if (n_keyframes < 0 || (n_keyframes && (!corner_xyzi || !n_corner || !surf_xyzi || !n_surf || !outlier_xyzi || !n_outlier || !poses6)))
+    return ALEGO_BAD_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
+  const int K = n_keyframes;
+  std::vector<float> M((size_t)std::max(K, 1) * 12);
+  std::vector<const float *> cp(K), sp(2 * (size_t)K);
+  std::vector<int> cn(K), sn(2 * (size_t)K);
+  long long tot_c = 0, tot_s = 0;
+  for (int k = 0; k < K; ++k) {
+    if (n_corner[k] < 0 || n_surf[k] < 0 || n_outlier[k] < 0 || (n_corner[k] && !corner_xyzi[k]) || (n_surf[k] && !surf_xyzi[k]) ||
+        (n_outlier[k] && !outlier_xyzi[k]))
+      return ALEGO_BAD_ARG;
+    keyframe_matrix(poses6 + (size_t)k * 6, M.data() + (size_t)k * 12);
+    cp[k] = corner_xyzi[k]; cn[k] = n_corner[k];
+    // surf_from_map_ += surf keyframe, then the outlier keyframe (:239-243)
+    sp[2 * k] = surf_xyzi[k]; sn[2 * k] = n_surf[k];
+    sp[2 * k + 1] = outlier_xyzi[k]; sn[2 * k + 1] = n_outlier[k];
+    tot_c += n_corner[k];
+    tot_s += (long long)n_surf[k] + n_outlier[k];
+  }
+  if (tot_c > 0x3fffffff || tot_s > 0x3fffffff) { h->err = "alego_lm_assemble_map: too many points"; return ALEGO_BAD_ARG; }
+  const int old_c = h->map_cap_c, old_s = h->map_cap_s;
+  if ((rc = realloc_keep(h, &h->map_corner, &h->map_cap_c, (int)tot_c)) != ALEGO_OK) return rc;
+  if ((rc = realloc_keep(h, &h->map_surf, &h->map_cap_s, (int)tot_s)) != ALEGO_OK) return rc;
+  if (h->map_cap_c != old_c && (rc = grid_alloc(h, &h->g_map_corner, h->map_cap_c, 1.01f, 1)) != ALEGO_OK) return rc;
+  if (h->map_cap_s != old_s && (rc = grid_alloc(h, &h->g_map_surf, h->map_cap_s, 1.01f, 1)) != ALEGO_OK) return rc;
+  // ds_corner_ / ds_surf_ (:316-319)
+  if ((rc = lm_assemble_cloud(h, cp.data(), cn.data(), K, M.data(), std::max(K, 1), 0, (float)h->P.lm_corner_leaf,
+                              h->map_corner + (size_t)seq * h->map_cap_c, h->n_map_corner + seq)) != ALEGO_OK) return rc;
+  if ((rc = lm_assemble_cloud(h, sp.data(), sn.data(), 2 * K, M.data(), std::max(K, 1), 1, (float)h->P.lm_surf_leaf,
+                              h->map_surf + (size_t)seq * h->map_cap_s, h->n_map_surf + seq)) != ALEGO_OK) return rc;
+  h->map_index_valid = false;
+  return ALEGO_OK;
+}
+
+int alego_lm_get_map(AlegoHandle *h, int seq, float *corner_xyzi, int32_t *n_corner, float *surf_xyzi, int32_t *n_surf) {
+  int rc = check(h, seq);
+  if (rc != ALEGO_OK) return rc;
+  if (!h->map_corner || !h->map_surf) { h->err = "alego_lm_get_map: no local map"; return ALEGO_NOT_READY; }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  int nc = 0, ns = 0;
+  if ((rc = fetch_int(h, h->n_map_corner + seq, &nc)) != ALEGO_OK) return rc;
+  if ((rc = fetch_int(h, h->n_map_surf + seq, &ns)) != ALEGO_OK) return rc;
+  if (n_corner) *n_corner = nc;
+  if (n_surf) *n_surf = ns;
+  if (corner_xyzi && (rc = d2h(h, corner_xyzi, h->map_corner + (size_t)seq * h->map_cap_c, (size_t)nc * sizeof(float4))) != ALEGO_OK) return rc;
+  if (surf_xyzi && (rc = d2h(h, surf_xyzi, h->map_surf + (size_t)seq * h->map_cap_s, (size_t)ns * sizeof(float4))) != ALEGO_OK) return rc;
   return ALEGO_OK;
 }
 

@@ -9,6 +9,9 @@
 // K15   lm_assoc<PLANE> : per surf query — 5-NN, 5x3 least squares A n = -1, normalise, 0.2 m test (:419-462)
 // K16/K17 lm_solve   : one CTA per sequence — LidarEdge/LidarPlane residuals, Huber, 6x6 reduction, LM
 //                      (solver.cuh), lm_outer_iters fresh solves (:360-478), transformUpdate (:481-489)
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "grid.cuh"
 #include "lm_kernels.cuh"
@@ -637,3 +640,64 @@ int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float 
 }
 
 int lm_ensure_buffers(AlegoHandle *h, int need_c, int need_s, int need_o) { return lm_ensure_ds_buffers(h, need_c, need_s, need_o); }
+
+// ---------------------------------------------------------------------------------------------------
+// N1: local-map assembly — the cloud side of extractSurroundingKeyFrames (laserMapping.cpp:194-323).
+namespace {
+// pcl::transformPointCloud (PCL 1.8 transforms.hpp) on a concatenation of segments: point i of segment s is mapped by
+// matrix s >> mat_shift (row-major 3x4 floats), x' = m00*x + m01*y + m02*z + m03 evaluated left to right in float,
+// intensity copied (laserMapping.h:163-177).
+__global__ void __launch_bounds__(256) lm_kf_transform_kernel(float4 *__restrict__ pts, int n, const int *__restrict__ seg_off, int n_seg,
+                                                              const float *__restrict__ M, int mat_shift) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_seg;  // segment s with seg_off[s] <= i < seg_off[s+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const float *m = M + (size_t)(lo >> mat_shift) * 12;
+    const float4 p = pts[i];
+    float4 o;
+    o.x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    o.y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    o.z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    o.w = p.w;
+    pts[i] = o;
+  }
+}
+}  // namespace
+
+// segs: n_seg host clouds (pointer, count) concatenated in order, transformed by M[s >> mat_shift], VoxelGrid(leaf) into
+// dst[0..*] on the device, count into n_dst (device).  Scratch is allocated per call: this runs once per keyframe.
+int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *seg_n, int n_seg, const float *M_host, int n_mat,
+                      int mat_shift, float leaf, float4 *dst, int *n_dst) {
+  cudaStream_t s = h->stream;
+  std::vector<int> off(n_seg + 1, 0);
+  for (int k = 0; k < n_seg; ++k) off[k + 1] = off[k] + seg_n[k];
+  const int n = off[n_seg];
+  if (n == 0) {
+    CUDA_TRY(h, cudaMemsetAsync(n_dst, 0, sizeof(int), s));
+    return ALEGO_OK;
+  }
+  float4 *d_in = nullptr;
+  u64 *d_keys = nullptr;
+  int *d_off = nullptr;
+  float *d_M = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d_in, (size_t)n * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)2 * n * sizeof(u64)));
+  CUDA_TRY(h, cudaMalloc(&d_off, (size_t)(n_seg + 1) * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&d_M, (size_t)n_mat * 12 * sizeof(float)));
+  for (int k = 0; k < n_seg; ++k)
+    if (seg_n[k] > 0)
+      CUDA_TRY(h, cudaMemcpyAsync(d_in + off[k], seg_ptr[k], (size_t)seg_n[k] * sizeof(float4), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), (size_t)(n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(d_M, M_host, (size_t)n_mat * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+  { LAUNCH(h, "lm_kf_transform");
+    lm_kf_transform_kernel<<<std::min(div_up(n, 256), 2048), 256, 0, s>>>(d_in, n, d_off, n_seg, d_M, mat_shift); }
+  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
+  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM, s>>>(d_in, n, leaf, dst, d_keys, n_dst); }
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(s));  // the host clouds and the scratch are released on return
+  cudaFree(d_in); cudaFree(d_keys); cudaFree(d_off); cudaFree(d_M);
+  return ALEGO_OK;
+}

@@ -7,3 +7,6 @@ int lm_build_map_index(AlegoHandle *h);                                     // l
 // index_ready: the caller has (re)built the local-map index already; launches go to h->launch_stream when it is set
 int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool index_ready);  // laserMapping.cpp:325-489
 int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float *out_xyzi, int *n_out);
+// N1 (laserMapping.cpp:194-323): concatenate host clouds, transform each by its keyframe matrix, VoxelGrid into dst (device)
+int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *seg_n, int n_seg, const float *M_host, int n_mat,
+                      int mat_shift, float leaf, float4 *dst, int *n_dst);

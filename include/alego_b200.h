@@ -160,6 +160,19 @@ int alego_lo_set_params(AlegoHandle *h, int seq, const double params[6]);
  * its kd-trees every mapped frame). */
 int alego_lm_set_map(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t n_corner, const float *surf_xyzi,
                      int32_t n_surf);
+/* Local-map assembly: the cloud side of LaserMapping::extractSurroundingKeyFrames (laserMapping.cpp:194-323) and
+ * transformPointCloud (laserMapping.h:163-177).  The caller selects the keyframes (the deque of the 50 most recent ones,
+ * :206-243, or the radius search, :246-311) and passes their stored clouds (corner_frames_ / surf_frames_ /
+ * outlier_frames_, host memory, xyzi) with their poses (cloud_keyposes_6d_: x, y, z, roll, pitch, yaw, float); the device
+ * transforms every cloud by its pose, concatenates them in keyframe order — corner_from_map_ += corner;
+ * surf_from_map_ += surf, then outlier (:239-243) — and applies ds_corner_ (lm_corner_leaf) / ds_surf_ (lm_surf_leaf)
+ * (:316-319).  The result becomes the local map of sequence `seq` exactly as after alego_lm_set_map, without leaving
+ * the device.  alego_lm_get_map reads corner_from_map_ds_ / surf_from_map_ds_ back (buffers sized by the caller: at most
+ * the total number of input points; any pointer may be NULL). */
+int alego_lm_assemble_map(AlegoHandle *h, int seq, int n_keyframes, const float *const *corner_xyzi, const int32_t *n_corner,
+                          const float *const *surf_xyzi, const int32_t *n_surf, const float *const *outlier_xyzi,
+                          const int32_t *n_outlier, const float *poses6 /*[n_keyframes][6]*/);
+int alego_lm_get_map(AlegoHandle *h, int seq, float *corner_xyzi, int32_t *n_corner, float *surf_xyzi, int32_t *n_surf);
 /* Stand-alone inputs for sequence `seq` (the /corner_last, /surf_last, /outlier clouds of
  * laserMapping.cpp:133-153) and the odometry prediction odom2laser (:154-164). When not called, the
  * clouds produced on the device by the LO stage of the same handle are used. */

@@ -1439,6 +1439,69 @@ int oracle_voxel_grid(const float *xyzi, int n, float leaf, int stable, float *o
   if (keys && !k.empty()) std::memcpy(keys, k.data(), k.size() * sizeof(unsigned));
   return ALEGO_OK;
 }
+// ---- N1: local-map assembly, the cloud side of extractSurroundingKeyFrames (src/laserMapping.cpp:194-323) ----------
+// transformPointCloud (include/alego/laserMapping.h:163-177): Matrix4f from
+// (AngleAxisf(yaw, Z) * AngleAxisf(pitch, Y) * AngleAxisf(roll, X)).toRotationMatrix() — Eigen (unpinned, not in the
+// container; restated from Eigen 3.3 Geometry/AngleAxis.h, Quaternion.h) converts every AngleAxis to a quaternion
+// (w = cos(a/2), vec = sin(a/2) * axis), multiplies the quaternions (generic quat_product) and expands toRotationMatrix();
+// then pcl::transformPointCloud (PCL 1.8 common/impl/transforms.hpp): x' = m00*x + m01*y + m02*z + m03 in float, left to
+// right, intensity copied.  corner_from_map_ += corner keyframes; surf_from_map_ += surf keyframe, then outlier keyframe
+// (:239-243); ds_corner_ (0.4) / ds_surf_ (0.8) VoxelGrid (:316-319).
+static void keyframe_matrix(const float pose6[6], float M[12]) {
+  auto quat = [](float angle, int axis, float q[4]) {
+    const float ha = 0.5f * angle;
+    q[0] = std::cos(ha); q[1] = q[2] = q[3] = 0.f;
+    q[1 + axis] = std::sin(ha);
+  };
+  auto mul = [](const float a[4], const float b[4], float o[4]) {
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+  };
+  float qz[4], qy[4], qx[4], qzy[4], q[4];
+  quat(pose6[5], 2, qz); quat(pose6[4], 1, qy); quat(pose6[3], 0, qx);
+  mul(qz, qy, qzy);
+  mul(qzy, qx, q);
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M[0] = 1.f - (tyy + tzz); M[1] = txy - twz;         M[2] = txz + twy;          M[3] = pose6[0];
+  M[4] = txy + twz;         M[5] = 1.f - (txx + tzz); M[6] = tyz - twx;          M[7] = pose6[1];
+  M[8] = txz - twy;         M[9] = tyz + twx;         M[10] = 1.f - (txx + tyy); M[11] = pose6[2];
+}
+static void append_transformed(const float *xyzi, int n, const float M[12], vector<P4> &out) {
+  const P4 *p = reinterpret_cast<const P4 *>(xyzi);
+  for (int i = 0; i < n; ++i) {
+    P4 o;
+    o.x = M[0] * p[i].x + M[1] * p[i].y + M[2] * p[i].z + M[3];
+    o.y = M[4] * p[i].x + M[5] * p[i].y + M[6] * p[i].z + M[7];
+    o.z = M[8] * p[i].x + M[9] * p[i].y + M[10] * p[i].z + M[11];
+    o.i = p[i].i;
+    out.push_back(o);
+  }
+}
+int oracle_lm_assemble_map(int n_kf, const float *const *corner, const int *nc, const float *const *surf, const int *ns,
+                           const float *const *outl, const int *no, const float *poses6, float leaf_c, float leaf_s, int stable,
+                           float *corner_out, int *n_corner_out, float *surf_out, int *n_surf_out, float *matrices_out) {
+  vector<P4> cm, sm, cds, sds;
+  for (int k = 0; k < n_kf; ++k) {
+    float M[12];
+    keyframe_matrix(poses6 + (size_t)k * 6, M);
+    if (matrices_out) std::memcpy(matrices_out + (size_t)k * 12, M, sizeof M);
+    append_transformed(corner[k], nc[k], M, cm);
+    append_transformed(surf[k], ns[k], M, sm);
+    append_transformed(outl[k], no[k], M, sm);
+  }
+  voxel_grid(cm, leaf_c, cds, stable != 0);
+  voxel_grid(sm, leaf_s, sds, stable != 0);
+  *n_corner_out = (int)cds.size();
+  *n_surf_out = (int)sds.size();
+  if (corner_out && !cds.empty()) std::memcpy(corner_out, cds.data(), cds.size() * sizeof(P4));
+  if (surf_out && !sds.empty()) std::memcpy(surf_out, sds.data(), sds.size() * sizeof(P4));
+  return ALEGO_OK;
+}
+
 // k-NN of nq queries against n points; idx [nq][k], dist [nq][k]; brute!=0 uses the O(n) scan
 int oracle_knn(const float *pts, int n, const float *q, int nq, int k, int brute, int32_t *idx, float *dist) {
   if (k < 1 || k > 8) return ALEGO_BAD_ARG;

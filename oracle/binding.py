@@ -52,6 +52,9 @@ def lib():
         L.oracle_lstsq5x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_std_sort_by_key.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_default_params.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_lm_assemble_map.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                             C.POINTER(C.c_int), C.c_void_p]
         _lib = L
     return _lib
 
@@ -168,6 +171,30 @@ def voxel_grid(pts, leaf, stable=False):
     n = C.c_int(0)
     lib().oracle_voxel_grid(_p(pts), len(pts), leaf, int(stable), _p(out), C.byref(n), _p(keys))
     return out[:n.value], keys[:n.value]
+
+
+def _cloud_ptrs(clouds):
+    clouds = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+    ptrs = (C.c_void_p * max(len(clouds), 1))(*[c.ctypes.data for c in clouds])
+    counts = np.array([len(c) for c in clouds], np.int32)
+    return clouds, ptrs, counts
+
+
+def lm_assemble_map(corner_kfs, surf_kfs, outlier_kfs, poses6, leaf_c=0.4, leaf_s=0.8, stable=True):
+    """extractSurroundingKeyFrames' cloud side (laserMapping.cpp:194-323): returns (corner_from_map_ds, surf_from_map_ds,
+    the K row-major 3x4 keyframe matrices)."""
+    K = len(corner_kfs)
+    ck, cp, cn = _cloud_ptrs(corner_kfs)
+    sk, sp, sn = _cloud_ptrs(surf_kfs)
+    ok, op, on = _cloud_ptrs(outlier_kfs)
+    poses6 = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+    co = np.zeros((max(int(cn.sum()), 1), 4), np.float32)
+    so = np.zeros((max(int(sn.sum() + on.sum()), 1), 4), np.float32)
+    M = np.zeros((max(K, 1), 12), np.float32)
+    nco, nso = C.c_int(0), C.c_int(0)
+    lib().oracle_lm_assemble_map(K, cp, _p(cn), sp, _p(sn), op, _p(on), _p(poses6), leaf_c, leaf_s, int(stable), _p(co), C.byref(nco),
+                                 _p(so), C.byref(nso), _p(M))
+    return co[:nco.value], so[:nso.value], M[:K]
 
 
 def knn(pts, q, k, brute=False):

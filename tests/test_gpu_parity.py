@@ -377,6 +377,51 @@ def test_scan_to_map_parity(alego, ob, n_corner, n_surf):
     g.close()
 
 
+def test_local_map_assembly_parity(alego, ob):
+    """alego_lm_assemble_map (N1, laserMapping.cpp:194-323) against the oracle: the assembled, voxel-filtered local map is
+    bit-exact, ragged / empty keyframes included, and scan-to-map on it equals scan-to-map on the same map uploaded with
+    alego_lm_set_map."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    w = alego.SynthWorld(seed=9)
+    corner, surf = w.make_map(6000, 30000, seed=9, radius=60.0)
+    rng = np.random.default_rng(9)
+    K = 7
+    # keyframes: random subsets of the world's structure expressed in each keyframe's own frame (inverse pose applied in double)
+    poses = (rng.uniform(-1, 1, (K, 6)) * np.array([8, 8, 0.2, 0.02, 0.02, 1.5])).astype(np.float32)
+    def to_kf(cloud, pose):
+        r, p, y = (float(v) for v in pose[3:])
+        Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(p), 0, np.sin(p)], [0, 1, 0], [-np.sin(p), 0, np.cos(p)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+        R = Rz @ Ry @ Rx
+        out = cloud.copy()
+        out[:, :3] = ((cloud[:, :3].astype(np.float64) - pose[:3].astype(np.float64)) @ R).astype(np.float32)
+        return out
+    ck = [to_kf(corner[rng.choice(len(corner), 900, replace=False)], poses[k]) for k in range(K)]
+    sk = [to_kf(surf[rng.choice(len(surf), 5000, replace=False)], poses[k]) for k in range(K)]
+    okf = [to_kf(surf[rng.choice(len(surf), 300, replace=False)], poses[k]) for k in range(K)]
+    ck[2] = ck[2][:0]      # ragged: an empty corner keyframe, an empty outlier keyframe
+    okf[4] = okf[4][:0]
+    want_c, want_s, _ = ob.lm_assemble_map(ck, sk, okf, poses, P.lm_corner_leaf, P.lm_surf_leaf, stable=True)
+    g = alego.Alego(P, n_seq=2)
+    g.lm_assemble_map(1, ck, sk, okf, poses)
+    got_c, got_s = g.lm_get_map(1)
+    assert np.array_equal(got_c, want_c), "corner_from_map_ds: " + first_diff(got_c, want_c)
+    assert np.array_equal(got_s, want_s), "surf_from_map_ds: " + first_diff(got_s, want_s)
+    # no keyframes yet (:202-205): empty map
+    g.lm_assemble_map(0, [], [], [], np.zeros((0, 6), np.float32))
+    e_c, e_s = g.lm_get_map(0)
+    assert len(e_c) == 0 and len(e_s) == 0
+    # the assembled map serves scan-to-map like an uploaded one
+    g.lm_set_map(0, want_c, want_s)
+    scan = w.render(P, alego.trajectory_pose(1, seed=9), noise_seed=77)
+    g.pipeline_config(lm_every=1)
+    buf, n = g.pack_scans([scan, scan])
+    poses_out = g.pipeline_step(buf, n)
+    assert np.array_equal(poses_out[0], poses_out[1])
+    g.close()
+
+
 def test_lm_guard_few_features(alego, ob):
     P = alego.default_params(alego.PRESET_VLP16_1800)
     w = alego.SynthWorld(seed=2)

@@ -301,3 +301,35 @@ def test_segment_bounds_and_label_numbering_properties(alego, ob):
     assert set(np.unique(labf)) <= {-1, 0, 1, 2}
     assert np.array_equal(np.sort(o.get("sharp_idx")), np.sort(np.nonzero(labf == 2)[0]))
     assert np.array_equal(np.sort(o.get("flat_idx")), np.sort(np.nonzero(labf == -1)[0]))
+
+
+def test_local_map_assembly_restatement(ob):
+    """N1 (laserMapping.cpp:194-323): keyframe matrix = Rz*Ry*Rx (float, via quaternions like Eigen), transformed keyframes are
+    concatenated corner | surf+outlier per keyframe and voxel-filtered; identity poses reduce to VoxelGrid of the concatenation."""
+    rng = np.random.default_rng(3)
+    K = 4
+    c = [rng.uniform(-20, 20, (120, 4)).astype(np.float32) for _ in range(K)]
+    s = [rng.uniform(-20, 20, (700, 4)).astype(np.float32) for _ in range(K)]
+    o = [rng.uniform(-20, 20, (60, 4)).astype(np.float32) for _ in range(K)]
+    poses = np.zeros((K, 6), np.float32)
+    cm, sm, M = ob.lm_assemble_map(c, s, o, poses)
+    ref_c, _ = ob.voxel_grid(np.concatenate(c), 0.4, stable=True)
+    ref_s, _ = ob.voxel_grid(np.concatenate([x for k in range(K) for x in (s[k], o[k])]), 0.8, stable=True)
+    assert np.array_equal(cm, ref_c) and np.array_equal(sm, ref_s)
+    assert np.array_equal(M.reshape(K, 3, 4)[:, :, :3], np.broadcast_to(np.eye(3, dtype=np.float32), (K, 3, 3)))
+    # rotation against a double-precision Rz*Ry*Rx, translation passed through
+    poses = rng.uniform(-1, 1, (K, 6)).astype(np.float32) * np.array([30, 30, 2, 0.05, 0.05, 3.0], np.float32)
+    _, _, M = ob.lm_assemble_map(c, s, o, poses)
+    for k in range(K):
+        r, p, y = (float(v) for v in poses[k, 3:])
+        Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(p), 0, np.sin(p)], [0, 1, 0], [-np.sin(p), 0, np.cos(p)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+        Mk = M[k].reshape(3, 4)
+        assert np.abs(Mk[:, :3] - Rz @ Ry @ Rx).max() < 5e-7
+        assert np.array_equal(Mk[:, 3], poses[k, :3])
+    # one keyframe, one point: the transform itself
+    pt = np.array([[1.5, -2.0, 0.25, 7.0]], np.float32)
+    cm, sm, M = ob.lm_assemble_map([pt], [np.zeros((0, 4), np.float32)], [np.zeros((0, 4), np.float32)], poses[:1])
+    want = M[0].reshape(3, 4)[:, :3].astype(np.float64) @ pt[0, :3].astype(np.float64) + poses[0, :3]
+    assert len(cm) == 1 and len(sm) == 0 and np.allclose(cm[0, :3], want, atol=1e-5) and cm[0, 3] == 7.0
