@@ -434,6 +434,10 @@ class Alego:
         self._cap_map = (int(cn.sum()), int(sn.sum() + on.sum()))
         return self._chk(self.L.alego_lm_assemble_map(self.h, seq, len(ck), cp, _ptr(cn), sp, _ptr(sn), op, _ptr(on), _ptr(poses6)))
 
+    def lm_get_downsampled(self, seq=0):
+        """(laser_corner_ds_, laser_surf_ds_, laser_outlier_ds_) of the last mapped sweep (laserMapping.cpp:325-346)."""
+        return self.debug("lm_corner_ds", seq), self.debug("lm_surf_ds", seq), self.debug("lm_outlier_ds", seq)
+
     def lm_get_map(self, seq=0):
         """(corner_from_map_ds_, surf_from_map_ds_) of sequence seq as (n,4) arrays."""
         nc, ns = C.c_int32(0), C.c_int32(0)

@@ -109,6 +109,50 @@ int LaserMapping::setLocalMap(int seq, const PointCloud &corner, const PointClou
 
 int LaserMapping::process(AlegoSolveReport *reports) { return alego_lm_scan2map(ctx_.handle(), reports); }
 
+int LaserMapping::saveKeyFrame(int seq, const float pose6[6]) {
+  if (seq < 0 || !pose6) return ALEGO_BAD_ARG;
+  if ((int)store_.size() <= seq) store_.resize(seq + 1);
+  const AlegoParams &p = ctx_.params();
+  const size_t cap = (size_t)p.n_scan * p.horizon_scan;
+  KeyFrame kf;
+  kf.corner.resize((size_t)p.n_scan * 120);
+  kf.surf.resize(cap);
+  kf.outlier.resize(cap);
+  int32_t nc = 0, ns = 0, no = 0;
+  const int rc = alego_lm_get_downsampled(ctx_.handle(), seq, &kf.corner[0].x, &nc, &kf.surf[0].x, &ns, &kf.outlier[0].x, &no, nullptr, nullptr);
+  if (rc != ALEGO_OK) return rc;
+  kf.corner.resize(nc); kf.surf.resize(ns); kf.outlier.resize(no);
+  kf.corner.shrink_to_fit(); kf.surf.shrink_to_fit(); kf.outlier.shrink_to_fit();
+  for (int q = 0; q < 6; ++q) kf.pose6[q] = pose6[q];
+  std::deque<KeyFrame> &dq = store_[seq];
+  if (dq.size() >= kRecentKeyframes) dq.pop_front();  // (:230-232)
+  dq.push_back(std::move(kf));
+  return ALEGO_OK;
+}
+
+int LaserMapping::setKeyFramePose(int seq, size_t k, const float pose6[6]) {
+  if (seq < 0 || seq >= (int)store_.size() || k >= store_[seq].size() || !pose6) return ALEGO_BAD_ARG;
+  for (int q = 0; q < 6; ++q) store_[seq][k].pose6[q] = pose6[q];
+  return ALEGO_OK;
+}
+
+int LaserMapping::extractSurroundingKeyFrames(int seq) {
+  if (seq < 0) return ALEGO_BAD_ARG;
+  if ((int)store_.size() <= seq) store_.resize(seq + 1);
+  const std::deque<KeyFrame> &dq = store_[seq];
+  const size_t K = dq.size();
+  std::vector<const float *> cp(K), sp(K), op(K);
+  std::vector<int32_t> cn(K), sn(K), on(K);
+  std::vector<float> poses(K * 6);
+  for (size_t k = 0; k < K; ++k) {
+    cp[k] = dq[k].corner.empty() ? nullptr : &dq[k].corner[0].x; cn[k] = (int32_t)dq[k].corner.size();
+    sp[k] = dq[k].surf.empty() ? nullptr : &dq[k].surf[0].x; sn[k] = (int32_t)dq[k].surf.size();
+    op[k] = dq[k].outlier.empty() ? nullptr : &dq[k].outlier[0].x; on[k] = (int32_t)dq[k].outlier.size();
+    for (int q = 0; q < 6; ++q) poses[k * 6 + q] = dq[k].pose6[q];
+  }
+  return alego_lm_assemble_map(ctx_.handle(), seq, (int)K, cp.data(), cn.data(), sp.data(), sn.data(), op.data(), on.data(), poses.data());
+}
+
 int LaserMapping::pose(int seq, double params[6], double t_map2laser[3], double r_map2laser[9], double t_map2odom[3],
                        double r_map2odom[9]) {
   return alego_lm_get_state(ctx_.handle(), seq, params, t_map2laser, r_map2laser, t_map2odom, r_map2odom);

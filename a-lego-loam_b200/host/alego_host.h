@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "../../include/alego_b200.h"
@@ -96,8 +97,25 @@ class LaserMapping {
   int process(AlegoSolveReport *reports = nullptr);
   int pose(int seq, double params[6], double t_map2laser[3], double r_map2laser[9], double t_map2odom[3], double r_map2odom[9]);
 
+  // ---- keyframe store + local-map assembly (the loop_closure_enabled_ branch of extractSurroundingKeyFrames, :206-243)
+  // saveKeyFramesAndFactor's cloud side (:491-545): keep the current sweep's downsampled clouds (laser_corner_ds_,
+  // laser_surf_ds_, laser_outlier_ds_) of sequence `seq` with the pose estimate of that keyframe; the deque holds the
+  // recent_keyframe_search_num_ (50, :48) most recent keyframes.  pose6 = x, y, z, roll, pitch, yaw (cloud_keyposes_6d_).
+  int saveKeyFrame(int seq, const float pose6[6]);
+  // correctPoses (:547-584): overwrite the pose of the k-th stored keyframe (0 = oldest) after a pose-graph update
+  int setKeyFramePose(int seq, size_t k, const float pose6[6]);
+  // transform + concatenate + VoxelGrid on the device -> local map of `seq` (alego_lm_assemble_map)
+  int extractSurroundingKeyFrames(int seq);
+  size_t keyFrameCount(int seq) const { return seq < (int)store_.size() ? store_[seq].size() : 0; }
+  static const size_t kRecentKeyframes = 50;
+
  private:
+  struct KeyFrame {
+    PointCloud corner, surf, outlier;
+    float pose6[6];
+  };
   AlegoContext &ctx_;
+  std::vector<std::deque<KeyFrame>> store_;  // per sequence
 };
 
 }  // namespace alego

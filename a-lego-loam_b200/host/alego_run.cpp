@@ -5,6 +5,9 @@
 // input file (little endian): int32 preset, n_seq, n_sweeps, lm_every ; per sequence: int32 n_corner, n_surf,
 // float32 corner[n_corner][4], surf[n_surf][4] ; per sweep, per sequence: int32 n, float32 xyzi[n][4]
 // output file: per sweep, per sequence: float64[12] = LM params_[6], LO t_w_cur_[3], LM t_map2laser[3]
+// optional 4th argument keyframe_every = k > 0: closed-loop mapping — after every k-th mapped sweep the sweep's downsampled
+// clouds are stored as a keyframe at the mapped pose (saveKeyFramesAndFactor's cloud side) and the local map is re-assembled
+// from the stored keyframes on the device (extractSurroundingKeyFrames, laserMapping.cpp:194-323).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -14,7 +17,8 @@
 static bool rd(FILE *f, void *dst, size_t bytes) { return bytes == 0 || std::fread(dst, 1, bytes, f) == bytes; }
 
 int main(int argc, char **argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: alego_run <sweeps.bin> <poses.bin> [device]\n"); return 2; }
+  if (argc < 3) { std::fprintf(stderr, "usage: alego_run <sweeps.bin> <poses.bin> [device] [keyframe_every]\n"); return 2; }
+  const int keyframe_every = argc > 4 ? std::atoi(argv[4]) : 0;
   FILE *fi = std::fopen(argv[1], "rb");
   if (!fi) { std::perror(argv[1]); return 2; }
   int32_t hdr[4];
@@ -55,6 +59,18 @@ int main(int argc, char **argv) {
     if (lm_every > 0 && t % lm_every == 0) {  // every lm_every-th frame (reference: 2, laserMapping.cpp:112)
       rc = lm.process();
       if (rc < 0) { std::fprintf(stderr, "LaserMapping: %s\n", ctx.last_error().c_str()); return 1; }
+      if (keyframe_every > 0 && (t / lm_every) % keyframe_every == 0) {
+        for (int b = 0; b < n_seq; ++b) {
+          double prm[6], tl[3], rl[9], to[3], ro[9];
+          if (lm.pose(b, prm, tl, rl, to, ro) != ALEGO_OK) return 1;
+          float pose6[6];
+          for (int q = 0; q < 6; ++q) pose6[q] = (float)prm[q];  // PointTypePose fields are float (utility.h:83-97)
+          if (lm.saveKeyFrame(b, pose6) != ALEGO_OK || lm.extractSurroundingKeyFrames(b) != ALEGO_OK) {
+            std::fprintf(stderr, "keyframes: %s\n", ctx.last_error().c_str());
+            return 1;
+          }
+        }
+      }
     }
     for (int b = 0; b < n_seq; ++b) {
       double out[12], lop[6], rw[9], r1[9], t2[3], r2[9];

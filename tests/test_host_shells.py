@@ -52,3 +52,46 @@ def test_alego_run_matches_ctypes_pipeline(alego, tmp_path):
         assert np.array_equal(got[t][:, 6:9], poses[:, 9:12]), t
         assert np.array_equal(got[t][:, 9:12], poses[:, 0:3]), t
     a.close()
+
+
+@pytest.mark.gpu
+def test_alego_run_closed_loop_keyframes(alego, tmp_path):
+    """alego_run with keyframe_every=1: the host core's keyframe deque + device local-map assembly (N1) gives the same
+    trajectory as the same steps driven through ctypes (get downsampled clouds -> alego_lm_assemble_map)."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed, n_sweeps = 5, 5
+    w = alego.SynthWorld(seed=seed)
+    cm, sm = w.make_map(4000, 20000, seed=seed, radius=60.0)
+    sweeps = [w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=17 * seed + t) for t in range(n_sweeps)]
+    fin, fout = str(tmp_path / "sweeps.bin"), str(tmp_path / "poses.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<4i", alego.PRESET_VLP16_1800, 1, n_sweeps, 1))
+        f.write(struct.pack("<2i", len(cm), len(sm)))
+        f.write(cm.astype("<f4").tobytes())
+        f.write(sm.astype("<f4").tobytes())
+        for s in sweeps:
+            f.write(struct.pack("<i", len(s)))
+            f.write(s.astype("<f4").tobytes())
+    r = subprocess.run([os.path.join(alego.HOST_DIR, "alego_run"), fin, fout, "0", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(fout, np.float64).reshape(n_sweeps, 1, 12)
+    a = alego.Alego(P, n_seq=1)
+    a.lm_set_map(0, cm, sm)
+    kfs, poses6 = [], []
+    moved = False
+    for t in range(n_sweeps):
+        buf, n = a.pack_scans([sweeps[t]])
+        a.ip_process(buf, n)
+        a.lo_extract()
+        a.lo_scan2scan()
+        a.lm_scan2map()
+        prm = a.lm_get_state(0)["params"]
+        assert np.array_equal(got[t, 0, 0:6], prm), t
+        kfs.append(a.lm_get_downsampled(0))
+        poses6.append(np.asarray(prm, np.float32))
+        a.lm_assemble_map(0, [k[0] for k in kfs], [k[1] for k in kfs], [k[2] for k in kfs], np.stack(poses6))
+        nc, ns = (len(x) for x in a.lm_get_map(0))
+        assert nc > 50 and ns > 500
+        moved = moved or abs(prm[0]) > 0.05
+    assert moved
+    a.close()
