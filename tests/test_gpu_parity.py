@@ -278,10 +278,12 @@ def run_sequence(alego, ob, P, seed, n_sweeps, with_lm, lm_every=1, map_sizes=(6
     return w, g, o
 
 
-@pytest.mark.parametrize("preset,seed", [(0, 0), (0, 1), (1, 2)])
-def test_scan_to_scan_parity(alego, ob, preset, seed):
-    """BASELINE config 2: LaserOdometry 2-step scan-to-scan on consecutive synthetic sweeps."""
+@pytest.mark.parametrize("preset,seed,corner_iters", [(0, 0, 5), (0, 1, 10), (1, 2, 5)])
+def test_scan_to_scan_parity(alego, ob, preset, seed, corner_iters):
+    """BASELINE config 2: LaserOdometry 2-step scan-to-scan on consecutive synthetic sweeps — 5 surf + 5 corner iterations as
+    in the code (laserOdometry.cpp:415,489) and 5 + 10 as in the README / BASELINE.json."""
     P = alego.default_params(preset)
+    P.lo_corner_iters = corner_iters
     w, g, o = run_sequence(alego, ob, P, seed, 4, with_lm=False)
     for t in range(4):
         scan = w.render(P, alego.trajectory_pose(t, speed=0.25, yaw_rate=0.02, seed=seed), noise_seed=50 + t)
@@ -321,10 +323,12 @@ def lm_standalone_case(alego, P, seed, n_corner, n_surf, offset):
     return w, corner_map, surf_map, scan
 
 
-@pytest.mark.parametrize("n_corner,n_surf", [(6000, 30000), (50000, 200000)])
-def test_scan_to_map_parity(alego, ob, n_corner, n_surf):
-    """BASELINE config 3: LaserMapping scan-to-map against a 50k corner + 200k surf local map (and a small one)."""
+@pytest.mark.parametrize("n_corner,n_surf,outer,iters", [(6000, 30000, 2, 20), (50000, 200000, 2, 20), (50000, 200000, 1, 10)])
+def test_scan_to_map_parity(alego, ob, n_corner, n_surf, outer, iters):
+    """BASELINE config 3: LaserMapping scan-to-map against a 50k corner + 200k surf local map (and a small one); 2 x 20 LM
+    iterations as in the code (laserMapping.cpp:360,470) and the 10 iterations BASELINE.json quotes."""
     P = alego.default_params(alego.PRESET_HDL64_1800)
+    P.lm_outer_iters, P.lm_max_iters = outer, iters
     w, cm, sm, scan = lm_standalone_case(alego, P, 5, n_corner, n_surf, None)
     # features of the sweep from the oracle front end, fed to both LaserMapping implementations
     o = ob.Oracle(P, stable_voxel=True)
@@ -435,7 +439,7 @@ def test_lm_guard_few_features(alego, ob):
     g.close()
 
 
-@pytest.mark.parametrize("preset,lm_every", [(0, 1), (1, 2)])
+@pytest.mark.parametrize("preset,lm_every", [(0, 1), (1, 2), (2, 1)])
 def test_full_pipeline_sequence(alego, ob, preset, lm_every):
     """IP -> LO -> LM over consecutive sweeps, every stage fed by the previous one on the device."""
     P = alego.default_params(preset)
