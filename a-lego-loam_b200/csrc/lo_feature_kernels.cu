@@ -329,6 +329,7 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
       while (true) {
         const bool cand = thr && nong && lane >= cursor && pk[idx - lo] == 0;
         const unsigned m = __ballot_sync(0xffffffffu, cand);
+        __syncwarp();  // every lane has read its flag before the chosen lane updates the window
         if (!m) break;
         const int first = __ffs(m) - 1;
         ++picked_num;
@@ -367,6 +368,7 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
       while (true) {
         const bool cand = thr && gr && lane >= cursor && pk[idx - lo] == 0;
         const unsigned m = __ballot_sync(0xffffffffu, cand);
+        __syncwarp();
         if (!m) break;
         const int first = __ffs(m) - 1;
         ++picked_num;

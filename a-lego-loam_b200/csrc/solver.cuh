@@ -100,7 +100,7 @@ struct LmShared {
   double acc[LM_NACC];
   double x[6], xc[6];
   double cand_cost;
-  int flag;
+  int flag, flag2;  // flag2: the gradient test after an accepted step (its own word: flag is still being read then)
 };
 
 // block reduction of acc[LM_NACC] per thread into sh->acc
@@ -341,10 +341,10 @@ __device__ LmResult block_lm_solve(const RS &rs, double *x_io, int max_iters, do
         push_trace(cost);
         double gmax = 0;
         for (int q = 0; q < 6; ++q) gmax = fmax(gmax, fabs(sh->acc[21 + q]));
-        sh->flag = gmax <= 1e-10 ? LM_FLAG_STOP : LM_FLAG_CANDIDATE;
+        sh->flag2 = gmax <= 1e-10 ? LM_FLAG_STOP : LM_FLAG_CANDIDATE;
       }
       __syncthreads();
-      if (sh->flag == LM_FLAG_STOP) break;
+      if (sh->flag2 == LM_FLAG_STOP) break;
     }
     __syncthreads();
   }
