@@ -57,6 +57,11 @@ def parse():
     return ap.parse_args()
 
 
+def workload_name(args):
+    return "%s IP+LO+LM, local map %dk corner + %dk surf re-indexed every mapped sweep, lm_every=%d" % (
+        args.preset, args.map_corner // 1000, args.map_surf // 1000, args.lm_every)
+
+
 def voxel_order(cloud, leaf):
     """Reorder a cloud the way pcl::VoxelGrid emits its output: ascending voxel index ijk0 + ijk1*dx + ijk2*dx*dy (stable)."""
     if len(cloud) == 0:
@@ -196,9 +201,9 @@ def run_reference(args, alego, P, rank, world):
         "impl": "reference", "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 geometry / f64 solver", "data": "synthetic",
-        "config": {"workload": "%s IP+LO+LM, local map %dk corner + %dk surf, lm_every=%d" % (args.preset, args.map_corner // 1000,
-                                                                                               args.map_surf // 1000, args.lm_every),
-                   "timed_steps_executed": len(step_times)},
+        "config": {"workload": workload_name(args), "map_order": args.map_order,
+                   "scans_per_step": cores * n_sweeps, "timed_steps_executed": len(step_times),
+                   "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
                          "sample": "%d cores x %d consecutive sweeps (one independent sequence per core) per step" % (cores, n_sweeps)},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -414,8 +419,7 @@ def main():
             "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 solver", "data": "synthetic (seeded ray-cast sweeps, %d unique sequences reused round-robin over the batch)" % N_UNIQUE,
-            "config": {"workload": "%s IP+LO+LM, local map %dk corner + %dk surf rebuilt-indexed every sweep, lm_every=%d" %
-                                   (args.preset, args.map_corner // 1000, args.map_surf // 1000, args.lm_every),
+            "config": {"workload": workload_name(args),
                        "n_seq_per_gpu": B, "scans_per_step": B * world, "points_per_scan": st["points"] / B,
                        "point_stride_floats": PS, "map_order": args.map_order,
                        "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 4 * PS / 1e6),
