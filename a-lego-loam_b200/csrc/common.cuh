@@ -279,12 +279,23 @@ __device__ __forceinline__ int block_excl_scan(int v, int *smem, int *total) {
 // Approximate atan2f for decisions that are re-checked exactly (ImageProjection's row / column binning) or only need a
 // conservative bound (azimuth bins of LaserOdometry's ring search): |error| < 1e-6 rad (degree-15 odd minimax polynomial on [0,1], 1.5e-7, plus the
 // approximate division and the quadrant folds).  Returns false for operands it does not cover (zero / denormal / huge).
+// single MUFU instructions (2-ulp approximations) for operands known to be normal floats
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 #define ALEGO_FAST_ATAN_ERR 1e-6
 __device__ __forceinline__ bool fast_atan2(float y, float x, float &r) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  if (!(mx > 1e-30f && mx < 1e30f)) return false;
-  const float t = __fdividef(mn, mx);
+  if (!(mx > 1e-30f && ax + ay < 1e30f)) return false;  // also rejects NaN / inf operands (fmaxf would drop a NaN)
+  const float t = mn * rcp_approx(mx);  // mx is in [1e-30, 1e30]: no denormal / overflow handling needed
   const float u = t * t;
   float p = -0.00405456405133009f;
   p = __fmaf_rn(p, u, 0.021862948313355446f);

@@ -38,9 +38,9 @@ __device__ __forceinline__ bool project_rowcol(float x, float y, float z, const 
   // accepted only when the cell coordinate is farther from an integer than the fast path's error bound (P.eps_row /
   // P.eps_col, >= 2e-3 cell), otherwise the exact form decides.
   const float s2 = x * x + y * y;
-  const float hyp = s2 * rsqrtf(fmaxf(s2, 1e-30f));
+  const float hyp = s2 * rsqrt_approx(fmaxf(s2, 1e-30f));
   float va = 0.f, ha = 0.f;
-  const bool fast_row = fast_atan2(z, hyp, va), fast_col = fast_atan2(y, x, ha);
+  const bool fast_row = s2 < 1e30f && fast_atan2(z, hyp, va), fast_col = fast_atan2(y, x, ha);
   // float cell coordinates: the float scaling adds < 1e-6 * |coordinate| to the angle error (covered by eps_row / eps_col)
   const float row_ff = __fmaf_rn(va, P.row_scale_f, P.row_off_f);
   const float col_ff = (6.283185307f - ha) * P.col_scale_f;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) ip_image_kernel(const float *__restrict__
     // fast float estimate; the exact double evaluation only near the 10 degree threshold
     float af = 0.f;
     const float h2 = fx * fx + fy * fy;
-    const bool fast = fast_atan2(fz, h2 * rsqrtf(fmaxf(h2, 1e-30f)), af);
+    const bool fast = h2 < 1e30f && fast_atan2(fz, h2 * rsqrt_approx(fmaxf(h2, 1e-30f)), af);
     bool is_ground;
     const float da = fabsf(af * 57.29577951f - (float)P.sensor_mount_ang);
     if (fast && fabsf(da - 10.f) > 1e-2f) {

@@ -175,7 +175,8 @@ def test_ip_rays_anywhere_in_the_cell(alego, ob, preset):
     P = alego.default_params(preset)
     scans = make_scans(alego, P, [21, 22, 23], jitter_cells=0.4999)
     special = np.array([[0, 0, 0, 1], [5, 0, 0, 1], [-5, 0, 0, 1], [0, 5, 0, 1], [0, -5, 0, 1], [0, 0, 5, 1], [0, 0, -5, 1],
-                        [3, 3, 0, 1], [-3, 3, -0.5, 1], [1e-20, 1e-20, 0, 1], [-0.0, -7, -1, 1]], np.float32)
+                        [3, 3, 0, 1], [-3, 3, -0.5, 1], [1e-20, 1e-20, 0, 1], [-0.0, -7, -1, 1],
+                        [2e19, 1e19, 60, 1], [1e25, -3e25, 1e26, 1]], np.float32)
     scans[2] = np.concatenate([scans[2], special])
     g = alego.Alego(P, n_seq=3, max_points=max(len(s) for s in scans))
     buf, n = g.pack_scans(scans)
