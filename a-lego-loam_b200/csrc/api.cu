@@ -128,7 +128,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
       p->lm_max_iters < 0)
     return ALEGO_BAD_ARG;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ALEGO_CUDA_ERROR;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= ALEGO_MAX_DEVICES) return ALEGO_CUDA_ERROR;
   AlegoHandle *h = new AlegoHandle();
   *out = h;
   h->P = *p;

@@ -12,6 +12,7 @@
 #include "../../include/alego_b200.h"
 
 #define ALEGO_MAX_RINGS 128
+#define ALEGO_MAX_DEVICES 64
 #define ALEGO_INFLIGHT 3  // steps alego_pipeline_submit keeps in flight (device staging buffers, pinned result slots)
 #define ALEGO_EMPTY_RANGE 3.402823466e+38f  // FLT_MAX: "no return" marker of the range image (reference: DBL_MAX, imageProjection.cpp:33)
 #define ALEGO_LABEL_INVALID 999999          // imageProjection.cpp:311

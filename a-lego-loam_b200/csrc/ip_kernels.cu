@@ -545,13 +545,13 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   cudaStream_t s = h->stream;
   const int pt_blocks = min(div_up(h->Nmax, 32 * P.R), 4096);
   const int cell_blocks = min(div_up(h->RC, 256), 4096);
-  static bool proj_attr_set = false;
-  if (!proj_attr_set) {
+  static bool proj_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!proj_attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(ip_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(32 * (ALEGO_MAX_RINGS + 1) * sizeof(float4))));
     CUDA_TRY(h, cudaFuncSetAttribute(ip_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(ALEGO_MAX_RINGS * (IMG_W + 1) * (sizeof(float4) + 1))));
-    proj_attr_set = true;
+    proj_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "ip_project");
     ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(reinterpret_cast<const float *>(h->raw), h->n_pts, h->winner, h->Nmax, h->in_stride, P); }

@@ -544,10 +544,10 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   if (rc != ALEGO_OK) return rc;
   const LmInputs in = make_inputs(h);
   { LAUNCH(h, "lm_prepare"); lm_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lm_use_ext, h->o2l_lo[1 - h->cur], h->o2l, h->m2o, h->m2l, B); }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(lm_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
-    attr_set = true;
+    attr_set[h->dev] = true;
   }
   const int cs = h->ds_cap_s, cc = h->ds_cap_c, co = h->ds_cap_o;
   u64 *sort_c = h->vox_sort, *sort_s = sort_c + (size_t)B * 2 * cc, *sort_o = sort_s + (size_t)B * 2 * (cs + co);
@@ -576,10 +576,10 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   { LAUNCH(h, "lm_fit_surf");
     lm_fit_kernel<false><<<dim3(min(div_up(cs + co, 128), 64), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
                                                                        h->lm_nn_s, h->lm_plane, 8); }
-  static bool solve_attr_set = false;
-  if (!solve_attr_set) {
+  static bool solve_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!solve_attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_STAGE_BYTES));
-    solve_attr_set = true;
+    solve_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "lm_solve");
     lm_solve_kernel<<<B, 256, LM_STAGE_BYTES, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,

@@ -528,10 +528,10 @@ int lo_extract_device(AlegoHandle *h) {
                                                                              h->flabel, h->sort_idx, RC); }
   const int sort_cap = ((C / 6 + 8) + 3) & ~3;
   const size_t sort_smem = (size_t)SORT_WARPS * ((size_t)sort_cap * 14 + 16);
-  static bool sort_attr_set = false;
-  if (!sort_attr_set) {
+  static bool sort_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!sort_attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(lo_sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    sort_attr_set = true;
+    sort_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "lo_sort_segments");
     lo_sort_segments_kernel<<<div_up(B * R * 6, SORT_WARPS), SORT_WARPS * 32, sort_smem, s>>>(h->curv, h->start_ring, h->end_ring,

@@ -442,10 +442,10 @@ int lo_scan2scan_device(AlegoHandle *h) {
   const double gate = h->P.nearest_feature_dist, hub = h->P.huber_delta;
   // shared-memory staging of the residual blocks: every surf (12 floats) and corner (9 floats) slot, capped at 200 KB
   const size_t lo_stage_bytes = std::min<size_t>((size_t)R * (24 * 12 + 12 * 9) * sizeof(float), 200 * 1024);
-  static bool lo_attr_set = false;
-  if (!lo_attr_set) {
+  static bool lo_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!lo_attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(lo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    lo_attr_set = true;
+    lo_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
   { LAUNCH(h, "lo_assoc_surf");
