@@ -99,7 +99,7 @@ class ClockSampler:
         self.gpu = gpu_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -323,7 +323,6 @@ def main():
     t_wall1 = time.time()
     ms_dev = g.timer_elapsed_ms(0, 1)
     launches = g.launch_count() - l0
-    clocks = sampler.stop(t_wall0, t_wall1)
 
     # H2D probe: what this box's PCIe link gives a plain pinned-memory copy of one step's sweeps (context for e2e, which is
     # link-bound once the pass itself is faster than the copy)
@@ -364,6 +363,7 @@ def main():
     # larger) host wall clock between the two synchronisation points is taken when it exceeds the event time
     ms_e2e_dev = g.timer_elapsed_ms(2, 3)
     ms_e2e = max(ms_e2e_dev, ms_e2e_host)
+    clocks = sampler.stop(t_wall0, time.time())  # SM clocks / throttle reasons from the start of pass A to the end of pass B
 
     # ---------------- pass C: per-kernel CUDA events on the same workload ----------------
     fill(2 * n_steps)

@@ -23,7 +23,8 @@ for r in data:
     name = re.sub(r"<.*", "", name).replace("void ", "").strip()
     t = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
     acc.setdefault(name, []).append(t)
+MULTI_ROLE = ("grid_count", "grid_scan", "grid_fill", "lm_knn", "lm_fit", "lm_voxel", "lo_assoc", "lo_solve", "lo_pose")
 out = {"n_seq": int(sys.argv[2]), "preset": sys.argv[3], "point_stride": int(sys.argv[4]), "source": sys.argv[1],
-       "note": "kernels launched once per step: mean over the captured launches; others (grid_*, lm_knn, lm_fit, lm_voxel, lo_assoc, lo_solve) are listed per launch in order",
-       "dram_bytes_per_launch": {k: (sum(v) / len(v) if k in ("ip_project", "ip_gather", "ip_ground", "ccl_rows", "ccl_merge", "ccl_flatten", "ip_rowcount", "ip_compact", "lo_curv_occl", "lo_sort_segments", "lo_select", "lo_less_flat_voxel", "lo_finalize", "lm_solve") else v) for k, v in acc.items()}}
+       "note": "kernels with one role per step: mean over the captured launches; the others (%s) serve several clouds / phases and are listed per launch in capture order" % ", ".join(MULTI_ROLE),
+       "dram_bytes_per_launch": {k: (v if k in MULTI_ROLE else sum(v) / len(v)) for k, v in acc.items()}}
 print(json.dumps(out, indent=1))
