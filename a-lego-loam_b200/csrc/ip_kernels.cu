@@ -155,21 +155,29 @@ __global__ void __launch_bounds__(256) ip_image_kernel(const float *__restrict__
   const size_t base = (size_t)b * P.RC;
   const float *sweep = raw + (size_t)b * Nmax * stride;
   const int ncell = P.R * SW;
+  // winners of the strip, read along the image rows (coalesced) ...
+  int *s_win = reinterpret_cast<int *>(s_ground + (((size_t)ncell + 3) & ~(size_t)3));  // [R][SW]
   for (int t = threadIdx.x; t < ncell; t += blockDim.x) {
     const int row = t / SW, c = t - row * SW;
     int col = col0 + c - 1;
     if (col < 0) col += P.C;
-    float4 v = make_float4(0.f, 0.f, 0.f, ALEGO_EMPTY_RANGE);
-    if (col < P.C) {
-      const int w = winner[base + (size_t)row * P.C + col];
+    s_win[t] = col < P.C ? winner[base + (size_t)row * P.C + col] : -1;
+    s_ground[t] = 0;
+  }
+  __syncthreads();
+  // ... and gathered along the image COLUMNS: for a ring-fastest sweep the points of one column are consecutive in the input,
+  // so the lanes of a warp (consecutive rows) read a contiguous span instead of 32 points a firing apart
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < SW; c += nwarp)
+    for (int row = lane; row < P.R; row += 32) {
+      const int w = s_win[row * SW + c];
+      float4 v = make_float4(0.f, 0.f, 0.f, ALEGO_EMPTY_RANGE);
       if (w >= 0) {
         const float4 p = load_point(sweep, w, stride);
         v = make_float4(p.x, p.y, p.z, sqrtf(p.x * p.x + p.y * p.y + p.z * p.z));  // (:99) float sum, float sqrt
       }
+      s_pt[row * SW + c] = v;
     }
-    s_pt[t] = v;
-    s_ground[t] = 0;
-  }
   __syncthreads();
   // ---- ground (:106-132): one thread per vertical pair (i, i+1), i < ground_scan_id
   const int grows = min(P.ground_scan_id, P.R - 1);
@@ -550,12 +558,12 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
     CUDA_TRY(h, cudaFuncSetAttribute(ip_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(32 * (ALEGO_MAX_RINGS + 1) * sizeof(float4))));
     CUDA_TRY(h, cudaFuncSetAttribute(ip_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(ALEGO_MAX_RINGS * (IMG_W + 1) * (sizeof(float4) + 1))));
+                                     (int)(ALEGO_MAX_RINGS * (IMG_W + 1) * (sizeof(float4) + 1 + sizeof(int)) + 16)));
     proj_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "ip_project");
     ip_project_kernel<<<dim3(pt_blocks, B), 256, (size_t)32 * (P.R + 1) * sizeof(float4), s>>>(reinterpret_cast<const float *>(h->raw), h->n_pts, h->winner, h->Nmax, h->in_stride, P); }
-  const size_t img_smem = (size_t)P.R * (IMG_W + 1) * (sizeof(float4) + 1);
+  const size_t img_smem = (size_t)P.R * (IMG_W + 1) * (sizeof(float4) + 1 + sizeof(int)) + 16;
   { LAUNCH(h, "ip_image");
     ip_image_kernel<<<dim3(div_up(P.C, IMG_W), B), 256, img_smem, s>>>(reinterpret_cast<const float *>(h->raw), h->in_stride, h->winner,
                                                                    h->cloud, h->range, h->ground, h->cell_flags, h->Nmax, P); }
