@@ -353,8 +353,9 @@ class Alego:
         return {"params": p, "t_map2laser": t1, "r_map2laser": r1.reshape(3, 3), "t_map2odom": t2, "r_map2odom": r2.reshape(3, 3)}
 
     # ---- whole path
-    def pipeline_config(self, lm_every=1, rebuild_map_index_every_step=True, overlap_map_build=True):
-        return self._chk(self.L.alego_pipeline_config(self.h, lm_every, int(rebuild_map_index_every_step), 0 if overlap_map_build else -1))
+    def pipeline_config(self, lm_every=1, rebuild_map_index_every_step=True, overlap_map_build=True, graphs=False):
+        opt = (2 if graphs else 0) if overlap_map_build else -1
+        return self._chk(self.L.alego_pipeline_config(self.h, lm_every, int(rebuild_map_index_every_step), opt))
 
     def pipeline_submit(self, buf, n):
         """Asynchronous pipeline_step: buf must be pinned (pinned_empty) and untouched until collected; <= 2 in flight."""

@@ -151,6 +151,9 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lo_done, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side_tail, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_g_fork, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_g_lo, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_g_tail, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lm_done[k], cudaEventDisableTiming));
   for (int k = 0; k < ALEGO_INFLIGHT; ++k) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
@@ -301,6 +304,10 @@ void alego_destroy(AlegoHandle *h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_lo_done) cudaEventDestroy(h->ev_lo_done);
   if (h->ev_side_tail) cudaEventDestroy(h->ev_side_tail);
+  for (auto &g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (cudaEvent_t e : {h->ev_g_fork, h->ev_g_lo, h->ev_g_tail})
+    if (e) cudaEventDestroy(e);
   for (int k = 0; k < 2; ++k)
     if (h->ev_lm_done[k]) cudaEventDestroy(h->ev_lm_done[k]);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -546,6 +553,7 @@ int alego_lo_set_params(AlegoHandle *h, int seq, const double params[6]) {
 // ---------------------------------------------------------------------------------------------------
 static int realloc_keep(AlegoHandle *h, float4 **buf, int *cap, int need) {
   if (need <= *cap) return ALEGO_OK;
+  ++h->graph_epoch;  // captured graphs hold the old pointer
   const int ncap = std::max(need, 1024);
   float4 *nb = nullptr;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -768,6 +776,8 @@ int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_ev
   h->lm_every = lm_every;
   h->rebuild_map_every_step = rebuild_map_index_every_step != 0;
   h->overlap_lm = use_cuda_graph >= 0;  // third argument: < 0 keeps LaserMapping on the main stream (no overlap with the next sweep's front end)
+  h->use_graphs = use_cuda_graph > 0 && (use_cuda_graph & 2) != 0;  // bit 1: alego_pipeline_step replays a captured CUDA graph
+  ++h->graph_epoch;
   return ALEGO_OK;
 }
 
@@ -780,20 +790,30 @@ int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_ev
 // mapping of sweep t before it overwrites that parity.
 static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   int rc;
-  bool any_ext = false;
-  for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
-  if (any_ext) {  // the pipeline feeds LaserMapping from LaserOdometry's device clouds
-    if ((rc = join_side(h)) != ALEGO_OK) return rc;
-    CUDA_TRY(h, cudaMemsetAsync(h->lm_use_ext, 0, h->B * sizeof(int), h->stream));
-    std::fill(h->lm_scan_is_external.begin(), h->lm_scan_is_external.end(), 0);
+  const bool cap = h->capturing;  // recorded into a CUDA graph: the side stream forks from and joins the main stream inside
+  if (!cap) {
+    bool any_ext = false;
+    for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
+    if (any_ext) {  // the pipeline feeds LaserMapping from LaserOdometry's device clouds
+      if ((rc = join_side(h)) != ALEGO_OK) return rc;
+      CUDA_TRY(h, cudaMemsetAsync(h->lm_use_ext, 0, h->B * sizeof(int), h->stream));
+      std::fill(h->lm_scan_is_external.begin(), h->lm_scan_is_external.end(), 0);
+    }
   }
   const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
   const bool overlap = h->overlap_lm && !h->profiling;
   const int par = h->cur;  // buffer parity of this sweep's clouds
-  if (run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
+  if (!cap && run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
   // ---- front end (main stream)
-  if (overlap && h->lm_done_valid[par]) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_lm_done[par], 0));
-  if (!overlap && (rc = join_side(h)) != ALEGO_OK) return rc;
+  if (cap) {
+    if (overlap) {
+      CUDA_TRY(h, cudaEventRecord(h->ev_g_fork, h->stream));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_g_fork, 0));
+    }
+  } else {
+    if (overlap && h->lm_done_valid[par]) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_lm_done[par], 0));
+    if (!overlap && (rc = join_side(h)) != ALEGO_OK) return rc;
+  }
   if ((rc = ip_run_internal(h)) != ALEGO_OK) return rc;
   // ImageProjection is the only reader of the raw sweep: its staging buffer may be refilled from here on
   if (consumed_ev) CUDA_TRY(h, cudaEventRecord(consumed_ev, h->stream));
@@ -803,8 +823,9 @@ static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   h->stage_feat_done = false;
   // ---- mapping (side stream when overlapped)
   cudaStream_t ms = h->stream;
+  cudaEvent_t ev_lo = cap ? h->ev_g_lo : h->ev_lo_done;
   if (overlap) {
-    CUDA_TRY(h, cudaEventRecord(h->ev_lo_done, h->stream));
+    CUDA_TRY(h, cudaEventRecord(ev_lo, h->stream));
     ms = h->side_stream;
     h->launch_stream = ms;
   }
@@ -814,7 +835,7 @@ static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
     rc = lm_build_map_index(h);
     if (rc != ALEGO_OK) { h->launch_stream = nullptr; return rc; }
   }
-  if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(ms, h->ev_lo_done, 0));
+  if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(ms, ev_lo, 0));
   if (run_lm) {
     rc = lm_scan2map_device(h, h->lm_guard, true, true);
   } else {
@@ -824,19 +845,89 @@ static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   }
   h->launch_stream = nullptr;
   if (rc != ALEGO_OK) return rc;
-  if (overlap) {
+  if (overlap && cap) {  // join: the graph is complete when the main stream is
+    CUDA_TRY(h, cudaEventRecord(h->ev_g_tail, ms));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_g_tail, 0));
+  } else if (overlap) {
     CUDA_TRY(h, cudaEventRecord(h->ev_lm_done[par], ms));
     h->lm_done_valid[par] = true;
     CUDA_TRY(h, cudaEventRecord(h->ev_side_tail, ms));
     h->side_busy = true;
   }
+  h->pose_on_main = cap || !overlap;
   ++h->scan_count;
-  CUDA_TRY(h, cudaGetLastError());
+  if (!cap) CUDA_TRY(h, cudaGetLastError());
+  return ALEGO_OK;
+}
+
+static void drop_graphs(AlegoHandle *h) {
+  for (auto &g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+  h->graphs_epoch = h->graph_epoch;
+}
+
+// Graph mode of the synchronous step (launch-latency regime: one or a few sequences, ~40 launches of a few microseconds of
+// work each): the pass is captured once per (buffer parity, LM schedule, input buffer) and replayed with a single launch.
+static int pipeline_enqueue_graph(AlegoHandle *h) {
+  int rc;
+  // what the eager path does outside the streams
+  bool any_ext = false;
+  for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
+  const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
+  if (any_ext || h->profiling || h->scan_count < 2) return pipeline_enqueue(h);  // first sweeps (lazy set-up) run eagerly
+  if (run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
+  if ((rc = join_side(h)) != ALEGO_OK) return rc;
+  if (h->graphs_epoch != h->graph_epoch || h->graphs.size() > 64) drop_graphs(h);
+  const int par = h->cur;
+  const bool rebuild = run_lm && (h->rebuild_map_every_step || !h->map_index_valid);
+  PipelineGraph *g = nullptr;
+  for (auto &e : h->graphs)
+    if (e.par == par && e.run_lm == run_lm && e.rebuild == rebuild && e.raw == h->raw && e.n_pts == h->n_pts && e.stride == h->in_stride) g = &e;
+  if (g) {
+    CUDA_TRY(h, cudaGraphLaunch(g->exec, h->stream));
+    // host-side state the recorded calls would have advanced
+    h->outlier = h->outlier_buf[par];
+    h->n_outlier = h->n_outlier_buf[par];
+    h->stage_ip_done = true;
+    h->label_valid = false;
+    h->feat_buf = par;
+    h->cur = 1 - par;
+    h->stage_feat_done = false;
+    if (rebuild) h->map_index_valid = true;
+    h->launches += g->n_launches;
+    ++h->scan_count;
+  } else {
+    PipelineGraph e;
+    e.par = par; e.run_lm = run_lm; e.rebuild = rebuild; e.raw = h->raw; e.n_pts = h->n_pts; e.stride = h->in_stride;
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    h->capturing = true;
+    rc = pipeline_enqueue(h);
+    h->capturing = false;
+    h->launch_stream = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != ALEGO_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == ALEGO_OK) { h->err = std::string("graph capture: ") + cudaGetErrorString(ce); rc = ALEGO_CUDA_ERROR; }
+      return rc;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie); return ALEGO_CUDA_ERROR; }
+    e.n_launches = h->launches - l0;
+    CUDA_TRY(h, cudaGraphLaunch(e.exec, h->stream));
+    h->graphs.push_back(e);
+  }
+  h->lm_done_valid[0] = h->lm_done_valid[1] = false;  // every pass is joined into the main stream
+  h->side_busy = false;
+  h->pose_on_main = true;
   return ALEGO_OK;
 }
 
 // stream that produced d_pose of the pass enqueued last
-static cudaStream_t pose_stream(AlegoHandle *h) { return (h->overlap_lm && !h->profiling) ? h->side_stream : h->stream; }
+static cudaStream_t pose_stream(AlegoHandle *h) { return h->pose_on_main ? h->stream : h->side_stream; }
 
 int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points, double *poses_out) {
   if (!h) return ALEGO_BAD_ARG;
@@ -846,7 +937,7 @@ int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n
   if (xyzi_host) {
     if ((rc = alego_ip_upload(h, xyzi_host, n_points)) != ALEGO_OK) return rc;
   }
-  if ((rc = pipeline_enqueue(h)) != ALEGO_OK) return rc;
+  if ((rc = h->use_graphs ? pipeline_enqueue_graph(h) : pipeline_enqueue(h)) != ALEGO_OK) return rc;
   if (poses_out) {
     cudaStream_t ps = pose_stream(h);
     CUDA_TRY(h, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, ps));

@@ -38,6 +38,15 @@ struct KernelProfile {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+// One captured IP -> LO -> LM pass (alego_pipeline_step in graph mode): valid for exactly the buffers it was captured with
+struct PipelineGraph {
+  int par = 0, stride = 4;
+  bool run_lm = false, rebuild = false;
+  const void *raw = nullptr, *n_pts = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t n_launches = 0;
+};
+
 struct AlegoHandle {
   AlegoParams P;
   int dev = 0, B = 0, Nmax = 0, R = 0, C = 0, RC = 0;
@@ -54,6 +63,13 @@ struct AlegoHandle {
   cudaEvent_t ev_side_tail = nullptr;            // side stream: everything enqueued there so far
   bool side_busy = false;                        // work was enqueued on the side stream since the last join
   bool overlap_lm = true;
+  // CUDA graphs for the launch-latency regime (few sequences): alego_pipeline_config options bit 1
+  bool use_graphs = false;
+  bool capturing = false;          // pipeline_enqueue is being recorded into a graph
+  bool pose_on_main = false;       // the last pass left d_pose on the main stream (graph mode / no overlap)
+  unsigned graph_epoch = 0, graphs_epoch = 0;  // bumped whenever a captured pointer / setting may have changed
+  std::vector<PipelineGraph> graphs;
+  cudaEvent_t ev_g_fork = nullptr, ev_g_lo = nullptr, ev_g_tail = nullptr;  // fork / join inside a capture
   cudaEvent_t ev_copied[ALEGO_INFLIGHT] = {}, ev_consumed[ALEGO_INFLIGHT] = {}, ev_pose[ALEGO_INFLIGHT] = {};
   bool consumed_valid[ALEGO_INFLIGHT] = {};
   bool overlap_map_build = true;

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict
 
 int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2) {
   grid_free(g);
+  ++h->graph_epoch;  // captured graphs hold the old table / array pointers
   g->cap = cap;
   g->cell = cell;
   // buckets: next_pow2(cap / 2) << table_factor_log2.  A query reads whole buckets, so every point that merely collides

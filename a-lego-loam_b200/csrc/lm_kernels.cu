@@ -597,6 +597,7 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
   int want_o = std::max(std::max(h->out_cap, h->lm_cap_o), need_o);
   if (h->lm_corner_ds && want_c <= h->ds_cap_c && want_s <= h->ds_cap_s && want_o <= h->ds_cap_o) return ALEGO_OK;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  ++h->graph_epoch;  // captured graphs hold the old pointers
   cudaFree(h->lm_corner_ds); cudaFree(h->lm_surf_ds); cudaFree(h->lm_outlier_ds); cudaFree(h->lm_surf_total);
   cudaFree(h->lm_surf_total_ds); cudaFree(h->lm_edge); cudaFree(h->lm_plane); cudaFree(h->vox_sort);
   cudaFree(h->lm_nn_c); cudaFree(h->lm_nn_s);

@@ -208,7 +208,9 @@ int alego_pipeline_collect(AlegoHandle *h, double *poses_out);
  * rebuild_map_index_every_step: rebuild the local-map search index on every mapped sweep, like the reference's kd-tree
  * builds (laserMapping.cpp:356-357), instead of only after alego_lm_set_map.  options: 0 default — the LaserMapping stage
  * of sweep t (index build + scan-to-map) runs on a second stream and overlaps ImageProjection + LaserOdometry of sweep
- * t+1, like the reference's separate nodes; a negative value keeps everything on one stream (debugging). */
+ * t+1, like the reference's separate nodes; a negative value keeps everything on one stream (debugging); bit 1 (value 2):
+ * graph mode for the launch-latency regime (one or a few sequences) — alego_pipeline_step captures the pass once per
+ * buffer parity / LM schedule / input buffer into a CUDA graph and replays it with a single launch. */
 int alego_pipeline_config(AlegoHandle *h, int lm_every, int rebuild_map_index_every_step, int options);
 
 /* ---- stand-alone operators (used by LO/LM internally, exposed for tests and callers) ------------- */

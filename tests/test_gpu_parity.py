@@ -486,6 +486,41 @@ def test_batched_sequences_match_single(alego, ob):
     g.close()
 
 
+def test_graph_mode_matches_eager(alego):
+    """alego_pipeline_config(options bit 1): the CUDA-graph replay of the synchronous step gives bit-identical poses and
+    intermediate results, over both buffer parities and an lm_every = 2 schedule, and survives a map replacement."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seeds, T = [0, 1], 9
+    worlds = [alego.SynthWorld(seed=s) for s in seeds]
+    maps = [w.make_map(4000, 20000, seed=s, radius=60.0) for w, s in zip(worlds, seeds)]
+    sweeps = [[w.render(P, alego.trajectory_pose(t, seed=s), noise_seed=10 * s + t) for w, s in zip(worlds, seeds)] for t in range(T)]
+
+    def run(graphs):
+        g = alego.Alego(P, n_seq=len(seeds))
+        for b, (cm, sm) in enumerate(maps):
+            g.lm_set_map(b, cm, sm)
+        g.pipeline_config(lm_every=2, graphs=graphs)
+        buf = alego.pinned_empty((len(seeds), g.max_points, 4), np.float32)
+        out, launches = [], []
+        for t in range(T):
+            b_, n_ = g.pack_scans(sweeps[t])
+            buf[:] = b_
+            if t == 6:  # a bigger map: buffers are reallocated, captured graphs must be dropped
+                cm, sm = worlds[0].make_map(5000, 26000, seed=99, radius=60.0)
+                g.lm_set_map(0, cm, sm)
+            out.append((g.pipeline_step(buf, n_).copy(), g.debug("less_sharp_idx", 1).copy(), g.debug("lm_params", 0).copy()))
+            launches.append(g.launch_count())
+        g.close()
+        return out, launches
+
+    eager, l_e = run(False)
+    graph, l_g = run(True)
+    assert l_e == l_g  # the replayed launches are counted
+    for t in range(T):
+        for a, b in zip(eager[t], graph[t]):
+            assert np.array_equal(a, b), "sweep %d" % t
+
+
 def test_stage_order_errors(alego):
     P = alego.default_params(0)
     g = alego.Alego(P, n_seq=1)
