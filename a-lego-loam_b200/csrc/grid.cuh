@@ -6,6 +6,11 @@ __host__ __device__ __forceinline__ int grid_coord(float v, float inv_cell) { re
 // Bucket of a cell.  Blocks of 2^GRID_XB consecutive x cells hash together and keep their x order inside the block, so
 // the buckets of x-neighbours — and, after the counting sort, their points — are contiguous: a 3-cell x run is one or
 // two contiguous ranges instead of three scattered ones.  T is a power of two >= 1024.
+// bucket tables: per sequence T + 4 entries followed by GRID_MAX_CHUNKS chunk populations (see grid_scan_kernel)
+#define GRID_CHUNK_SHIFT 12
+#define GRID_CHUNK (1 << GRID_CHUNK_SHIFT)
+#define GRID_MAX_CHUNKS 1028  // tables of up to 4 Mi buckets
+#define GRID_TABLE_STRIDE(T) ((size_t)(T) + 4 + GRID_MAX_CHUNKS)
 #define GRID_XB 3
 __host__ __device__ __forceinline__ int grid_hash(int ix, int iy, int iz, int T) {
   const unsigned h = ((unsigned)(ix >> GRID_XB) * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);

@@ -236,7 +236,7 @@ __device__ __forceinline__ void knn5_offer(float d, int idx, float *bd, int *bi,
 
 __device__ __forceinline__ int knn5_gate(const GridIndex &g, int b, float qx, float qy, float qz, float *bd, int *bi) {
   const int T = g.table_size;
-  const int *cs = g.cell_start + (size_t)b * (T + 4);
+  const int *cs = g.cell_start + (size_t)b * GRID_TABLE_STRIDE(T);
   const float4 *sp = g.sorted + (size_t)b * g.cap;
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);

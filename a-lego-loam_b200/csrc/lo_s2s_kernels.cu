@@ -58,7 +58,7 @@ __device__ __forceinline__ void nearest_visit_cell(const int *__restrict__ cs, c
 template <int G> __device__ Best group_nearest(const GridIndex &g, int b, float qx, float qy, float qz, int max_shell, unsigned gm) {
   const int gl = group_lane<G>();
   const int T = g.table_size;
-  const int *cs = g.cell_start + (size_t)b * (T + 4);
+  const int *cs = g.cell_start + (size_t)b * GRID_TABLE_STRIDE(T);
   const float4 *sp = g.sorted + (size_t)b * g.cap;
   const float inv = 1.0f / g.cell;
   const int cx = grid_coord(qx, inv), cy = grid_coord(qy, inv), cz = grid_coord(qz, inv);
