@@ -338,8 +338,15 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t *__restric
   int *L = parent + base;
   const uint8_t *fl = flags + base;
   const int n = P.RC - P.C;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x)
-    if (fl[cell] & CELL_JOIN_DOWN) uf_unite(L, cell, cell + P.C);
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x) {
+    const int f = fl[cell];
+    if (!(f & CELL_JOIN_DOWN)) continue;
+    // the two runs were already united by the cell to the left when that cell joins down too and both rows continue their
+    // runs into this column: only the first column of every (run, run) contact touches the forest
+    const int col = cell % P.C;
+    if (col > 0 && (f & CELL_JOIN_LEFT) && (fl[cell + P.C] & CELL_JOIN_LEFT) && (fl[cell - 1] & CELL_JOIN_DOWN)) continue;
+    uf_unite(L, cell, cell + P.C);
+  }
 }
 
 // flatten + per-component size and highest row (rows of a 4-connected component are contiguous, so the
