@@ -269,6 +269,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    try:  # keep the rank (and the pinned sweep buffers it first-touches) on the CPUs next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = sorted(os.sched_getaffinity(0))
+        numa = "cpus %d-%d (%d)" % (numa[0], numa[-1], len(numa))
+    except Exception as e:  # best effort
+        numa = "unbound (%s)" % type(e).__name__
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -421,7 +430,7 @@ def main():
             "dtype": "f32 geometry / f64 solver", "data": "synthetic (seeded ray-cast sweeps, %d unique sequences reused round-robin over the batch)" % N_UNIQUE,
             "config": {"workload": workload_name(args),
                        "n_seq_per_gpu": B, "scans_per_step": B * world, "points_per_scan": st["points"] / B,
-                       "point_stride_floats": PS, "map_order": args.map_order,
+                       "point_stride_floats": PS, "map_order": args.map_order, "rank0_cpu_affinity": numa,
                        "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 4 * PS / 1e6),
                        "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
             "clocks": clocks,
