@@ -147,8 +147,6 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto &e : h->timer) CUDA_TRY(h, cudaEventCreate(&e));
-  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_lo_done, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side_tail, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_g_fork, cudaEventDisableTiming));
@@ -300,8 +298,6 @@ void alego_destroy(AlegoHandle *h) {
     if (h->ev_consumed[k]) cudaEventDestroy(h->ev_consumed[k]);
     if (h->ev_pose[k]) cudaEventDestroy(h->ev_pose[k]);
   }
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_lo_done) cudaEventDestroy(h->ev_lo_done);
   if (h->ev_side_tail) cudaEventDestroy(h->ev_side_tail);
   for (auto &g : h->graphs)

@@ -56,7 +56,6 @@ struct AlegoHandle {
                                          // with ImageProjection + LaserOdometry of sweep t+1, like the reference's three nodes
   cudaStream_t copy_stream = nullptr;    // H2D of the next sweep overlapped with the current pass (alego_pipeline_submit)
   cudaStream_t launch_stream = nullptr;  // when set, LAUNCH() / grid_build() target this stream instead of `stream`
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_lo_done = nullptr;              // main stream: LaserOdometry of the sweep finished (its clouds are final)
   cudaEvent_t ev_lm_done[2] = {nullptr, nullptr};  // side stream: LaserMapping has consumed the clouds of buffer parity k
   bool lm_done_valid[2] = {false, false};
@@ -72,7 +71,6 @@ struct AlegoHandle {
   cudaEvent_t ev_g_fork = nullptr, ev_g_lo = nullptr, ev_g_tail = nullptr;  // fork / join inside a capture
   cudaEvent_t ev_copied[ALEGO_INFLIGHT] = {}, ev_consumed[ALEGO_INFLIGHT] = {}, ev_pose[ALEGO_INFLIGHT] = {};
   bool consumed_valid[ALEGO_INFLIGHT] = {};
-  bool overlap_map_build = true;
   long long n_submitted = 0, n_collected = 0;
   std::string err;
   int64_t launches = 0;
