@@ -162,3 +162,35 @@ def test_cuda_reproduces_cfg3_small(alego, tag, iters):
     tr = a.debug("lm_trace")
     assert tr.shape == g[tag + "_lm_trace"].shape and np.allclose(tr, g[tag + "_lm_trace"], rtol=1e-6, atol=1e-8)
     a.close()
+
+
+# ------------------------------------------------------------------------------------------------ N1: local-map assembly
+def _n1_inputs(g):
+    K = len(g["poses6"])
+    return ([g["corner%d" % k] for k in range(K)], [g["surf%d" % k] for k in range(K)], [g["outlier%d" % k] for k in range(K)],
+            g["poses6"])
+
+
+def test_oracle_reproduces_n1_local_map(ob):
+    g = load("n1_local_map.npz")
+    ck, sk, okf, poses = _n1_inputs(g)
+    cm, sm, M = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=True)
+    assert np.array_equal(M, g["matrices"]) and np.array_equal(cm, g["corner_from_map_ds"]) and np.array_equal(sm, g["surf_from_map_ds"])
+    # known-answer sanity of the fixture: rotations are orthonormal, fewer map points than inputs, PCL order agrees to 2e-5
+    for Mk in M.reshape(-1, 3, 4):
+        assert np.abs(Mk[:, :3] @ Mk[:, :3].T - np.eye(3)).max() < 1e-6
+    assert 0 < len(sm) < sum(len(x) for x in sk) + sum(len(x) for x in okf)
+    cm2, sm2, _ = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=False)
+    assert cm2.shape == cm.shape and np.allclose(cm2, cm, rtol=0, atol=2e-5) and np.allclose(sm2, sm, rtol=0, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_n1_local_map(alego):
+    g = load("n1_local_map.npz")
+    ck, sk, okf, poses = _n1_inputs(g)
+    a = alego.Alego(vlp16(alego), n_seq=1)
+    a.lm_assemble_map(0, ck, sk, okf, poses)
+    cm, sm = a.lm_get_map(0)
+    assert np.array_equal(cm, g["corner_from_map_ds"]), first_diff(cm, g["corner_from_map_ds"])
+    assert np.array_equal(sm, g["surf_from_map_ds"]), first_diff(sm, g["surf_from_map_ds"])
+    a.close()
