@@ -228,6 +228,11 @@ def algorithmic_bytes(name, st):
         "ip_compact": 13.0 * cells + (16 + 4 + 25.0) * kept,
         "ip_label": 8.0 * cells,
         "lo_curv_occl": 21.0 * kept,                   # 4+4 read, 4+1+4+4 written per segmented point
+        # counting sort of the local map into the hashed grid, rebuilt every mapped sweep (the reference's kd-tree builds)
+        "grid_count_map_surf": 20.0 * st["map_surf_pts"],    # 16 B point + 4 B counter
+        "grid_fill_map_surf": 36.0 * st["map_surf_pts"],     # 16 B point + 4 B cursor + 16 B sorted copy
+        "grid_count_map_corner": 20.0 * st["map_corner_pts"],
+        "grid_fill_map_corner": 36.0 * st["map_corner_pts"],
     }
     return table.get(name)
 
@@ -403,7 +408,9 @@ def main():
         value = scans / (ms_dev * 1e-3)
         e2e_value = scans / (ms_e2e * 1e-3)
         st = {"points": float(np.mean(pts_per_step)), "cells": float(B * P.n_scan * P.horizon_scan), "kept": kept, "B": B,
-              "ground_rows": min(P.ground_scan_id + 1, P.n_scan), "R": P.n_scan, "stride": PS}
+              "ground_rows": min(P.ground_scan_id + 1, P.n_scan), "R": P.n_scan, "stride": PS,
+              "map_surf_pts": float(B * np.mean([len(q["map_surf"]) for q in seqs])),
+              "map_corner_pts": float(B * np.mean([len(q["map_corner"]) for q in seqs]))}
         total_kernel_ms = sum(ms for _, ms in prof.values())
         kernels = {}
         for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):

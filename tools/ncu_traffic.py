@@ -27,4 +27,13 @@ MULTI_ROLE = ("grid_count", "grid_scan", "grid_fill", "lm_knn", "lm_fit", "lm_vo
 out = {"n_seq": int(sys.argv[2]), "preset": sys.argv[3], "point_stride": int(sys.argv[4]), "source": sys.argv[1],
        "note": "kernels with one role per step: mean over the captured launches; the others (%s) serve several clouds / phases and are listed per launch in capture order" % ", ".join(MULTI_ROLE),
        "dram_bytes_per_launch": {k: (v if k in MULTI_ROLE else sum(v) / len(v)) for k, v in acc.items()}}
+# the grid-build kernels run once per cloud and step; the four clouds differ in size by an order of magnitude each, so the roles
+# are recognisable from the traffic itself: corner_last < surf_last < map_corner < map_surf
+for k in ("grid_count", "grid_scan", "grid_fill"):
+    v = out["dram_bytes_per_launch"].get(k)
+    if isinstance(v, list) and len(v) >= 4:
+        roles = ("corner_last", "surf_last", "map_corner", "map_surf")
+        per_step = [sorted(v[i:i + 4]) for i in range(0, len(v) - len(v) % 4, 4)]
+        for r, name in enumerate(roles):
+            out["dram_bytes_per_launch"]["%s_%s" % (k, name)] = sum(p[r] for p in per_step) / len(per_step)
 print(json.dumps(out, indent=1))
