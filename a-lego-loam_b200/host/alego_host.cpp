@@ -1,6 +1,7 @@
 // alego_host.cpp — see alego_host.h.  Thin: argument marshalling only, every numeric step is a C-ABI call.
 #include "alego_host.h"
 
+#include <algorithm>
 #include <cstring>
 
 namespace alego {
@@ -18,6 +19,51 @@ int AlegoContext::init(const AlegoParams &p, int device, int n_seq, int max_poin
 }
 
 std::string AlegoContext::last_error() const { return alego_last_error(h_); }
+
+static inline float load_f32(const uint8_t *p, bool swap) {
+  uint8_t b[4];
+  if (swap) { b[0] = p[3]; b[1] = p[2]; b[2] = p[1]; b[3] = p[0]; }
+  else std::memcpy(b, p, 4);
+  float v;
+  std::memcpy(&v, b, 4);
+  return v;
+}
+
+static inline bool host_is_bigendian() {
+  const uint16_t one = 1;
+  return *reinterpret_cast<const uint8_t *>(&one) == 0;
+}
+
+long decode_pointcloud2(const PointCloud2View &m, float *out, int stride, size_t capacity_points) {
+  if (!out || (stride != 3 && stride != 4)) return -1;
+  const size_t n = (size_t)m.width * m.height;
+  if (n == 0) return 0;
+  const uint32_t row_step = m.row_step ? m.row_step : m.width * m.point_step;
+  const uint32_t last = std::max(std::max(m.off_x, m.off_y), std::max(m.off_z, (uint32_t)std::max(m.off_intensity, 0)));
+  if (!m.data || m.point_step < last + 4 || row_step < m.width * m.point_step || n > capacity_points) return -1;
+  const bool swap = m.is_bigendian != host_is_bigendian();
+  float *o = out;
+  for (uint32_t r = 0; r < m.height; ++r) {
+    const uint8_t *p = m.data + (size_t)r * row_step;
+    for (uint32_t c = 0; c < m.width; ++c, p += m.point_step, o += stride) {
+      o[0] = load_f32(p + m.off_x, swap);
+      o[1] = load_f32(p + m.off_y, swap);
+      o[2] = load_f32(p + m.off_z, swap);
+      if (stride == 4) o[3] = m.off_intensity >= 0 ? load_f32(p + m.off_intensity, swap) : 0.f;
+    }
+  }
+  return (long)n;
+}
+
+size_t encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data) {
+  if (!xyzi || !data) return 0;
+  std::memset(data, 0, n * 32);
+  for (size_t i = 0; i < n; ++i) {
+    std::memcpy(data + i * 32, xyzi + i * 4, 12);
+    std::memcpy(data + i * 32 + 16, xyzi + i * 4 + 3, 4);
+  }
+  return n * 32;
+}
 
 ImageProjection::~ImageProjection() {
   if (pinned_) alego_host_free(pinned_);
@@ -38,6 +84,16 @@ int ImageProjection::process(const std::vector<PointCloud> &clouds) {
     if (n > (size_t)ctx_.max_points()) return ALEGO_BAD_ARG;
     n_points_[b] = (int32_t)n;
     if (n) std::memcpy(pinned_ + (size_t)b * ctx_.max_points() * 4, clouds[b].data(), n * sizeof(PointXYZI));
+  }
+  return alego_ip_process(ctx_.handle(), pinned_, n_points_.data());
+}
+
+int ImageProjection::process(const std::vector<PointCloud2View> &msgs) {
+  if (!pinned_ || (int)msgs.size() != ctx_.n_seq()) return ALEGO_BAD_ARG;
+  for (int b = 0; b < ctx_.n_seq(); ++b) {
+    const long n = decode_pointcloud2(msgs[b], pinned_ + (size_t)b * ctx_.max_points() * 4, 4, (size_t)ctx_.max_points());
+    if (n < 0) return ALEGO_BAD_ARG;
+    n_points_[b] = (int32_t)n;
   }
   return alego_ip_process(ctx_.handle(), pinned_, n_points_.data());
 }
@@ -159,3 +215,15 @@ int LaserMapping::pose(int seq, double params[6], double t_map2laser[3], double 
 }
 
 }  // namespace alego
+
+extern "C" {
+long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                                   uint32_t off_x, uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float *out,
+                                   int stride, size_t capacity_points) {
+  alego::PointCloud2View m;
+  m.data = data; m.width = width; m.height = height; m.point_step = point_step; m.row_step = row_step;
+  m.off_x = off_x; m.off_y = off_y; m.off_z = off_z; m.off_intensity = off_intensity; m.is_bigendian = is_bigendian != 0;
+  return alego::decode_pointcloud2(m, out, stride, capacity_points);
+}
+size_t alego_host_encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data) { return alego::encode_pointcloud2_xyzi(xyzi, n, data); }
+}

@@ -35,6 +35,25 @@ struct PointXYZI {  // pcl::PointXYZI payload (utility.h:44), 16 bytes
 };
 typedef std::vector<PointXYZI> PointCloud;
 
+// ---- wire format on either side of the path (the part that needs no ROS) ---------------------------
+// A sensor_msgs/PointCloud2 payload as the subscriber receives it (/lslidar_point_cloud, imageProjection.cpp:42,49-59 —
+// the reference hands it to pcl::fromROSMsg): `width * height` records of `point_step` bytes (rows `row_step` bytes apart)
+// with FLOAT32 fields x / y / z / intensity at the given byte offsets (off_intensity < 0: no such field).
+struct PointCloud2View {
+  const uint8_t *data = nullptr;
+  uint32_t width = 0, height = 1, point_step = 0, row_step = 0;
+  uint32_t off_x = 0, off_y = 4, off_z = 8;
+  int32_t off_intensity = -1;
+  bool is_bigendian = false;
+};
+// pcl::fromROSMsg for this path: decode into `stride` floats per point (3: x, y, z — what the kernels read; 4: + intensity,
+// 0 when the message has none).  NaN / inf stay in place (removeNaNFromPointCloud happens on the device).  Returns the number
+// of points written, or -1 when the view is inconsistent or `capacity_points` is too small.
+long decode_pointcloud2(const PointCloud2View &msg, float *out, int stride, size_t capacity_points);
+// pcl::toROSMsg layout of a PointXYZI cloud (/segmented_cloud, /outlier, imageProjection.cpp:318-336): x, y, z at 0, 4, 8,
+// intensity at 16, point_step 32, little endian.  `data` needs 32 * n bytes; returns the bytes written.
+size_t encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data);
+
 // shared by the three stage objects of one process (nodelet mode: one manager process, zero-copy hand-offs —
 // here: the hand-offs stay in HBM)
 class AlegoContext {
@@ -63,6 +82,8 @@ class ImageProjection {
   int onInit();  // imageProjection.cpp:6-47 minus the ROS plumbing: pinned staging for the decoded sweeps
   // pcCB for a batch: clouds[b] is the decoded /lslidar_point_cloud of sequence b (NaNs allowed, dropped on the device)
   int process(const std::vector<PointCloud> &clouds);
+  // the same straight from the subscriber's messages: decoded into the pinned staging buffer, no intermediate cloud
+  int process(const std::vector<PointCloud2View> &msgs);
   // what publish() sends for sequence `seq` (:318-336): /seg_info, /segmented_cloud, /outlier
   int results(int seq, CloudInfo *info, PointCloud *segmented, PointCloud *outlier);
 
@@ -119,3 +140,11 @@ class LaserMapping {
 };
 
 }  // namespace alego
+
+// C entry points of the two wire-format helpers (ctypes tests, other-language shells)
+extern "C" {
+long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                                   uint32_t off_x, uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float *out,
+                                   int stride, size_t capacity_points);
+size_t alego_host_encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data);
+}

@@ -19,6 +19,50 @@ def test_host_library_builds_and_links(alego):
     assert r.returncode == 2 and "usage" in r.stderr
 
 
+def test_pointcloud2_wire_format_helpers(alego):
+    """sensor_msgs/PointCloud2 <-> sweep buffers (the wire format either side of the path, SURVEY §8f N3 without ROS):
+    arbitrary field offsets / point_step / row padding, both byte orders, packed-xyz and xyzi outputs, NaNs passed through."""
+    import ctypes as C
+    L = C.CDLL(alego.HOST_PATH)
+    L.alego_host_decode_pointcloud2.restype = C.c_long
+    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+    L.alego_host_encode_pointcloud2_xyzi.restype = C.c_size_t
+    L.alego_host_encode_pointcloud2_xyzi.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    rng = np.random.default_rng(1)
+    W, H, step, pad = 37, 3, 22, 5     # velodyne-like record: x y z @0,4,8, intensity @16, ring uint16 @20; rows padded by 5 bytes
+    xyzi = rng.normal(0, 20, (H, W, 4)).astype(np.float32)
+    xyzi[1, 4, 1] = np.nan
+    xyzi[2, 0, 0] = np.inf
+    for big in (False, True):
+        raw = np.zeros((H, W * step + pad), np.uint8)
+        dt = ">f4" if big else "<f4"
+        for r in range(H):
+            rec = raw[r, :W * step].reshape(W, step)
+            for k, off in enumerate((0, 4, 8, 16)):
+                rec[:, off:off + 4] = xyzi[r, :, k].astype(dt).view(np.uint8).reshape(W, 4)
+            rec[:, 20:22] = 7
+        for stride in (3, 4):
+            out = np.zeros((W * H, stride), np.float32)
+            n = L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data,
+                                                stride, len(out))
+            assert n == W * H
+            assert np.array_equal(out, xyzi.reshape(-1, 4)[:, :stride], equal_nan=True)
+        out = np.zeros((W * H, 4), np.float32)   # a message without an intensity field decodes to intensity 0
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, -1, int(big), out.ctypes.data, 4, len(out)) == W * H
+        assert (out[:, 3] == 0).all()
+        # inconsistent views are refused: capacity too small, point_step smaller than a field, row_step smaller than a row
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, 5) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, 10, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, 10, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+    # publisher side: PCL's PointXYZI layout (x y z @0,4,8, intensity @16, 32-byte records), and it decodes back
+    flat = np.ascontiguousarray(xyzi.reshape(-1, 4))
+    msg = np.zeros(len(flat) * 32, np.uint8)
+    assert L.alego_host_encode_pointcloud2_xyzi(flat.ctypes.data, len(flat), msg.ctypes.data) == len(flat) * 32
+    back = np.zeros_like(flat)
+    assert L.alego_host_decode_pointcloud2(msg.ctypes.data, len(flat), 1, 32, 0, 0, 4, 8, 16, 0, back.ctypes.data, 4, len(back)) == len(flat)
+    assert np.array_equal(back, flat, equal_nan=True)
+
+
 @pytest.mark.gpu
 def test_alego_run_matches_ctypes_pipeline(alego, tmp_path):
     P = alego.default_params(alego.PRESET_VLP16_1800)
