@@ -232,7 +232,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   // scan-to-scan
   int rc = grid_alloc(h, &h->g_surf_last, (int)RC, 0.5f);  // dense cloud (every ring voxelised on its own): small cells keep the buckets short
   if (rc != ALEGO_OK) return rc;
-  rc = grid_alloc(h, &h->g_corner_last, (int)(R * 120), 1.0f);
+  rc = grid_alloc(h, &h->g_corner_last, (int)(R * 120), 2.0f);  // sparse cloud: bigger cells settle the 1-NN in the first 3x3x3 pass
   if (rc != ALEGO_OK) return rc;
   DMALLOC(h, h->lo_params, B * 6);
   DMALLOC(h, h->lo_pose, B);
