@@ -51,6 +51,12 @@ class AlegoSolveReport(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class AlegoImuQueue(C.Structure):
+    """The IMU ring buffers of laserOdometry.h:36-46 (caller-owned arrays of `length` doubles)."""
+    _fields_ = [("length", C.c_int32), ("ptr_last", C.c_int32), ("ptr_last_iter", C.c_int32), ("reserved", C.c_int32)] + [
+        (k, C.POINTER(C.c_double)) for k in ("time", "roll", "pitch", "yaw", "shift_x", "shift_y", "shift_z", "velo_x", "velo_y", "velo_z")]
+
+
 class AlegoCloudInfo(C.Structure):
     """Mirror of msg/cloud_info.msg:1-12 (Header omitted)."""
     _fields_ = [("startRingIndex", C.POINTER(C.c_int32)), ("endRingIndex", C.POINTER(C.c_int32)),
@@ -129,6 +135,7 @@ def lib():
         "alego_stage_select": (C.c_int, [H, C.c_int]),
         "alego_ip_get": (C.c_int, [H, C.c_int, C.POINTER(AlegoCloudInfo), C.c_void_p, C.c_void_p, PI, C.c_void_p]),
         "alego_lo_extract": (C.c_int, [H]),
+        "alego_lo_adjust_distortion": (C.c_int, [H, PD, C.POINTER(AlegoImuQueue), C.c_double, PI]),
         "alego_lo_get_features": (C.c_int, [H, C.c_int, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p]),
         "alego_lo_scan2scan": (C.c_int, [H, C.POINTER(AlegoSolveReport)]),
         "alego_lo_get_state": (C.c_int, [H, C.c_int, PD, PD, PD]),
@@ -169,7 +176,7 @@ EXPORTED_SYMBOLS = [
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
     "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
     "alego_timer_elapsed_ms", "alego_profile_enable", "alego_profile_reset", "alego_profile_count", "alego_profile_get",
-    "alego_launch_count", "alego_debug_get",
+    "alego_launch_count", "alego_debug_get", "alego_lo_adjust_distortion",
 ]
 
 
@@ -294,6 +301,23 @@ class Alego:
     # ---- LaserOdometry
     def lo_extract(self):
         return self._chk(self.L.alego_lo_extract(self.h))
+
+    def lo_adjust_distortion(self, scan_times, queues, ptr_last, ptr_last_iter, scan_period=0.2):
+        """adjustDistortion (laserOdometry.cpp:557-657) on the segmented cloud of every sequence, in place on the device.
+        queues: per sequence a (10, len) float64 array (time, roll, pitch, yaw, shift xyz, velocity xyz); ptr_last /
+        ptr_last_iter: per sequence imu_ptr_last_ / imu_ptr_last_iter_.  Returns (points visited [n_seq], new ptr_last_iter)."""
+        B = self.n_seq
+        t = np.ascontiguousarray(scan_times, np.float64).reshape(B)
+        qs = [np.ascontiguousarray(q, np.float64).reshape(10, -1) for q in queues]
+        arr = (AlegoImuQueue * B)()
+        PD = C.POINTER(C.c_double)
+        for b in range(B):
+            arr[b].length, arr[b].ptr_last, arr[b].ptr_last_iter = qs[b].shape[1], int(ptr_last[b]), int(ptr_last_iter[b])
+            for k, name in enumerate(("time", "roll", "pitch", "yaw", "shift_x", "shift_y", "shift_z", "velo_x", "velo_y", "velo_z")):
+                setattr(arr[b], name, qs[b][k].ctypes.data_as(PD))
+        n = np.zeros(B, np.int32)
+        self._chk(self.L.alego_lo_adjust_distortion(self.h, t.ctypes.data_as(PD), arr, float(scan_period), n.ctypes.data_as(C.POINTER(C.c_int32))))
+        return n, np.array([arr[b].ptr_last_iter for b in range(B)], np.int32)
 
     def lo_get_features(self, seq=0):
         R, RC = self.R, self.R * self.Cc

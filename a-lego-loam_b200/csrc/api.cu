@@ -320,7 +320,7 @@ void alego_destroy(AlegoHandle *h) {
                   h->lo_trace_n, h->map_corner, h->map_surf, h->n_map_corner, h->n_map_surf, h->lm_in_corner, h->lm_in_surf,
                   h->lm_in_outlier, h->lm_in_n, h->lm_use_ext, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total,
                   h->lm_surf_total_ds, h->lm_n, h->lm_params, h->m2o, h->o2l, h->m2l, h->lm_edge, h->lm_plane, h->lm_report,
-                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose, h->lm_nn_c, h->lm_nn_s};
+                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose, h->lm_nn_c, h->lm_nn_s, h->imu_q, h->imu_ptr, h->imu_t0};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   grid_free(&h->g_surf_last);
@@ -485,6 +485,58 @@ int alego_lo_extract(AlegoHandle *h) {
   const int rc = lo_extract_device(h);
   if (rc == ALEGO_OK) { h->stage_feat_done = true; h->feat_buf = h->cur; }
   return rc;
+}
+
+// adjustDistortion (laserOdometry.cpp:557-726, IMU branch): between ImageProjection and the feature stage, in place on the
+// segmented cloud of every sequence.
+int alego_lo_adjust_distortion(AlegoHandle *h, const double *scan_time, AlegoImuQueue *queues, double scan_period, int32_t *n_adjusted) {
+  if (!h || !scan_time || !queues || !(scan_period > 0.)) return ALEGO_BAD_ARG;
+  if (!h->stage_ip_done) { h->err = "alego_lo_adjust_distortion before alego_ip_process"; return ALEGO_NOT_READY; }
+  const int B = h->B, len = queues[0].length;
+  if (len < 1) { h->err = "alego_lo_adjust_distortion: empty IMU queue"; return ALEGO_BAD_ARG; }
+  std::vector<double> q((size_t)B * 10 * len);
+  std::vector<int> ptr(3 * (size_t)B, 0);
+  for (int b = 0; b < B; ++b) {
+    const AlegoImuQueue &Q = queues[b];
+    const double *src[10] = {Q.time, Q.roll, Q.pitch, Q.yaw, Q.shift_x, Q.shift_y, Q.shift_z, Q.velo_x, Q.velo_y, Q.velo_z};
+    if (Q.length != len || Q.ptr_last >= len || Q.ptr_last_iter < 0 || Q.ptr_last_iter >= len) {
+      h->err = "alego_lo_adjust_distortion: inconsistent IMU queue"; return ALEGO_BAD_ARG;
+    }
+    for (int k = 0; k < 10; ++k) {
+      if (!src[k]) { h->err = "alego_lo_adjust_distortion: null IMU array"; return ALEGO_BAD_ARG; }
+      std::memcpy(q.data() + ((size_t)b * 10 + k) * len, src[k], (size_t)len * sizeof(double));
+    }
+    // the forward-only pointer walk of :587-595 equals a search only for stamps that do not run backwards over the live
+    // entries imu_ptr_last_iter_ .. imu_ptr_last_ (any IMU driver; the reference assumes it as well)
+    if (Q.ptr_last > 0)
+      for (int k = Q.ptr_last_iter; k != Q.ptr_last; k = (k + 1) % len)
+        if (Q.time[(k + 1) % len] < Q.time[k]) { h->err = "alego_lo_adjust_distortion: IMU stamps run backwards"; return ALEGO_BAD_ARG; }
+    ptr[b] = Q.ptr_last;
+    ptr[B + b] = Q.ptr_last_iter;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
+  if (len != h->imu_len) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->imu_q) cudaFree(h->imu_q);
+    h->imu_q = nullptr;
+    h->imu_len = 0;
+    DMALLOC(h, h->imu_q, (size_t)B * 10 * len);
+    if (!h->imu_ptr) DMALLOC(h, h->imu_ptr, 3 * (size_t)B);
+    if (!h->imu_t0) DMALLOC(h, h->imu_t0, B);
+    h->imu_len = len;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->imu_q, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->imu_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->imu_t0, scan_time, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = lo_adjust_distortion_device(h, h->imu_q, len, h->imu_ptr, h->imu_ptr + B, h->imu_t0, scan_period, h->imu_ptr + 2 * B);
+  if (rc != ALEGO_OK) return rc;
+  if ((rc = d2h(h, ptr.data(), h->imu_ptr, ptr.size() * sizeof(int))) != ALEGO_OK) return rc;
+  for (int b = 0; b < B; ++b) {
+    queues[b].ptr_last_iter = ptr[B + b];
+    if (n_adjusted) n_adjusted[b] = ptr[2 * B + b];
+  }
+  return ALEGO_OK;
 }
 
 int alego_lo_get_features(AlegoHandle *h, int seq, int32_t *sharp_idx, int32_t *n_sharp, int32_t *less_sharp_idx, int32_t *n_less_sharp,

@@ -152,6 +152,12 @@ struct AlegoHandle {
   int *az_off[2] = {nullptr, nullptr};         // [B][R][AZ_BINS+1] bin starts inside each ring
   int cur = 0;                                 // which buffer holds the CURRENT scan's clouds
 
+  // ---------------- LaserOdometry distortion correction (optional stage) ----------------
+  double *imu_q = nullptr;     // [B][10][imu_len]  time, roll, pitch, yaw, shift xyz, velocity xyz (laserOdometry.h:36-46)
+  int imu_len = 0;
+  int *imu_ptr = nullptr;      // [3][B]  imu_ptr_last_, imu_ptr_last_iter_, points visited
+  double *imu_t0 = nullptr;    // [B]  scan_time
+
   // ---------------- LaserOdometry scan-to-scan ----------------
   GridIndex g_surf_last, g_corner_last;
   double *lo_params = nullptr;  // [B][6]

@@ -2,6 +2,7 @@
 #include "alego_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace alego {
@@ -129,6 +130,90 @@ int ImageProjection::results(int seq, CloudInfo *info, PointCloud *segmented, Po
   return ALEGO_OK;
 }
 
+ImuQueue::ImuQueue(int length) : len_(std::max(length, 1)), a_((size_t)10 * std::max(length, 1), 0.0) {}
+
+AlegoImuQueue ImuQueue::view() const {
+  AlegoImuQueue v{};
+  v.length = len_;
+  v.ptr_last = ptr_last;
+  v.ptr_last_iter = ptr_last_iter;
+  const double *b = a_.data();
+  v.time = b; v.roll = b + len_; v.pitch = b + 2 * len_; v.yaw = b + 3 * len_;
+  v.shift_x = b + 4 * len_; v.shift_y = b + 5 * len_; v.shift_z = b + 6 * len_;
+  v.velo_x = b + 7 * len_; v.velo_y = b + 8 * len_; v.velo_z = b + 9 * len_;
+  return v;
+}
+
+// tf::Matrix3x3(tf::Quaternion).getRPY (tf/LinearMath/Matrix3x3.h: setRotation + getEulerYPR, first solution), in double
+static void quaternion_to_rpy(double x, double y, double z, double w, double &roll, double &pitch, double &yaw) {
+  const double d = x * x + y * y + z * z + w * w;
+  const double s = 2.0 / d;
+  const double xs = x * s, ys = y * s, zs = z * s;
+  const double wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+  const double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  if (std::fabs(m20) >= 1) {  // gimbal lock
+    yaw = 0;
+    roll = std::atan2(m21, m22);
+    pitch = m20 < 0 ? M_PI / 2.0 : -M_PI / 2.0;
+  } else {
+    pitch = -std::asin(m20);
+    roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+    yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+  }
+}
+
+void ImuQueue::push(const ImuMsg &m) {
+  double *T = a_.data(), *RO = T + len_, *PI_ = T + 2 * len_, *YA = T + 3 * len_;
+  double *S[3] = {T + 4 * len_, T + 5 * len_, T + 6 * len_}, *V[3] = {T + 7 * len_, T + 8 * len_, T + 9 * len_};
+  double roll, pitch, yaw;
+  quaternion_to_rpy(m.qx, m.qy, m.qz, m.qw, roll, pitch, yaw);
+  const double acc_x = m.ax + 9.81 * std::sin(pitch);                    // :768-770
+  const double acc_y = m.ay - 9.81 * std::cos(pitch) * std::sin(roll);
+  const double acc_z = m.az - 9.81 * std::cos(pitch) * std::cos(roll);
+  ptr_last = (ptr_last + 1) % len_;                                      // :772-776
+  if ((ptr_last + 1) % len_ == ptr_front) ptr_front = (ptr_front + 1) % len_;
+  T[ptr_last] = m.stamp;
+  RO[ptr_last] = roll; PI_[ptr_last] = pitch; YA[ptr_last] = yaw;
+  // Eigen::Quaternionf(w, x, y, z).toRotationMatrix() * Vector3f(acc) (:784-785), float
+  const float w = (float)m.qw, x = (float)m.qx, y = (float)m.qy, z = (float)m.qz;
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  const float Rm[9] = {1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.f - (txx + tyy)};
+  const float af[3] = {(float)acc_x, (float)acc_y, (float)acc_z};
+  float acc[3];
+  for (int k = 0; k < 3; ++k) acc[k] = (Rm[k * 3] * af[0] + Rm[k * 3 + 1] * af[1]) + Rm[k * 3 + 2] * af[2];
+  const int back = (ptr_last - 1 + len_) % len_;                         // :790-803
+  const double time_diff = T[ptr_last] - T[back];
+  if (time_diff < 1.) {
+    for (int k = 0; k < 3; ++k) {
+      S[k][ptr_last] = S[k][back] + V[k][back] * time_diff + acc[k] * time_diff * time_diff * 0.5;
+      V[k][ptr_last] = V[k][back] + acc[k] * time_diff;
+    }
+  }
+}
+
+int LaserOdometry::onInit() {
+  if (!ctx_.handle()) return ALEGO_NOT_READY;
+  imu_.assign(ctx_.n_seq(), ImuQueue(200));
+  return ALEGO_OK;
+}
+
+int LaserOdometry::imuHandler(int seq, const ImuMsg &msg) {
+  if (seq < 0 || seq >= (int)imu_.size()) return ALEGO_BAD_ARG;
+  imu_[seq].push(msg);
+  return ALEGO_OK;
+}
+
+int LaserOdometry::adjustDistortion(const double *scan_time, int32_t *n_adjusted, double scan_period) {
+  if (!scan_time || imu_.empty()) return ALEGO_BAD_ARG;
+  std::vector<AlegoImuQueue> v(imu_.size());
+  for (size_t b = 0; b < imu_.size(); ++b) v[b] = imu_[b].view();
+  const int rc = alego_lo_adjust_distortion(ctx_.handle(), scan_time, v.data(), scan_period, n_adjusted);
+  if (rc != ALEGO_OK) return rc;
+  for (size_t b = 0; b < imu_.size(); ++b) imu_[b].ptr_last_iter = v[b].ptr_last_iter;  // :656
+  return ALEGO_OK;
+}
+
 int LaserOdometry::process(AlegoSolveReport *reports) {
   const int rc = alego_lo_extract(ctx_.handle());
   if (rc != ALEGO_OK) return rc;
@@ -226,4 +311,15 @@ long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t
   return alego::decode_pointcloud2(m, out, stride, capacity_points);
 }
 size_t alego_host_encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data) { return alego::encode_pointcloud2_xyzi(xyzi, n, data); }
+void *alego_host_imu_create(int length) { return new alego::ImuQueue(length); }
+void alego_host_imu_destroy(void *q) { delete static_cast<alego::ImuQueue *>(q); }
+void alego_host_imu_push(void *q, const double msg[8]) {
+  static_cast<alego::ImuQueue *>(q)->push(alego::ImuMsg{msg[0], msg[1], msg[2], msg[3], msg[4], msg[5], msg[6], msg[7]});
+}
+void alego_host_imu_get(const void *q, double *arrays, int32_t ptrs[3]) {
+  const alego::ImuQueue *Q = static_cast<const alego::ImuQueue *>(q);
+  const AlegoImuQueue v = Q->view();
+  if (arrays) std::memcpy(arrays, v.time, sizeof(double) * 10 * (size_t)v.length);
+  if (ptrs) { ptrs[0] = Q->ptr_front; ptrs[1] = Q->ptr_last; ptrs[2] = Q->ptr_last_iter; }
+}
 }

@@ -93,10 +93,40 @@ class ImageProjection {
   std::vector<int32_t> n_points_;
 };
 
+// sensor_msgs/Imu as imuHandler reads it (laserOdometry.cpp:761-771): stamp, orientation quaternion, linear acceleration
+struct ImuMsg {
+  double stamp;
+  double qx, qy, qz, qw;
+  double ax, ay, az;
+};
+
+// The IMU ring buffers of LaserOdometry (laserOdometry.h:36-46) and imuHandler's dead-reckoning (laserOdometry.cpp:761-804):
+// orientation -> roll / pitch / yaw (tf::Matrix3x3::getRPY), gravity removed from the acceleration in the sensor frame, rotated
+// to the IMU's world frame (float, Eigen::Quaternionf), velocity and shift integrated while consecutive stamps are < 1 s apart.
+class ImuQueue {
+ public:
+  explicit ImuQueue(int length = 200);  // imu_queue_length, utility.h:70
+  void push(const ImuMsg &m);
+  AlegoImuQueue view() const;           // borrowed pointers, valid until the next push
+  int ptr_front = 0, ptr_last = -1, ptr_last_iter = 0;  // laserOdometry.cpp:17-19
+  int length() const { return len_; }
+
+ private:
+  int len_;
+  std::vector<double> a_;  // [10][len]: time, roll, pitch, yaw, shift xyz, velocity xyz
+};
+
 class LaserOdometry {
  public:
   explicit LaserOdometry(AlegoContext &ctx) : ctx_(ctx) {}
-  int onInit() { return ALEGO_OK; }  // laserOdometry.cpp:6-77: state lives in the handle (params_, t_w_cur_, r_w_cur_)
+  // laserOdometry.cpp:6-77: solver state lives in the handle (params_, t_w_cur_, r_w_cur_); the IMU queues start empty (:17-29)
+  int onInit();
+  // /imu/data subscriber of sequence `seq` (:71, :761-804)
+  int imuHandler(int seq, const ImuMsg &msg);
+  // step 1 of mainLoop (:111-116, body :557-657) — optional, the reference has the call commented out: motion-compensates the
+  // segmented clouds ImageProjection left in HBM with the IMU queues; scan_time[n_seq] = stamp of the sweeps (t1, :96)
+  int adjustDistortion(const double *scan_time, int32_t *n_adjusted = nullptr, double scan_period = 0.2);
+  const ImuQueue *imuQueue(int seq) const { return seq >= 0 && seq < (int)imu_.size() ? &imu_[seq] : nullptr; }
   // one pass of mainLoop after message sync (:118-535): features + scan-to-scan; reports[n_seq] may be null
   int process(AlegoSolveReport *reports = nullptr);
   int odometry(int seq, double params[6], double t_w_cur[3], double r_w_cur[9]);  // /odom/lidar (:513-529)
@@ -106,6 +136,7 @@ class LaserOdometry {
 
  private:
   AlegoContext &ctx_;
+  std::vector<ImuQueue> imu_;  // per sequence
 };
 
 class LaserMapping {
@@ -147,4 +178,9 @@ long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t
                                    uint32_t off_x, uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float *out,
                                    int stride, size_t capacity_points);
 size_t alego_host_encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data);
+// alego::ImuQueue for ctypes: msg = stamp, qx, qy, qz, qw, ax, ay, az; get copies the [10][length] arrays and the three pointers
+void *alego_host_imu_create(int length);
+void alego_host_imu_destroy(void *q);
+void alego_host_imu_push(void *q, const double msg[8]);
+void alego_host_imu_get(const void *q, double *arrays, int32_t ptrs[3] /* front, last, last_iter */);
 }

@@ -134,6 +134,28 @@ int alego_stage_select(AlegoHandle *h, int slot);
 int alego_ip_get(AlegoHandle *h, int seq, AlegoCloudInfo *info, float *segmented_xyzi, float *outlier_xyzi,
                  int32_t *n_outlier, int32_t *label_image);
 
+/* ---- LaserOdometry, motion-distortion correction (optional): LaserOdometry::adjustDistortion
+ *      (src/laserOdometry.cpp:557-726, IMU branch :581-657).  The reference has the call commented out (:115), so the
+ *      pipeline entry points never run it; a caller that wants it calls it between alego_ip_* and alego_lo_extract. ---- */
+/* The IMU ring buffers imuHandler fills (laserOdometry.h:36-46, laserOdometry.cpp:761-804), caller-owned. */
+typedef struct AlegoImuQueue {
+  int32_t length;         /* imu_queue_length (utility.h:70, 200); at most 2048 */
+  int32_t ptr_last;       /* imu_ptr_last_: newest entry; <= 0 means "not enough IMU data", nothing is adjusted (:583) */
+  int32_t ptr_last_iter;  /* imu_ptr_last_iter_: in = where the previous sweep stopped; out = where this one stopped (:656) */
+  int32_t reserved;
+  const double *time, *roll, *pitch, *yaw;        /* [length] */
+  const double *shift_x, *shift_y, *shift_z;      /* [length] */
+  const double *velo_x, *velo_y, *velo_z;         /* [length] */
+} AlegoImuQueue;
+/* In place on the segmented cloud of every sequence (what alego_ip_get returns and alego_lo_extract reads).
+ * scan_time[n_seq]: stamp of the sweep (t1, :96); queues[n_seq]; scan_period: utility.h:53 (0.2).  n_adjusted[n_seq]
+ * (may be NULL): points visited before the "unsync imu and pc msg" return (:596-600) — the cloud size when that never
+ * happened, 0 when the queue holds fewer than two messages.  The IMU stamps must not run backwards over the entries
+ * ptr_last_iter .. ptr_last (ALEGO_BAD_ARG otherwise).  The use_odom branch (:660-714) is compiled out in the reference
+ * (use_imu = true, use_odom = false, utility.h:68-69) and is not provided. */
+int alego_lo_adjust_distortion(AlegoHandle *h, const double *scan_time, AlegoImuQueue *queues, double scan_period,
+                               int32_t *n_adjusted);
+
 /* ---- LaserOdometry, features: replaces steps 2-4 of LaserOdometry::mainLoop
  *      (src/laserOdometry.cpp:118-297) ------------------------------------------------------------ */
 int alego_lo_extract(AlegoHandle *h);

@@ -1502,6 +1502,90 @@ int oracle_lm_assemble_map(int n_kf, const float *const *corner, const int *nc, 
   return ALEGO_OK;
 }
 
+// ---- N2: LaserOdometry::adjustDistortion, IMU branch (src/laserOdometry.cpp:557-657) --------------------------------------
+// Literal sequential restatement: the forward-only walk of imu_ptr_front_ from imu_ptr_last_iter_ (:587-595), the early
+// `return` on unsynchronised stamps (:596-600), the interpolation in double stored to Eigen float vectors (:602-629), the
+// start pose taken from point 0 (:633-639) and adjusted_p = r_s_i * (r_c * p + shift_from_start) (:640-655).
+// Eigen (unpinned, not in the container; restated from Eigen 3.3): AngleAxisf products through float quaternions
+// (keyframe_matrix above), Matrix3f::inverse() = cofactor inverse of LU/InverseImpl.h (determinant from the cofactors of
+// column 0, summed by the unrolled redux a0 + (a1 + a2)), `Vector3f * double` converts the scalar to float first
+// (promote_scalar_arg), fixed 3x3 products accumulate left to right.  The use_odom branch (:660-714) is dead code
+// (use_imu = true, utility.h:68-69) and is not restated.
+// q: [10][len] doubles — time, roll, pitch, yaw, shift x y z, velocity x y z.  Returns the number of points visited.
+int oracle_adjust_distortion(float *xyzi, int n, const int *col, float start_orientation, float end_orientation, int horizon_scan,
+                             double scan_period, double scan_time, const double *q, int len, int ptr_last, int *ptr_last_iter) {
+  P4 *pts = reinterpret_cast<P4 *>(xyzi);
+  const double *imu_time = q;
+  int start_ori = (start_orientation + 2 * M_PI) / horizon_scan;
+  int end_ori = (end_orientation + 2 * M_PI) / horizon_scan;
+  if (start_ori >= horizon_scan) start_ori -= horizon_scan;
+  if (end_ori >= horizon_scan) end_ori -= horizon_scan;
+  int ori_diff = end_ori - start_ori;
+  if (ori_diff <= 0) ori_diff = horizon_scan;
+  float rpy_start[3] = {0, 0, 0}, shift_start[3] = {0, 0, 0}, velo_start[3] = {0, 0, 0}, rpy_cur[3], shift_cur[3], velo_cur[3];
+  float r_s_i[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  (void)rpy_start;
+  int last_iter = *ptr_last_iter, visited = 0;
+  for (int i = 0; i < n; ++i) {
+    P4 &p = pts[i];
+    const double rel_time = (col[i] - start_ori) * scan_period / ori_diff;
+    const double cur_time = scan_time + rel_time;
+    if (ptr_last > 0) {
+      int front = last_iter;
+      while (front != ptr_last) {
+        if (cur_time < imu_time[front]) break;
+        front = (front + 1) % len;
+      }
+      if (std::abs(cur_time - imu_time[front]) > scan_period) break;  // "unsync imu and pc msg": return
+      if (cur_time > imu_time[front]) {
+        for (int k = 0; k < 3; ++k) {
+          rpy_cur[k] = q[(1 + k) * len + front];
+          shift_cur[k] = q[(4 + k) * len + front];
+          velo_cur[k] = q[(7 + k) * len + front];
+        }
+      } else {
+        const int back = (front - 1 + len) % len;
+        const double ratio_front = (cur_time - imu_time[back]) / (imu_time[front] - imu_time[back]);
+        const double ratio_back = 1. - ratio_front;
+        for (int k = 0; k < 3; ++k) {
+          rpy_cur[k] = q[(1 + k) * len + front] * ratio_front + q[(1 + k) * len + back] * ratio_back;
+          shift_cur[k] = q[(4 + k) * len + front] * ratio_front + q[(4 + k) * len + back] * ratio_back;
+          velo_cur[k] = q[(7 + k) * len + front] * ratio_front + q[(7 + k) * len + back] * ratio_back;
+        }
+      }
+      const float pose6[6] = {0.f, 0.f, 0.f, rpy_cur[0], rpy_cur[1], rpy_cur[2]};
+      float M[12];
+      keyframe_matrix(pose6, M);
+      const float r_c[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+      if (i == 0) {
+        for (int k = 0; k < 3; ++k) { rpy_start[k] = rpy_cur[k]; shift_start[k] = shift_cur[k]; velo_start[k] = velo_cur[k]; }
+        auto cof = [&](int a, int b) {
+          const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+          return r_c[a1 * 3 + b1] * r_c[a2 * 3 + b2] - r_c[a1 * 3 + b2] * r_c[a2 * 3 + b1];
+        };
+        const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+        const float det = c0 * r_c[0] + (c1 * r_c[3] + c2 * r_c[6]);
+        const float invdet = 1.f / det;
+        r_s_i[0] = c0 * invdet; r_s_i[1] = c1 * invdet; r_s_i[2] = c2 * invdet;
+        r_s_i[3] = cof(0, 1) * invdet; r_s_i[4] = cof(1, 1) * invdet; r_s_i[5] = cof(2, 1) * invdet;
+        r_s_i[6] = cof(0, 2) * invdet; r_s_i[7] = cof(1, 2) * invdet; r_s_i[8] = cof(2, 2) * invdet;
+      } else {
+        const float relf = (float)rel_time;
+        float sh[3], a[3];
+        for (int k = 0; k < 3; ++k) sh[k] = (shift_cur[k] - shift_start[k]) - velo_start[k] * relf;
+        for (int k = 0; k < 3; ++k) a[k] = ((r_c[k * 3] * p.x + r_c[k * 3 + 1] * p.y) + r_c[k * 3 + 2] * p.z) + sh[k];
+        p.x = (r_s_i[0] * a[0] + r_s_i[1] * a[1]) + r_s_i[2] * a[2];
+        p.y = (r_s_i[3] * a[0] + r_s_i[4] * a[1]) + r_s_i[5] * a[2];
+        p.z = (r_s_i[6] * a[0] + r_s_i[7] * a[1]) + r_s_i[8] * a[2];
+      }
+      last_iter = front;
+      ++visited;
+    }
+  }
+  *ptr_last_iter = last_iter;
+  return visited;
+}
+
 // k-NN of nq queries against n points; idx [nq][k], dist [nq][k]; brute!=0 uses the O(n) scan
 int oracle_knn(const float *pts, int n, const float *q, int nq, int k, int brute, int32_t *idx, float *dist) {
   if (k < 1 || k > 8) return ALEGO_BAD_ARG;

@@ -55,6 +55,8 @@ def lib():
         L.oracle_lm_assemble_map.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                              C.POINTER(C.c_int), C.c_void_p]
+        L.oracle_adjust_distortion.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_double, C.c_double,
+                                               C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -195,6 +197,19 @@ def lm_assemble_map(corner_kfs, surf_kfs, outlier_kfs, poses6, leaf_c=0.4, leaf_
     lib().oracle_lm_assemble_map(K, cp, _p(cn), sp, _p(sn), op, _p(on), _p(poses6), leaf_c, leaf_s, int(stable), _p(co), C.byref(nco),
                                  _p(so), C.byref(nso), _p(M))
     return co[:nco.value], so[:nso.value], M[:K]
+
+
+def adjust_distortion(cloud, col, start_orientation, end_orientation, horizon_scan, scan_time, queue, ptr_last, ptr_last_iter,
+                      scan_period=0.2):
+    """LaserOdometry::adjustDistortion, IMU branch (laserOdometry.cpp:557-657).  queue: (10, len) float64 — time, roll, pitch, yaw,
+    shift xyz, velocity xyz.  Returns (adjusted cloud, points visited, imu_ptr_last_iter_ afterwards)."""
+    out = np.array(cloud, np.float32).reshape(-1, 4).copy()
+    col = np.ascontiguousarray(col, np.int32)
+    queue = np.ascontiguousarray(queue, np.float64).reshape(10, -1)
+    it = C.c_int(int(ptr_last_iter))
+    n = lib().oracle_adjust_distortion(_p(out), len(out), _p(col), float(start_orientation), float(end_orientation), int(horizon_scan),
+                                       float(scan_period), float(scan_time), _p(queue), queue.shape[1], int(ptr_last), C.byref(it))
+    return out, n, it.value
 
 
 def knn(pts, q, k, brute=False):
