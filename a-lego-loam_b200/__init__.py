@@ -57,6 +57,12 @@ class AlegoImuQueue(C.Structure):
         (k, C.POINTER(C.c_double)) for k in ("time", "roll", "pitch", "yaw", "shift_x", "shift_y", "shift_z", "velo_x", "velo_y", "velo_z")]
 
 
+class AlegoIcpResult(C.Structure):
+    """What performLoopClosure reads from the ICP object (laserMapping.cpp:686-688)."""
+    _fields_ = [("final_transformation", C.c_float * 16), ("fitness_score", C.c_double), ("has_converged", C.c_int32),
+                ("iterations", C.c_int32), ("convergence_state", C.c_int32), ("n_correspondences", C.c_int32)]
+
+
 class AlegoCloudInfo(C.Structure):
     """Mirror of msg/cloud_info.msg:1-12 (Header omitted)."""
     _fields_ = [("startRingIndex", C.POINTER(C.c_int32)), ("endRingIndex", C.POINTER(C.c_int32)),
@@ -135,6 +141,8 @@ def lib():
         "alego_stage_select": (C.c_int, [H, C.c_int]),
         "alego_ip_get": (C.c_int, [H, C.c_int, C.POINTER(AlegoCloudInfo), C.c_void_p, C.c_void_p, PI, C.c_void_p]),
         "alego_lo_extract": (C.c_int, [H]),
+        "alego_lc_icp": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double,
+                                   C.POINTER(AlegoIcpResult), C.c_void_p]),
         "alego_lo_adjust_distortion": (C.c_int, [H, PD, C.POINTER(AlegoImuQueue), C.c_double, PI]),
         "alego_lo_get_features": (C.c_int, [H, C.c_int, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p, PI, C.c_void_p]),
         "alego_lo_scan2scan": (C.c_int, [H, C.POINTER(AlegoSolveReport)]),
@@ -176,7 +184,7 @@ EXPORTED_SYMBOLS = [
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
     "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
     "alego_timer_elapsed_ms", "alego_profile_enable", "alego_profile_reset", "alego_profile_count", "alego_profile_get",
-    "alego_launch_count", "alego_debug_get", "alego_lo_adjust_distortion",
+    "alego_launch_count", "alego_debug_get", "alego_lo_adjust_distortion", "alego_lc_icp",
 ]
 
 
@@ -458,6 +466,19 @@ class Alego:
         poses6 = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
         self._cap_map = (int(cn.sum()), int(sn.sum() + on.sum()))
         return self._chk(self.L.alego_lm_assemble_map(self.h, seq, len(ck), cp, _ptr(cn), sp, _ptr(sn), op, _ptr(on), _ptr(poses6)))
+
+    def lc_icp(self, source, target, max_corr_dist=100.0, max_iterations=100, transformation_epsilon=1e-6, fitness_epsilon=1e-6):
+        """The ICP of performLoopClosure (laserMapping.cpp:667-688) on two (n,4) clouds: alego_lc_icp.  Returns a dict like
+        oracle.binding.icp."""
+        src = np.ascontiguousarray(source, np.float32).reshape(-1, 4)
+        tgt = np.ascontiguousarray(target, np.float32).reshape(-1, 4)
+        res = AlegoIcpResult()
+        trace = np.zeros((max_iterations, 14))
+        self._chk(self.L.alego_lc_icp(self.h, _ptr(src), len(src), _ptr(tgt), len(tgt), max_corr_dist, max_iterations,
+                                      transformation_epsilon, fitness_epsilon, C.byref(res), _ptr(trace)))
+        return {"T": np.array(res.final_transformation, np.float32).reshape(4, 4), "fitness": res.fitness_score,
+                "converged": bool(res.has_converged), "state": res.convergence_state, "iterations": res.iterations,
+                "n_correspondences": res.n_correspondences, "trace": trace[:res.iterations]}
 
     def lm_get_downsampled(self, seq=0):
         """(laser_corner_ds_, laser_surf_ds_, laser_outlier_ds_) of the last mapped sweep (laserMapping.cpp:325-346)."""

@@ -320,13 +320,15 @@ void alego_destroy(AlegoHandle *h) {
                   h->lo_trace_n, h->map_corner, h->map_surf, h->n_map_corner, h->n_map_surf, h->lm_in_corner, h->lm_in_surf,
                   h->lm_in_outlier, h->lm_in_n, h->lm_use_ext, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total,
                   h->lm_surf_total_ds, h->lm_n, h->lm_params, h->m2o, h->o2l, h->m2l, h->lm_edge, h->lm_plane, h->lm_report,
-                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose, h->lm_nn_c, h->lm_nn_s, h->imu_q, h->imu_ptr, h->imu_t0};
+                  h->lm_trace, h->lm_trace_n, h->lm_guard, h->d_pose, h->lm_nn_c, h->lm_nn_s, h->imu_q, h->imu_ptr, h->imu_t0, h->imu_start, h->icp_src, h->icp_src0, h->icp_tgt,
+                  h->icp_partials, h->icp_trace, h->icp_state, h->icp_n};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   grid_free(&h->g_surf_last);
   grid_free(&h->g_corner_last);
   grid_free(&h->g_map_corner);
   grid_free(&h->g_map_surf);
+  grid_free(&h->g_icp);
   if (h->h_pose) cudaFreeHost(h->h_pose);
   for (auto &k : h->prof)
     for (auto &pr : k.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -524,12 +526,13 @@ int alego_lo_adjust_distortion(AlegoHandle *h, const double *scan_time, AlegoImu
     DMALLOC(h, h->imu_q, (size_t)B * 10 * len);
     if (!h->imu_ptr) DMALLOC(h, h->imu_ptr, 3 * (size_t)B);
     if (!h->imu_t0) DMALLOC(h, h->imu_t0, B);
+    if (!h->imu_start) DMALLOC(h, h->imu_start, 16 * (size_t)B);
     h->imu_len = len;
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->imu_q, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->imu_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->imu_t0, scan_time, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  int rc = lo_adjust_distortion_device(h, h->imu_q, len, h->imu_ptr, h->imu_ptr + B, h->imu_t0, scan_period, h->imu_ptr + 2 * B);
+  int rc = lo_adjust_distortion_device(h, h->imu_q, len, h->imu_ptr, h->imu_ptr + B, h->imu_t0, scan_period, h->imu_ptr + 2 * B, h->imu_start);
   if (rc != ALEGO_OK) return rc;
   if ((rc = d2h(h, ptr.data(), h->imu_ptr, ptr.size() * sizeof(int))) != ALEGO_OK) return rc;
   for (int b = 0; b < B; ++b) {
@@ -719,6 +722,26 @@ int alego_lm_get_map(AlegoHandle *h, int seq, float *corner_xyzi, int32_t *n_cor
   if (corner_xyzi && (rc = d2h(h, corner_xyzi, h->map_corner + (size_t)seq * h->map_cap_c, (size_t)nc * sizeof(float4))) != ALEGO_OK) return rc;
   if (surf_xyzi && (rc = d2h(h, surf_xyzi, h->map_surf + (size_t)seq * h->map_cap_s, (size_t)ns * sizeof(float4))) != ALEGO_OK) return rc;
   return ALEGO_OK;
+}
+
+// The ICP of performLoopClosure (laserMapping.cpp:667-688)
+int alego_lc_icp(AlegoHandle *h, const float *source_xyzi, int32_t n_source, const float *target_xyzi, int32_t n_target,
+                 double max_correspondence_distance, int32_t max_iterations, double transformation_epsilon,
+                 double euclidean_fitness_epsilon, AlegoIcpResult *out, double *trace) {
+  if (!h || !out || n_source < 0 || n_target < 0 || (n_source && !source_xyzi) || (n_target && !target_xyzi) || max_iterations < 1 ||
+      !(max_correspondence_distance > 0.))
+    return ALEGO_BAD_ARG;
+  if (n_source == 0 || n_target == 0) {  // PCL: "Invalid or empty point cloud dataset given" — align() returns without converging
+    std::memset(out, 0, sizeof *out);
+    for (int k = 0; k < 4; ++k) out->final_transformation[k * 5] = 1.f;
+    out->convergence_state = 5;
+    out->fitness_score = 1.7976931348623157e308;
+    return ALEGO_FEW_FEATURES;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->dev));
+  if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
+  return lc_icp_device(h, source_xyzi, n_source, target_xyzi, n_target, max_correspondence_distance, max_iterations,
+                       transformation_epsilon, euclidean_fitness_epsilon, out, trace);
 }
 
 int alego_lm_set_scan(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t n_corner, const float *surf_xyzi, int32_t n_surf,

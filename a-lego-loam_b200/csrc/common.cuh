@@ -157,6 +157,7 @@ struct AlegoHandle {
   int imu_len = 0;
   int *imu_ptr = nullptr;      // [3][B]  imu_ptr_last_, imu_ptr_last_iter_, points visited
   double *imu_t0 = nullptr;    // [B]  scan_time
+  float *imu_start = nullptr;  // [B][16]  r_s_i (9), shift_start (3), velo_start (3) of the sweep (laserOdometry.cpp:633-639)
 
   // ---------------- LaserOdometry scan-to-scan ----------------
   GridIndex g_surf_last, g_corner_last;
@@ -198,6 +199,14 @@ struct AlegoHandle {
   double *lm_trace = nullptr;  // [B][outer*(iters+1)][7]
   int *lm_trace_n = nullptr;
   int lm_trace_cap = 0, lo_trace_cap = 0;
+
+  // ---------------- loop-closure ICP (one cloud pair at a time, independent of B) ----------------
+  float4 *icp_src = nullptr, *icp_src0 = nullptr, *icp_tgt = nullptr;  // current / original source, target
+  int icp_cap_src = 0, icp_cap_tgt = 0, icp_trace_cap = 0;
+  GridIndex g_icp;
+  double *icp_partials = nullptr, *icp_trace = nullptr;
+  void *icp_state = nullptr;  // IcpState (lc_icp_kernels.cu)
+  int *icp_n = nullptr;       // [2] source / target point counts
 
   // host staging for small D2H results
   double *h_pose = nullptr;  // pinned [B][12]

@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float4 *__restrict
 
 }  // namespace
 
-int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2) {
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2, int batch) {
   grid_free(g);
+  const int nb = batch > 0 ? batch : h->B;
   ++h->graph_epoch;  // captured graphs hold the old table / array pointers
   g->cap = cap;
   g->cell = cell;
@@ -93,9 +94,9 @@ int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_fact
   if (T < 1024) T = 1024;
   T <<= table_factor_log2;
   g->table_size = T;
-  CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)h->B * GRID_TABLE_STRIDE(T) * sizeof(int)));
-  CUDA_TRY(h, cudaMalloc(&g->sorted, (size_t)h->B * cap * sizeof(float4)));
-  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)h->B * GRID_TABLE_STRIDE(T) * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMalloc(&g->cell_start, (size_t)nb * GRID_TABLE_STRIDE(T) * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&g->sorted, (size_t)nb * cap * sizeof(float4)));
+  CUDA_TRY(h, cudaMemsetAsync(g->cell_start, 0, (size_t)nb * GRID_TABLE_STRIDE(T) * sizeof(int), h->stream));
   return ALEGO_OK;
 }
 
@@ -108,8 +109,8 @@ void grid_free(GridIndex *g) {
 }
 
 int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag,
-               bool pack_ring) {
-  const int B = h->B, T = g->table_size;
+               bool pack_ring, int batch) {
+  const int B = batch > 0 ? batch : h->B, T = g->table_size;
   cudaStream_t s = h->launch_stream ? h->launch_stream : h->stream;
   const float inv = 1.0f / g->cell;
   const int blocks = min(div_up(g->cap, 256), 128);  // capacity-sized clouds are mostly far from full: bounded grid, stride loops

@@ -26,11 +26,12 @@ __device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const f
   return r;
 }
 
-int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2 = 0);
+// batch: number of clouds the index holds (default: one per sequence of the handle)
+int grid_alloc(AlegoHandle *h, GridIndex *g, int cap, float cell, int table_factor_log2 = 0, int batch = -1);
 void grid_free(GridIndex *g);
 // pts: [B] clouds `pts_stride` points apart; point count of sequence b = n_ptr[b * n_stride]
 // pack_ring: store int(intensity) (the ring id of LaserOdometry's feature clouds) in bits 24..30 of the index word
 #define GRID_RING_SHIFT 24
 #define GRID_INDEX_MASK 0x00ffffff
 int grid_build(AlegoHandle *h, GridIndex *g, const float4 *pts, size_t pts_stride, const int *n_ptr, int n_stride, const char *tag,
-               bool pack_ring = false);
+               bool pack_ring = false, int batch = -1);

@@ -10,3 +10,6 @@ int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float 
 // N1 (laserMapping.cpp:194-323): concatenate host clouds, transform each by its keyframe matrix, VoxelGrid into dst (device)
 int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *seg_n, int n_seg, const float *M_host, int n_mat,
                       int mat_shift, float leaf, float4 *dst, int *n_dst);
+// N4 (laserMapping.cpp:652-711): pcl::IterativeClosestPoint of performLoopClosure, host clouds in, result out
+int lc_icp_device(AlegoHandle *h, const float *src_host, int n_src, const float *tgt_host, int n_tgt, double max_corr_dist,
+                  int max_iterations, double transformation_epsilon, double fitness_epsilon, AlegoIcpResult *out, double *trace_host);

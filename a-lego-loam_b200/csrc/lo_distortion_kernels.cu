@@ -7,7 +7,8 @@
 // point i is F(max_{j<=i} cur_time_j), F(t) = first live entry with t < imu_time_ — and cur_time is a monotone function of
 // the point's column index, so the pointer is a PREFIX MAXIMUM of the column indices followed by a binary search.  The
 // `return` of the unsynchronised case (:596-600) leaves the points before it adjusted and the rest untouched: the first
-// such point is a min-reduction.  Everything else is per point.
+// such point is a min-reduction.  That walk is one CTA per sequence (lo_adjust_walk, integer work); everything else is per
+// point and runs over the whole GPU (lo_adjust_apply).
 //
 // Arithmetic follows the reference: times, ratios and the interpolated roll / pitch / yaw / shift / velocity in double,
 // stored into Eigen float vectors; rotation = (AngleAxisf(yaw,Z) * AngleAxisf(pitch,Y) * AngleAxisf(roll,X)) through float
@@ -91,20 +92,18 @@ __device__ __forceinline__ double point_rel_time(int col, int start_ori, int ori
 }
 
 __global__ void __launch_bounds__(DIST_THREADS)
-lo_adjust_distortion_kernel(float4 *__restrict__ seg_cloud, const int *__restrict__ seg_col, const int *__restrict__ Mv,
-                            const float *__restrict__ orient, int RC, int C, double scan_period, const double *__restrict__ queues,
-                            int len, const int *__restrict__ ptr_last, int *__restrict__ ptr_last_iter,
-                            const double *__restrict__ scan_time, int *__restrict__ n_done, int *__restrict__ front_of) {
+lo_adjust_walk_kernel(const int *__restrict__ seg_col, const int *__restrict__ Mv, const float *__restrict__ orient, int RC, int C,
+                      double scan_period, const double *__restrict__ queues, int len, const int *__restrict__ ptr_last,
+                      int *__restrict__ ptr_last_iter, const double *__restrict__ scan_time, int *__restrict__ n_done,
+                      int *__restrict__ front_of, float *__restrict__ start_pose) {
   const int b = blockIdx.x;
   const int M = Mv[b];
   const double *q = queues + (size_t)b * 10 * len;
-  float4 *cloud = seg_cloud + (size_t)b * RC;
   const int *col = seg_col + (size_t)b * RC;
   int *front = front_of + (size_t)b * RC;
   __shared__ double s_time[DIST_MAX_IMU];
   __shared__ int s_warp[32];
   __shared__ int s_carry, s_stop;
-  __shared__ float s_rsi[9], s_shift0[3], s_velo0[3];
 
   const int last = ptr_last[b], iter0 = ptr_last_iter[b];
   if (last <= 0 || M <= 0) {  // :583: nothing is touched before the second IMU message
@@ -171,18 +170,42 @@ lo_adjust_distortion_kernel(float4 *__restrict__ seg_cloud, const int *__restric
     float rc[9], inv[9];
     rpy_matrix(s0.rpy, rc);
     inverse3(rc, inv);
-    for (int k = 0; k < 9; ++k) s_rsi[k] = inv[k];
-    for (int k = 0; k < 3; ++k) { s_shift0[k] = s0.shift[k]; s_velo0[k] = s0.velo[k]; }
+    float *o = start_pose + (size_t)b * 16;
+    for (int k = 0; k < 9; ++k) o[k] = inv[k];
+    for (int k = 0; k < 3; ++k) { o[9 + k] = s0.shift[k]; o[12 + k] = s0.velo[k]; }
     n_done[b] = S;
     ptr_last_iter[b] = front[S - 1];  // :656
   }
-  __syncthreads();
+}
 
-  // ---- pass 2: every other point before the stop (:640-655) ---------------------------------------------------------
-  for (int i = 1 + threadIdx.x; i < S; i += DIST_THREADS) {
+// ---- every other point before the stop (:640-655), the whole GPU over all sequences ----------------------------------------
+__global__ void __launch_bounds__(256)
+lo_adjust_apply_kernel(float4 *__restrict__ seg_cloud, const int *__restrict__ seg_col, const float *__restrict__ orient, int RC, int C,
+                       double scan_period, const double *__restrict__ queues, int len, const double *__restrict__ scan_time,
+                       const int *__restrict__ n_done, const int *__restrict__ front_of, const float *__restrict__ start_pose) {
+  const int b = blockIdx.y;
+  const int S = n_done[b];
+  if (S <= 1) return;
+  const double *q = queues + (size_t)b * 10 * len;
+  float4 *cloud = seg_cloud + (size_t)b * RC;
+  const int *col = seg_col + (size_t)b * RC;
+  const int *front = front_of + (size_t)b * RC;
+  __shared__ float s_rsi[9], s_shift0[3], s_velo0[3];
+  if (threadIdx.x < 9) s_rsi[threadIdx.x] = start_pose[(size_t)b * 16 + threadIdx.x];
+  else if (threadIdx.x < 12) s_shift0[threadIdx.x - 9] = start_pose[(size_t)b * 16 + threadIdx.x];
+  else if (threadIdx.x < 15) s_velo0[threadIdx.x - 12] = start_pose[(size_t)b * 16 + threadIdx.x];
+  __syncthreads();
+  int start_ori = (int)(((double)orient[b * 4 + 0] + 2 * 3.14159265358979323846) / C);
+  int end_ori = (int)(((double)orient[b * 4 + 1] + 2 * 3.14159265358979323846) / C);
+  if (start_ori >= C) start_ori -= C;
+  if (end_ori >= C) end_ori -= C;
+  int ori_diff = end_ori - start_ori;
+  if (ori_diff <= 0) ori_diff = C;
+  const double t0 = scan_time[b];
+  for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
     const double rel_time = point_rel_time(col[i], start_ori, ori_diff, scan_period);
     ImuSample s;
-    imu_sample(q, s_time, len, front[i], t0 + rel_time, s);
+    imu_sample(q, q, len, front[i], t0 + rel_time, s);
     float rc[9];
     rpy_matrix(s.rpy, rc);
     const float relf = (float)rel_time;  // Eigen promotes the double scalar to the vector's float
@@ -203,13 +226,17 @@ lo_adjust_distortion_kernel(float4 *__restrict__ seg_cloud, const int *__restric
 }  // namespace
 
 int lo_adjust_distortion_device(AlegoHandle *h, const double *queues_dev, int len, const int *ptr_last_dev, int *ptr_last_iter_dev,
-                                const double *scan_time_dev, double scan_period, int *n_done_dev) {
+                                const double *scan_time_dev, double scan_period, int *n_done_dev, float *start_pose_dev) {
   if (len < 1 || len > DIST_MAX_IMU) { h->err = "alego_lo_adjust_distortion: queue length must be 1..2048"; return ALEGO_BAD_ARG; }
-  { LAUNCH(h, "lo_adjust_distortion");
-    // sort_idx is free between ImageProjection and lo_curv_occl (which rewrites it): pointer position of every point
-    lo_adjust_distortion_kernel<<<h->B, DIST_THREADS, 0, h->stream>>>(h->seg_cloud, h->seg_col, h->M, h->orient, h->RC, h->C, scan_period,
-                                                                      queues_dev, len, ptr_last_dev, ptr_last_iter_dev, scan_time_dev,
-                                                                      n_done_dev, h->sort_idx); }
+  // sort_idx is free between ImageProjection and lo_curv_occl (which rewrites it): pointer position of every point
+  { LAUNCH(h, "lo_adjust_walk");
+    lo_adjust_walk_kernel<<<h->B, DIST_THREADS, 0, h->stream>>>(h->seg_col, h->M, h->orient, h->RC, h->C, scan_period, queues_dev, len,
+                                                                ptr_last_dev, ptr_last_iter_dev, scan_time_dev, n_done_dev, h->sort_idx,
+                                                                start_pose_dev); }
+  { LAUNCH(h, "lo_adjust_apply");
+    lo_adjust_apply_kernel<<<dim3(min(div_up(h->RC, 256), 96), h->B), 256, 0, h->stream>>>(h->seg_cloud, h->seg_col, h->orient, h->RC, h->C,
+                                                                                        scan_period, queues_dev, len, scan_time_dev,
+                                                                                        n_done_dev, h->sort_idx, start_pose_dev); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

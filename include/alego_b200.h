@@ -195,6 +195,26 @@ int alego_lm_assemble_map(AlegoHandle *h, int seq, int n_keyframes, const float 
                           const float *const *surf_xyzi, const int32_t *n_surf, const float *const *outlier_xyzi,
                           const int32_t *n_outlier, const float *poses6 /*[n_keyframes][6]*/);
 int alego_lm_get_map(AlegoHandle *h, int seq, float *corner_xyzi, int32_t *n_corner, float *surf_xyzi, int32_t *n_surf);
+/* ---- LaserMapping, loop-closure ICP: the pcl::IterativeClosestPoint<PointT, PointT> object of
+ *      LaserMapping::performLoopClosure (src/laserMapping.cpp:667-688) — point-to-point, SVD (Umeyama) estimation,
+ *      DefaultConvergenceCriteria.  Loop detection, the keyframe store and the iSAM2 update stay with the caller. -------- */
+typedef struct AlegoIcpResult {
+  float final_transformation[16]; /* icp.getFinalTransformation(), row-major 4x4 (correction_frame, :688) */
+  double fitness_score;           /* icp.getFitnessScore() (:687): mean squared 1-NN distance of the aligned source */
+  int32_t has_converged;          /* icp.hasConverged() (:686) */
+  int32_t iterations;             /* nr_iterations_ */
+  int32_t convergence_state;      /* 0 not converged, 1 iterations, 2 transform, 3 abs MSE, 4 rel MSE, 5 no correspondences */
+  int32_t n_correspondences;      /* of the last iteration */
+} AlegoIcpResult;
+/* source = latest_keyframe_, target = near_history_keyframes_ (host memory, xyzi, finite coordinates), both already in the
+ * map frame (detectLoopClosure, :764-822).  The reference's settings: max_correspondence_distance 100, max_iterations 100,
+ * transformation_epsilon 1e-6, euclidean_fitness_epsilon 1e-6 (:668-671); align() runs from the identity guess (:684).
+ * trace (may be NULL): [max_iterations][14] doubles per executed iteration — correspondences, their mean squared distance,
+ * the incremental rotation (9, row-major) and translation (3).  Returns ALEGO_FEW_FEATURES for an empty cloud. */
+int alego_lc_icp(AlegoHandle *h, const float *source_xyzi, int32_t n_source, const float *target_xyzi, int32_t n_target,
+                 double max_correspondence_distance, int32_t max_iterations, double transformation_epsilon,
+                 double euclidean_fitness_epsilon, AlegoIcpResult *out, double *trace);
+
 /* Stand-alone inputs for sequence `seq` (the /corner_last, /surf_last, /outlier clouds of
  * laserMapping.cpp:133-153) and the odometry prediction odom2laser (:154-164). When not called, the
  * clouds produced on the device by the LO stage of the same handle are used. */

@@ -1586,6 +1586,173 @@ int oracle_adjust_distortion(float *xyzi, int n, const int *col, float start_ori
   return visited;
 }
 
+// ---- N4: loop-closure ICP, LaserMapping::performLoopClosure (src/laserMapping.cpp:652-711) -------------------------------
+// pcl::IterativeClosestPoint<PointXYZI, PointXYZI> with setMaxCorrespondenceDistance(100), setMaximumIterations(100),
+// setTransformationEpsilon(1e-6), setEuclideanFitnessEpsilon(1e-6), setRANSACIterations(0) (no rejector is installed, so the
+// last one has no effect), align() with the identity guess (the computed initial_guess is never passed, :684), then
+// hasConverged(), getFitnessScore(), getFinalTransformation() (:686-688).  PCL is not in the container (unpinned; restated
+// from PCL 1.8 registration/impl/icp.hpp, correspondence_estimation.hpp, transformation_estimation_svd.hpp,
+// default_convergence_criteria.hpp and Eigen 3.3 Geometry/Umeyama.h):
+//   loop: correspondences = 1-NN of every (current) source point in the target, kept when d^2 <= max_dist^2; fewer than 3 ->
+//   not converged, stop; transformation_ = umeyama(src, tgt, no scaling) in float; the source cloud is transformed in place
+//   (float, x' = m00 x + m01 y + m02 z + m03); final_transformation_ = transformation_ * final_transformation_; ++iterations;
+//   DefaultConvergenceCriteria: (1) iterations >= max -> converged (failure_after_max_iter_ = false); (2) cos_angle =
+//   0.5 (trace R - 1) >= 1 - transformation_epsilon and |t|^2 <= transformation_epsilon -> converged
+//   (max_iterations_similar_transforms_ = 0); (3) mse = mean of the correspondence distances (squared, float, summed in
+//   double); |mse - prev| < 1e-12 -> converged; |mse - prev| / prev < euclidean_fitness_epsilon -> converged; prev = mse.
+//   getFitnessScore(): mean squared 1-NN distance of the ORIGINAL source transformed by final_transformation_.
+// exact_sums = 0: umeyama's reductions are accumulated in float, sequentially (the literal reading; Eigen's real order inside
+// its GEMM kernel is not knowable here).  exact_sums = 1: the same quantities accumulated in double and rounded to float where
+// Eigen holds floats — the variant the device reproduces (like stable_voxel for VoxelGrid); tests compare both ways.
+// trace: per iteration 14 doubles — correspondences, mse, incremental R (9, row-major), t (3).
+namespace {
+void svd_rotation(const float sigma[9], float R[9]) {  // U * diag(1, 1, det(U) det(V)) * V^T of sigma = U S V^T
+  double A[9], AtA[9], w[3], V[9];
+  for (int k = 0; k < 9; ++k) A[k] = sigma[k];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) AtA[i * 3 + j] = A[0 * 3 + i] * A[0 * 3 + j] + A[1 * 3 + i] * A[1 * 3 + j] + A[2 * 3 + i] * A[2 * 3 + j];
+  eig3_sym(AtA, w, V);  // ascending: column 2 = largest singular value
+  double v[3][3], u[3][3];  // [k] = k-th singular vector, descending
+  for (int k = 0; k < 3; ++k)
+    for (int r = 0; r < 3; ++r) v[k][r] = V[r * 3 + (2 - k)];
+  for (int k = 0; k < 2; ++k) {
+    double n2 = 0;
+    for (int r = 0; r < 3; ++r) { u[k][r] = A[r * 3] * v[k][0] + A[r * 3 + 1] * v[k][1] + A[r * 3 + 2] * v[k][2]; n2 += u[k][r] * u[k][r]; }
+    const double inv = n2 > 0 ? 1.0 / std::sqrt(n2) : 0.0;
+    for (int r = 0; r < 3; ++r) u[k][r] *= inv;
+  }
+  {  // u1 re-orthogonalised against u0 (ill-conditioned sigma), u2 = u0 x u1: det(U) = +1
+    double d = u[0][0] * u[1][0] + u[0][1] * u[1][1] + u[0][2] * u[1][2], n2 = 0;
+    for (int r = 0; r < 3; ++r) { u[1][r] -= d * u[0][r]; n2 += u[1][r] * u[1][r]; }
+    const double inv = n2 > 0 ? 1.0 / std::sqrt(n2) : 0.0;
+    for (int r = 0; r < 3; ++r) u[1][r] *= inv;
+  }
+  u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
+  u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+  u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+  const double detV = v[0][0] * (v[1][1] * v[2][2] - v[1][2] * v[2][1]) - v[0][1] * (v[1][0] * v[2][2] - v[1][2] * v[2][0]) +
+                      v[0][2] * (v[1][0] * v[2][1] - v[1][1] * v[2][0]);
+  const double s2 = detV < 0 ? -1.0 : 1.0;  // det(U) = +1 by construction
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = (float)(u[0][r] * v[0][c] + u[1][r] * v[1][c] + s2 * u[2][r] * v[2][c]);
+}
+}  // namespace
+
+int oracle_icp(const float *src_xyzi, int n_src, const float *tgt_xyzi, int n_tgt, double max_corr_dist, int max_iterations,
+               double transformation_epsilon, double fitness_epsilon, int exact_sums, float *T16, double *fitness, int *converged,
+               int *state_out, double *trace) {
+  vector<P4> src(reinterpret_cast<const P4 *>(src_xyzi), reinterpret_cast<const P4 *>(src_xyzi) + n_src);
+  const vector<P4> src0 = src;
+  vector<P4> tgt(reinterpret_cast<const P4 *>(tgt_xyzi), reinterpret_cast<const P4 *>(tgt_xyzi) + n_tgt);
+  KdTree tree;
+  tree.build(tgt);
+  float Tfin[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const double max_d2 = max_corr_dist * max_corr_dist;
+  double prev_mse = std::numeric_limits<double>::max();
+  int iterations = 0, state = 0;  // 0 not converged, 1 iterations, 2 transform, 3 abs mse, 4 rel mse, 5 no correspondences
+  vector<int> cq, cm;
+  vector<float> cd;
+  while (state == 0) {
+    cq.clear(); cm.clear(); cd.clear();
+    for (int i = 0; i < n_src; ++i) {
+      int idx; float d;
+      if (tree.knn(src[i], 1, &idx, &d) < 1) continue;
+      if ((double)d > max_d2) continue;
+      cq.push_back(i); cm.push_back(idx); cd.push_back(d);
+    }
+    const int n = (int)cq.size();
+    if (n < 3) { state = 5; break; }
+    // Eigen::umeyama(src, dst, false), float
+    const float one_over_n = 1.f / (float)n;
+    float sm[3], dm[3], sigma[9];
+    if (!exact_sums) {
+      float ss[3] = {0, 0, 0}, ds[3] = {0, 0, 0};
+      for (int k = 0; k < n; ++k) {
+        const P4 &a = src[cq[k]], &b = tgt[cm[k]];
+        ss[0] += a.x; ss[1] += a.y; ss[2] += a.z;
+        ds[0] += b.x; ds[1] += b.y; ds[2] += b.z;
+      }
+      for (int c = 0; c < 3; ++c) { sm[c] = ss[c] * one_over_n; dm[c] = ds[c] * one_over_n; }
+      float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < n; ++k) {
+        const P4 &a = src[cq[k]], &b = tgt[cm[k]];
+        const float sd[3] = {a.x - sm[0], a.y - sm[1], a.z - sm[2]}, dd[3] = {b.x - dm[0], b.y - dm[1], b.z - dm[2]};
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) acc[r * 3 + c] += dd[r] * sd[c];
+      }
+      for (int k = 0; k < 9; ++k) sigma[k] = one_over_n * acc[k];
+    } else {
+      double ss[3] = {0, 0, 0}, ds[3] = {0, 0, 0}, cr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < n; ++k) {
+        const P4 &a = src[cq[k]], &b = tgt[cm[k]];
+        const double s3[3] = {a.x, a.y, a.z}, d3[3] = {b.x, b.y, b.z};
+        for (int r = 0; r < 3; ++r) {
+          ss[r] += s3[r]; ds[r] += d3[r];
+          for (int c = 0; c < 3; ++c) cr[r * 3 + c] += d3[r] * s3[c];
+        }
+      }
+      for (int c = 0; c < 3; ++c) { sm[c] = (float)ss[c] * one_over_n; dm[c] = (float)ds[c] * one_over_n; }
+      // sum (d - dm)(s - sm)^T with the float means, exactly
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          sigma[r * 3 + c] = one_over_n * (float)(cr[r * 3 + c] - (double)dm[r] * ss[c] - ds[r] * (double)sm[c] + (double)n * (double)dm[r] * (double)sm[c]);
+    }
+    float R[9], T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    svd_rotation(sigma, R);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r * 3 + c];
+      T[r * 4 + 3] = dm[r] - ((R[r * 3] * sm[0] + R[r * 3 + 1] * sm[1]) + R[r * 3 + 2] * sm[2]);
+    }
+    // transformCloud (in place) and final_transformation_ = transformation_ * final_transformation_
+    for (int i = 0; i < n_src; ++i) {
+      const P4 p = src[i];
+      src[i].x = ((T[0] * p.x + T[1] * p.y) + T[2] * p.z) + T[3];
+      src[i].y = ((T[4] * p.x + T[5] * p.y) + T[6] * p.z) + T[7];
+      src[i].z = ((T[8] * p.x + T[9] * p.y) + T[10] * p.z) + T[11];
+    }
+    float Tn[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) Tn[r * 4 + c] = ((T[r * 4] * Tfin[c] + T[r * 4 + 1] * Tfin[4 + c]) + T[r * 4 + 2] * Tfin[8 + c]) + T[r * 4 + 3] * Tfin[12 + c];
+    std::memcpy(Tfin, Tn, sizeof Tn);
+    double mse = 0;
+    for (int k = 0; k < n; ++k) mse += cd[k];
+    mse /= (double)n;
+    if (trace) {
+      double *tr = trace + (size_t)iterations * 14;
+      tr[0] = n; tr[1] = mse;
+      for (int k = 0; k < 9; ++k) tr[2 + k] = R[k];
+      for (int k = 0; k < 3; ++k) tr[11 + k] = T[k * 4 + 3];
+    }
+    ++iterations;
+    // DefaultConvergenceCriteria::hasConverged
+    if (iterations >= max_iterations) { state = 1; break; }
+    const double cos_angle = 0.5 * ((double)T[0] + (double)T[5] + (double)T[10] - 1);
+    const double translation_sqr = (double)T[3] * T[3] + (double)T[7] * T[7] + (double)T[11] * T[11];
+    if (cos_angle >= 1.0 - transformation_epsilon && translation_sqr <= transformation_epsilon) { state = 2; break; }
+    if (std::fabs(mse - prev_mse) < 1e-12) { state = 3; break; }
+    if (std::fabs(mse - prev_mse) / prev_mse < fitness_epsilon) { state = 4; break; }
+    prev_mse = mse;
+  }
+  // getFitnessScore (max_range = DBL_MAX)
+  double fs = 0;
+  int nr = 0;
+  for (int i = 0; i < n_src; ++i) {
+    const P4 p = src0[i];
+    P4 q = p;
+    q.x = ((Tfin[0] * p.x + Tfin[1] * p.y) + Tfin[2] * p.z) + Tfin[3];
+    q.y = ((Tfin[4] * p.x + Tfin[5] * p.y) + Tfin[6] * p.z) + Tfin[7];
+    q.z = ((Tfin[8] * p.x + Tfin[9] * p.y) + Tfin[10] * p.z) + Tfin[11];
+    int idx; float d;
+    if (tree.knn(q, 1, &idx, &d) < 1) continue;
+    fs += d; ++nr;
+  }
+  if (fitness) *fitness = nr > 0 ? fs / nr : std::numeric_limits<double>::max();
+  if (converged) *converged = (state >= 1 && state <= 4) ? 1 : 0;
+  if (state_out) *state_out = state;
+  if (T16) std::memcpy(T16, Tfin, sizeof Tfin);
+  return iterations;
+}
+
 // k-NN of nq queries against n points; idx [nq][k], dist [nq][k]; brute!=0 uses the O(n) scan
 int oracle_knn(const float *pts, int n, const float *q, int nq, int k, int brute, int32_t *idx, float *dist) {
   if (k < 1 || k > 8) return ALEGO_BAD_ARG;

@@ -57,6 +57,8 @@ def lib():
                                              C.POINTER(C.c_int), C.c_void_p]
         L.oracle_adjust_distortion.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_double, C.c_double,
                                                C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_icp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
         _lib = L
     return _lib
 
@@ -210,6 +212,23 @@ def adjust_distortion(cloud, col, start_orientation, end_orientation, horizon_sc
     n = lib().oracle_adjust_distortion(_p(out), len(out), _p(col), float(start_orientation), float(end_orientation), int(horizon_scan),
                                        float(scan_period), float(scan_time), _p(queue), queue.shape[1], int(ptr_last), C.byref(it))
     return out, n, it.value
+
+
+ICP_STATES = ("not converged", "iterations", "transform", "abs mse", "rel mse", "no correspondences")
+
+
+def icp(src, tgt, max_corr_dist=100.0, max_iterations=100, transformation_epsilon=1e-6, fitness_epsilon=1e-6, exact_sums=True):
+    """pcl::IterativeClosestPoint as LaserMapping::performLoopClosure configures it (laserMapping.cpp:667-688).  Returns a dict:
+    T (4x4 float32 final_transformation_), fitness (getFitnessScore), converged, state, iterations, trace [iterations][14]."""
+    src = np.ascontiguousarray(src, np.float32).reshape(-1, 4)
+    tgt = np.ascontiguousarray(tgt, np.float32).reshape(-1, 4)
+    T = np.zeros(16, np.float32)
+    trace = np.zeros((max(max_iterations, 1), 14))
+    fit, conv, st = C.c_double(0), C.c_int(0), C.c_int(0)
+    it = lib().oracle_icp(_p(src), len(src), _p(tgt), len(tgt), max_corr_dist, max_iterations, transformation_epsilon, fitness_epsilon,
+                          int(exact_sums), _p(T), C.byref(fit), C.byref(conv), C.byref(st), _p(trace))
+    return {"T": T.reshape(4, 4), "fitness": fit.value, "converged": bool(conv.value), "state": st.value, "iterations": it,
+            "trace": trace[:it]}
 
 
 def knn(pts, q, k, brute=False):

@@ -1,4 +1,5 @@
-"""SURVEY §8f "next" rows beyond N1: N2 LaserOdometry::adjustDistortion (laserOdometry.cpp:557-657).
+"""SURVEY §8f "next" rows beyond N1: N2 LaserOdometry::adjustDistortion (laserOdometry.cpp:557-657) and N4 the loop-closure ICP of
+LaserMapping::performLoopClosure (laserMapping.cpp:652-711); the N4 part is at the end of the file.
 
 CPU part: the oracle's literal restatement against an independent float64 numpy evaluation of the same formulas and against
 properties of the function (no IMU data -> untouched, unsynchronised stamps -> partial update, constant IMU state -> identity).
@@ -284,4 +285,179 @@ def test_gpu_adjust_distortion(alego, ob, preset):
     g.ip_process(buf, n)
     with pytest.raises(alego.AlegoError):
         g.lo_adjust_distortion(t0, [bad] + queues[1:], ptr_last, ptr_iter)
+    g.close()
+
+
+# ========================================================================================================================
+# N4: loop-closure ICP (pcl::IterativeClosestPoint as configured at laserMapping.cpp:667-671)
+#
+# Tolerances: ICP stops on thresholds (|t|^2 <= 1e-6, relative MSE change < 1e-6), so two evaluations that differ in the last
+# float bits may stop one iteration apart; the last steps are <= 1e-3 m by construction.  Hence: same iteration count ->
+# transforms within 2e-5 (float rounding of a 4x4 chain); one iteration apart -> within 2e-3 m / 2e-4.  The oracle's literal
+# float reductions (exact_sums=False, Eigen::umeyama's float sums over ~10^4 points of magnitude 10..50 m) carry ~1e-4 m of
+# summation noise themselves, which bounds what any comparison against the real PCL could show.
+# ========================================================================================================================
+ICP_T_TIGHT, ICP_T_LOOSE = 2e-5, 2e-3
+ICP_T_FLOAT_SUMS = 3e-4  # against the literal float reductions
+
+
+def icp_scene(rng, n, noise=0.01, ext=30.0):
+    """ground + two walls + a few poles within +-ext metres"""
+    a = rng.uniform(-ext, ext, (n, 2))
+    g = np.c_[a, rng.normal(-1.7, noise, n)]
+    w1 = np.c_[rng.uniform(-ext, ext, n), 0.4 * ext + rng.normal(0, noise, n), rng.uniform(-1.7, 4, n)]
+    w2 = np.c_[-0.5 * ext + rng.normal(0, noise, n), rng.uniform(-ext, ext, n), rng.uniform(-1.7, 4, n)]
+    poles = []
+    for _ in range(6):
+        c = rng.uniform(-0.8 * ext, 0.8 * ext, 2)
+        poles.append(np.c_[c[0] + rng.normal(0, 0.03, n // 20), c[1] + rng.normal(0, 0.03, n // 20), rng.uniform(-1.7, 3, n // 20)])
+    p = np.concatenate([g, w1, w2] + poles)
+    return np.c_[p, np.zeros(len(p))].astype(np.float32)
+
+
+def misalign(cloud, ypr, t):
+    """source such that the aligning transform is (R(ypr), t): src = R^T (p - t)"""
+    from scipy.spatial.transform import Rotation
+    R = Rotation.from_euler("ZYX", ypr).as_matrix()
+    out = cloud.copy()
+    out[:, :3] = ((cloud[:, :3].astype(np.float64) - t) @ R).astype(np.float32)
+    return out, R
+
+
+def scipy_icp(src, tgt, max_corr_dist=100.0, max_iterations=100, eps_t=1e-6, eps_f=1e-6):
+    """Independent float64 ICP with PCL's control flow: cKDTree 1-NN, Kabsch through numpy's SVD, the same stop rules."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(tgt[:, :3].astype(np.float64))
+    cur = src[:, :3].astype(np.float64).copy()
+    Tf = np.eye(4)
+    prev, it, state = np.finfo(np.float64).max, 0, 0
+    while state == 0:
+        d, j = tree.query(cur)
+        keep = d * d <= max_corr_dist ** 2
+        if keep.sum() < 3:
+            state = 5
+            break
+        s, t = cur[keep], tgt[j[keep], :3].astype(np.float64)
+        sm, tm = s.mean(0), t.mean(0)
+        U, _, Vt = np.linalg.svd((t - tm).T @ (s - sm) / len(s))
+        S = np.diag([1, 1, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+        R = U @ S @ Vt
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, tm - R @ sm
+        cur = cur @ R.T + T[:3, 3]
+        Tf = T @ Tf
+        mse = float((d[keep] ** 2).mean())
+        it += 1
+        if it >= max_iterations:
+            state = 1
+        elif 0.5 * (np.trace(R) - 1) >= 1 - eps_t and (T[:3, 3] ** 2).sum() <= eps_t:
+            state = 2
+        elif abs(mse - prev) < 1e-12:
+            state = 3
+        elif abs(mse - prev) / prev < eps_f:
+            state = 4
+        else:
+            prev = mse
+    al = src[:, :3].astype(np.float64) @ Tf[:3, :3].T + Tf[:3, 3]
+    d, _ = tree.query(al)
+    return {"T": Tf, "iterations": it, "state": state, "fitness": float((d * d).mean())}
+
+
+def assert_icp_close(a, b, tag="", max_iter_diff=1, base_tol=None):
+    """two ICP runs of the same problem: equal up to the stop-threshold effect described above.  max_iter_diff > 1 is for the
+    comparison with the float-summation variant: while point-to-point ICP creeps along a surface the relative MSE change hovers
+    around the 1e-6 threshold for several iterations, and 1e-4 m of summation noise decides which of them stops the loop."""
+    d_it = abs(a["iterations"] - b["iterations"])
+    assert d_it <= max_iter_diff, (tag, a["iterations"], b["iterations"])
+    tol = (ICP_T_TIGHT if base_tol is None else base_tol) + ICP_T_LOOSE * d_it
+    assert np.allclose(a["T"][:3, 3], b["T"][:3, 3], rtol=0, atol=tol), (tag, a["T"], b["T"])
+    assert np.allclose(a["T"][:3, :3], b["T"][:3, :3], rtol=0, atol=tol / 10 + 1e-6), (tag, a["T"], b["T"])
+    assert abs(a["fitness"] - b["fitness"]) <= 1e-3 * max(b["fitness"], 1e-6) + tol, (tag, a["fitness"], b["fitness"])
+
+
+def test_oracle_icp_matches_scipy_and_recovers_motion(ob):
+    rng = np.random.default_rng(4)
+    tgt = icp_scene(rng, 3000)
+    src, R = misalign(tgt[::3], [0.03, 0.01, -0.008], np.array([0.4, -0.25, 0.08]))  # the same surface samples, moved
+    want = scipy_icp(src, tgt)
+    for exact in (True, False):
+        got = ob.icp(src, tgt, exact_sums=exact)
+        assert got["converged"] and got["state"] in (2, 4) and got["iterations"] == len(got["trace"])
+        assert abs(got["iterations"] - want["iterations"]) <= 1
+        assert np.allclose(got["T"], want["T"], rtol=0, atol=ICP_T_LOOSE), (got["T"], want["T"])
+        assert abs(got["fitness"] - want["fitness"]) < 1e-3 * want["fitness"] + 1e-4
+        # the planted motion is recovered (point-to-point ICP on identical samples has the exact answer as its fixed point)
+        assert np.allclose(got["T"][:3, 3], [0.4, -0.25, 0.08], atol=0.02) and np.allclose(got["T"][:3, :3], R, atol=2e-3)
+    a, b = ob.icp(src, tgt, exact_sums=True), ob.icp(src, tgt, exact_sums=False)
+    assert_icp_close(a, b, "exact vs float sums", max_iter_diff=10, base_tol=ICP_T_FLOAT_SUMS)
+
+
+def test_oracle_icp_stop_rules(ob):
+    rng = np.random.default_rng(6)
+    tgt = icp_scene(rng, 1500)
+    # identical clouds: every correspondence has distance 0 -> identity, stops on the transformation threshold at once
+    r = ob.icp(tgt, tgt)
+    assert r["converged"] and r["state"] == 2 and r["iterations"] == 1 and r["fitness"] == 0.0
+    assert np.allclose(r["T"], np.eye(4), atol=1e-6)
+    src, _ = misalign(tgt, [0.02, 0.0, 0.0], np.array([0.3, 0.1, 0.0]))
+    # maximum iterations reached counts as converged (failure_after_max_iter_ = false)
+    r = ob.icp(src, tgt, max_iterations=3)
+    assert r["converged"] and r["state"] == 1 and r["iterations"] == 3
+    # no correspondence inside the distance gate: "Not enough correspondences found", not converged, identity
+    far = tgt.copy()
+    far[:, 0] += 500.0
+    r = ob.icp(far, tgt, max_corr_dist=1.0)
+    assert not r["converged"] and r["state"] == 5 and r["iterations"] == 0 and np.array_equal(r["T"], np.eye(4, dtype=np.float32))
+    # the gate is on the squared distance, inclusive (distance > max_dist_sqr is dropped, correspondence_estimation.hpp)
+    r2 = ob.icp(src, tgt, max_corr_dist=0.5)
+    assert r2["trace"][0, 0] < len(src)
+
+
+@pytest.mark.gpu
+def test_gpu_icp_matches_oracle(alego, ob):
+    P = alego.default_params(0)
+    g = alego.Alego(P, n_seq=2)  # the ICP buffers do not depend on the batch size of the handle
+    rng = np.random.default_rng(8)
+    # 1) synthetic planes + poles, moderate misalignment; a dozen source points floating 8-15 m above everything (exhaustive pass)
+    tgt = icp_scene(rng, 6000)
+    src, _ = misalign(icp_scene(rng, 2500), [0.025, -0.01, 0.006], np.array([0.35, 0.3, -0.05]))
+    src[:12, 2] += rng.uniform(8, 15, 12).astype(np.float32)  # neighbours farther than two 2 m cell rings
+    want = ob.icp(src, tgt, exact_sums=True)
+    got = g.lc_icp(src, tgt)
+    assert got["converged"] == want["converged"] and got["state"] == want["state"]
+    assert_icp_close(got, want, "planes")
+    k = min(got["iterations"], want["iterations"]) - 1
+    # iteration by iteration: correspondence counts equal, mean squared distance and increments equal to float rounding
+    assert np.array_equal(got["trace"][:k, 0], want["trace"][:k, 0])
+    assert np.allclose(got["trace"][:k, 1], want["trace"][:k, 1], rtol=1e-5, atol=1e-9)
+    assert np.allclose(got["trace"][:k, 2:], want["trace"][:k, 2:], rtol=0, atol=ICP_T_TIGHT)
+    assert_icp_close(got, ob.icp(src, tgt, exact_sums=False), "planes vs float sums", max_iter_diff=10, base_tol=ICP_T_FLOAT_SUMS)
+    # 2) the world of the benchmark: local map (1 m voxels) as history cloud, a rendered sweep's features as latest keyframe
+    world = alego.SynthWorld(seed=5)
+    corner, surf = world.make_map(4000, 40000, seed=5, radius=50.0)
+    hist, _ = ob.voxel_grid(np.concatenate([corner, surf]), 1.0)
+    key = np.concatenate([corner[::3], surf[::7]]).copy()
+    key, _ = misalign(key, [-0.015, 0.004, 0.0], np.array([-0.2, 0.15, 0.03]))
+    want = ob.icp(key, hist, exact_sums=True)
+    got = g.lc_icp(key, hist)
+    assert got["state"] == want["state"] and want["converged"]
+    assert_icp_close(got, want, "world")
+    # 3) stop rules and gates through the C ABI
+    r = g.lc_icp(tgt, tgt)
+    assert r["converged"] and r["state"] == 2 and r["iterations"] == 1 and r["fitness"] < 1e-10 and np.allclose(r["T"], np.eye(4), atol=1e-6)
+    r = g.lc_icp(src, tgt, max_iterations=3)
+    assert r["converged"] and r["state"] == 1 and r["iterations"] == 3
+    far = tgt.copy()
+    far[:, 0] += 500.0
+    r = g.lc_icp(far, tgt, max_corr_dist=1.0)
+    assert not r["converged"] and r["state"] == 5 and r["iterations"] == 0 and np.array_equal(r["T"], np.eye(4, dtype=np.float32))
+    w2 = ob.icp(src, tgt, max_corr_dist=0.5)
+    r2 = g.lc_icp(src, tgt, max_corr_dist=0.5)
+    assert r2["trace"][0, 0] == w2["trace"][0, 0] and r2["state"] == w2["state"]
+    assert_icp_close(r2, w2, "gated")
+    # a larger cloud after a smaller one (buffers grow), then the small one again (capacity kept)
+    big_t = icp_scene(rng, 30000)
+    big_s, _ = misalign(icp_scene(rng, 9000), [0.01, 0.0, 0.0], np.array([0.1, -0.1, 0.0]))
+    assert_icp_close(g.lc_icp(big_s, big_t), ob.icp(big_s, big_t, exact_sums=True), "big")
+    assert_icp_close(g.lc_icp(src, tgt), ob.icp(src, tgt, exact_sums=True), "small again")
     g.close()
