@@ -603,7 +603,9 @@ int alego_lo_set_params(AlegoHandle *h, int seq, const double params[6]) {
 
 // ---------------------------------------------------------------------------------------------------
 static int realloc_keep(AlegoHandle *h, float4 **buf, int *cap, int need) {
-  if (need <= *cap) return ALEGO_OK;
+  // an EMPTY cloud still gets a buffer: the first mapped frames of a run have no keyframe yet, the map clouds are empty and
+  // scan2MapOptimization's guard skips the solve (laserMapping.cpp:196-199, :350-354) — that is a valid state, not "no map"
+  if (*buf && need <= *cap) return ALEGO_OK;
   ++h->graph_epoch;  // captured graphs hold the old pointer
   const int ncap = std::max(need, 1024);
   float4 *nb = nullptr;

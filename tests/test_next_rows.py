@@ -461,3 +461,50 @@ def test_gpu_icp_matches_oracle(alego, ob):
     assert_icp_close(g.lc_icp(big_s, big_t), ob.icp(big_s, big_t, exact_sums=True), "big")
     assert_icp_close(g.lc_icp(src, tgt), ob.icp(src, tgt, exact_sums=True), "small again")
     g.close()
+
+
+# ========================================================================================================================
+# bootstrap: the first mapped frames of a run (what the nodelet shell does when no map was loaded)
+# ========================================================================================================================
+@pytest.mark.gpu
+def test_gpu_bootstrap_from_empty_local_map(alego, ob):
+    """No keyframe yet: extractSurroundingKeyFrames leaves the map clouds empty (laserMapping.cpp:196-199), the guard of
+    scan2MapOptimization skips the solve (:350-354), the first keyframe is saved with the unchanged estimate (:491-545); from then
+    on the local map is assembled from the stored keyframes (:206-243, alego_lm_assemble_map) and the solves run.  Device against
+    the oracle driven through the same steps."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 6
+    w = alego.SynthWorld(seed=seed)
+    g = alego.Alego(P, n_seq=1)
+    o = ob.Oracle(P, lm_every=1, stable_voxel=True)
+    empty = np.zeros((0, 4), np.float32)
+    g.lm_set_map(0, empty, empty)
+    o.lm_set_map(empty, empty)
+    g.pipeline_config(lm_every=1)
+    kfs, poses6 = [], []
+    for t in range(5):
+        scan = w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=300 + t)
+        buf, n = g.pack_scans([scan])
+        poses = g.pipeline_step(buf, n)
+        o.pipeline_step(scan)
+        rep, orep = g.solve_report("lm", 0), o.report("lm")
+        assert rep["status"] == orep["status"] and rep["iterations"] == orep["iterations"], (t, rep, orep)
+        assert rep["n_corner"] == orep["n_corner"] and rep["n_surf"] == orep["n_surf"], (t, rep, orep)
+        if t == 0:
+            assert rep["status"] == alego.FEW_FEATURES and rep["iterations"] == 0 and np.all(poses[0, 3:9] == 0.0)
+        else:
+            assert rep["status"] == alego.OK and rep["iterations"] > 0
+        assert np.abs(poses[0, 3:9] - o.get("lm_params")).max() < 1e-4, t   # north_star pose tolerance
+        ds = g.lm_get_downsampled(0)
+        for a, name in zip(ds, ("lm_corner_ds", "lm_surf_ds", "lm_outlier_ds")):
+            assert np.array_equal(a, o.get(name)), (t, name)
+        kfs.append(ds)
+        poses6.append(np.asarray(o.get("lm_params"), np.float32))  # the same keyframe poses on both sides
+        ck, sk, ok_ = [k[0] for k in kfs], [k[1] for k in kfs], [k[2] for k in kfs]
+        g.lm_assemble_map(0, ck, sk, ok_, np.stack(poses6))
+        cm, sm, _ = ob.lm_assemble_map(ck, sk, ok_, np.stack(poses6), P.lm_corner_leaf, P.lm_surf_leaf, stable=True)
+        o.lm_set_map(cm, sm)
+        gc, gs = g.lm_get_map(0)
+        assert np.array_equal(gc, cm) and np.array_equal(gs, sm), t
+    assert abs(poses[0, 3] - alego.trajectory_pose(4, seed=seed)[0]) < 0.3  # sanity: it tracks the trajectory
+    g.close()
