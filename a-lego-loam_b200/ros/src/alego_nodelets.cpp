@@ -263,6 +263,8 @@ class LaserMapping : public nodelet::Nodelet {
     if (!ctx) return;
     core_.reset(new alego::LaserMapping(*ctx));
     if (core_->onInit() != ALEGO_OK) { NODELET_FATAL("LaserMapping::onInit failed"); return; }
+    // no keyframe yet: empty map clouds, the guard of scan2MapOptimization skips the solve until the first keyframe (:196-199, :350)
+    if (core_->setLocalMap(0, alego::PointCloud(), alego::PointCloud()) != ALEGO_OK) { NODELET_FATAL("LaserMapping: no local map"); return; }
     pub_odom_aft_mapped_ = nh_.advertise<nav_msgs::Odometry>("/odom_aft_mapped", 10);
     sub_laser_odom_ = nh_.subscribe<nav_msgs::Odometry>("/odom/lidar", 10, &LaserMapping::laserOdomHandler, this);
   }
@@ -280,10 +282,12 @@ class LaserMapping : public nodelet::Nodelet {
       if (rc != ALEGO_OK && rc != ALEGO_FEW_FEATURES) { NODELET_WARN("LaserMapping rc=%d", rc); return; }
       double params[6], t_m2l[3], r_m2l[9], t_m2o[3], r_m2o[9];
       if (core_->pose(0, params, t_m2l, r_m2l, t_m2o, r_m2o) != ALEGO_OK) return;
-      // saveKeyFramesAndFactor's cloud side (:491-545): a keyframe every 0.3 m, as the reference's distance gate does
+      // saveKeyFramesAndFactor's cloud side (:491-545): the first frame, then whenever the squared distance to the previous
+      // keyframe reaches min_keyframe_dist_ = 1.0 (:43, :501-508).  Without the pose graph the keyframe pose is the estimate itself.
       const double dx = t_m2l[0] - last_kf_[0], dy = t_m2l[1] - last_kf_[1], dz = t_m2l[2] - last_kf_[2];
-      if (core_->keyFrameCount(0) == 0 || std::sqrt(dx * dx + dy * dy + dz * dz) >= 0.3) {
-        const float pose6[6] = {(float)t_m2l[0], (float)t_m2l[1], (float)t_m2l[2], (float)params[3], (float)params[4], (float)params[5]};
+      if (core_->keyFrameCount(0) == 0 || dx * dx + dy * dy + dz * dz >= 1.0) {
+        float pose6[6];
+        for (int k = 0; k < 6; ++k) pose6[k] = (float)params[k];  // PointTypePose fields are float (utility.h:83-97)
         if (core_->saveKeyFrame(0, pose6) == ALEGO_OK)
           for (int k = 0; k < 3; ++k) last_kf_[k] = t_m2l[k];
       }

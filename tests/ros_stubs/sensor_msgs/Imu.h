@@ -1,0 +1,19 @@
+#pragma once
+#include <memory>
+#include <std_msgs/Header.h>
+namespace geometry_msgs {
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+struct Vector3 { double x = 0, y = 0, z = 0; };
+struct Point { double x = 0, y = 0, z = 0; };
+struct Pose { Point position; Quaternion orientation; };
+struct PoseWithCovariance { Pose pose; };
+}  // namespace geometry_msgs
+namespace sensor_msgs {
+struct Imu {
+  std_msgs::Header header;
+  geometry_msgs::Quaternion orientation;
+  geometry_msgs::Vector3 angular_velocity, linear_acceleration;
+};
+typedef std::shared_ptr<Imu> ImuPtr;
+typedef std::shared_ptr<const Imu> ImuConstPtr;
+}  // namespace sensor_msgs
