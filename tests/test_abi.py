@@ -53,3 +53,17 @@ def test_null_and_bad_arguments_do_not_crash(alego):
     assert L.alego_ip_run(None) == alego.BAD_ARG
     L.alego_destroy.argtypes = [ctypes.c_void_p]
     L.alego_destroy(None)
+    # the "next row" entry points refuse a null handle before touching CUDA
+    L.alego_lc_icp.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                               ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    res = alego.AlegoIcpResult()
+    assert L.alego_lc_icp(None, None, 0, None, 0, 100.0, 100, 1e-6, 1e-6, ctypes.byref(res), None) == alego.BAD_ARG
+    L.alego_lo_adjust_distortion.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    assert L.alego_lo_adjust_distortion(None, None, None, 0.2, None) == alego.BAD_ARG
+
+
+def test_next_row_struct_layouts(alego):
+    # AlegoImuQueue: 4 int32 + 10 pointers; AlegoIcpResult: 16 floats + double + 4 int32 (include/alego_b200.h)
+    assert ctypes.sizeof(alego.AlegoImuQueue) == 4 * 4 + 10 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(alego.AlegoIcpResult) == 16 * 4 + 8 + 4 * 4
+    assert alego.AlegoIcpResult.fitness_score.offset == 64 and alego.AlegoIcpResult.has_converged.offset == 72
