@@ -1638,6 +1638,9 @@ void svd_rotation(const float sigma[9], float R[9]) {  // U * diag(1, 1, det(U) 
 }
 }  // namespace
 
+// the rotation step alone (tests: against numpy's SVD, reflections and rank-deficient covariances included)
+int oracle_umeyama_rotation(const float *sigma9, float *R9) { svd_rotation(sigma9, R9); return ALEGO_OK; }
+
 int oracle_icp(const float *src_xyzi, int n_src, const float *tgt_xyzi, int n_tgt, double max_corr_dist, int max_iterations,
                double transformation_epsilon, double fitness_epsilon, int exact_sums, float *T16, double *fitness, int *converged,
                int *state_out, double *trace) {

@@ -57,6 +57,7 @@ def lib():
                                              C.POINTER(C.c_int), C.c_void_p]
         L.oracle_adjust_distortion.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_double, C.c_double,
                                                C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_umeyama_rotation.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_icp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
                                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
         _lib = L
@@ -212,6 +213,14 @@ def adjust_distortion(cloud, col, start_orientation, end_orientation, horizon_sc
     n = lib().oracle_adjust_distortion(_p(out), len(out), _p(col), float(start_orientation), float(end_orientation), int(horizon_scan),
                                        float(scan_period), float(scan_time), _p(queue), queue.shape[1], int(ptr_last), C.byref(it))
     return out, n, it.value
+
+
+def umeyama_rotation(sigma):
+    """R = U diag(1, 1, det(U) det(V)) V^T of the 3x3 covariance sigma = U S V^T (the rotation Eigen::umeyama returns)."""
+    sigma = np.ascontiguousarray(sigma, np.float32).reshape(9)
+    R = np.zeros(9, np.float32)
+    lib().oracle_umeyama_rotation(_p(sigma), _p(R))
+    return R.reshape(3, 3)
 
 
 ICP_STATES = ("not converged", "iterations", "transform", "abs mse", "rel mse", "no correspondences")

@@ -392,6 +392,39 @@ def test_oracle_icp_matches_scipy_and_recovers_motion(ob):
     assert_icp_close(a, b, "exact vs float sums", max_iter_diff=10, base_tol=ICP_T_FLOAT_SUMS)
 
 
+def test_umeyama_rotation_matches_numpy_svd(ob):
+    """The rotation step of the transformation estimation (the same routine text runs on the device, lc_icp_kernels.cu): against
+    numpy's SVD on random covariances, on covariances whose best orthogonal fit is a reflection (det(U) det(V) < 0 -> the smallest
+    singular direction is flipped, Umeyama eq. 39-43) and on rank-2 covariances (planar correspondences)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+
+    def ref(sig):
+        U, s, Vt = np.linalg.svd(sig.astype(np.float64))
+        S = np.diag([1.0, 1.0, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+        return U @ S @ Vt
+
+    for k in range(200):
+        Rtrue = Rotation.from_rotvec(rng.normal(0, 1.0, 3)).as_matrix()
+        pts = rng.normal(0, 1, (50, 3)) * rng.uniform(0.2, 5.0, 3)
+        if k % 4 == 1:
+            pts[:, 2] = 0.0                      # planar: rank-2 covariance
+        sig = (Rtrue @ pts.T) @ pts / len(pts)   # sum t s^T with t = R s
+        if k % 4 == 2:
+            sig = sig @ np.diag([1.0, 1.0, -1.0])  # mirrored source: the unconstrained optimum is a reflection
+        if k % 4 == 3:
+            sig = sig + rng.normal(0, 0.05, (3, 3))  # noisy correspondences
+        sig32 = sig.astype(np.float32)
+        got = ob.umeyama_rotation(sig32).astype(np.float64)
+        assert np.abs(got @ got.T - np.eye(3)).max() < 1e-5 and abs(np.linalg.det(got) - 1) < 1e-5, k
+        if k % 4 != 1:
+            assert np.abs(got - ref(sig32)).max() < 2e-5, (k, got, ref(sig32))
+        else:  # rank 2: unique as long as two singular values are non-zero; compare through the action on the plane
+            assert np.abs(got @ pts.T - Rtrue @ pts.T).max() < 1e-4, k
+        if k % 4 == 0:
+            assert np.abs(got - Rtrue).max() < 2e-5, k
+
+
 def test_oracle_icp_stop_rules(ob):
     rng = np.random.default_rng(6)
     tgt = icp_scene(rng, 1500)
