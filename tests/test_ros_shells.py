@@ -37,7 +37,7 @@ def test_plugin_names_topics_and_message_match_the_reference_surface():
                   "/corner_last", "/odom_aft_mapped"):
         assert '"%s"' % topic in src, topic
     # msg/cloud_info.msg:1-12 — and its C mirror AlegoCloudInfo
-    msg = [l.split() for l in open(os.path.join(ROS, "msg", "cloud_info.msg")) if l.strip() and not l.startswith("#")]
+    msg = [l.split("#")[0].split() for l in open(os.path.join(ROS, "msg", "cloud_info.msg")) if l.split("#")[0].strip()]
     assert msg == [["Header", "header"], ["int32[]", "startRingIndex"], ["int32[]", "endRingIndex"], ["float32", "startOrientation"],
                    ["float32", "endOrientation"], ["float32", "orientationDiff"], ["bool[]", "segmentedCloudGroundFlag"],
                    ["int32[]", "segmentedCloudColInd"], ["float32[]", "segmentedCloudRange"]]
