@@ -203,3 +203,118 @@ def test_oracle_ip_and_features_match_numpy_restatement(alego, ob, preset, seed)
         for k in ("sharp_idx", "less_sharp_idx", "flat_idx"):
             assert np.array_equal(o.get(k), f[k]), k
         assert len(f["sharp_idx"]) > 0 and len(f["flat_idx"]) > 0
+
+
+def test_oracle_scan_to_map_association_matches_numpy_restatement(alego, ob):
+    """LaserMapping's data association (laserMapping.cpp:371-462) restated with scipy's cKDTree, numpy's eigh and lstsq: the same
+    queries produce residual blocks, with the same line points (up to the sign of the eigenvector) and plane parameters."""
+    from scipy.spatial import cKDTree
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 7
+    w = alego.SynthWorld(seed=seed)
+    corner_map, surf_map = w.make_map(5000, 30000, seed=seed, radius=60.0)
+    o = ob.Oracle(P, lm_every=1, stable_voxel=True)
+    o.lm_set_map(corner_map, surf_map)
+    o.pipeline_step(w.render(P, alego.trajectory_pose(0, seed=seed), noise_seed=seed))  # first sweep: map2laser is the identity
+    # (the association of that first mapped sweep ran with map2odom = odom2laser = identity; the solve then moved the pose)
+    resids = o.get("lm_resids")
+    rep = o.report("lm")
+    edge, plane = resids[resids[:, 0] == 2], resids[resids[:, 0] == 3]
+    assert len(edge) == rep["n_corner"] > 20 and len(plane) == rep["n_surf"] > 200
+
+    def five_nn(tree, pts32, q):
+        _, j = tree.query(q.astype(np.float64), k=5)
+        # squared L2 accumulated in float like FLANN's L2_Simple: the gate compares that value (:376, :426)
+        d = np.zeros(len(q), np.float32)
+        far = pts32[j[:, 4]]
+        for c in range(3):
+            t = q[:, c] - far[:, c]
+            d = d + t * t
+        return j, d
+
+    # corner: PCA of the five neighbours, line iff the largest eigenvalue exceeds 3x the middle one (:397-403)
+    cq = o.get("lm_corner_ds")[:, :3]
+    j, d4 = five_nn(cKDTree(corner_map[:, :3].astype(np.float64)), corner_map[:, :3], cq)
+    sel, want = [], []
+    for i in np.nonzero(d4 < 1.0)[0]:
+        nb = corner_map[j[i], :3].astype(np.float64)
+        c = nb.sum(0) / 5.0
+        lam, vec = np.linalg.eigh((nb - c).T @ (nb - c))
+        if lam[2] > 3 * lam[1]:
+            sel.append(i)
+            want.append(np.concatenate([cq[i], c + 0.1 * vec[:, 2], c - 0.1 * vec[:, 2]]))
+    assert np.array_equal(o.get("lm_corner_sel"), np.array(sel, np.int32))
+    want = np.array(want)
+    got = edge[:, 1:10]
+    assert np.array_equal(got[:, :3], want[:, :3])
+    same = np.abs(got[:, 3:9] - want[:, 3:9]).max(1)
+    swapped = np.abs(got[:, 3:9] - want[:, [6, 7, 8, 3, 4, 5]]).max(1)
+    assert np.minimum(same, swapped).max() < 1e-6  # eigenvector sign is free: the residual does not depend on it
+
+    # surf: plane through the five neighbours by least squares of A n = -1, accepted iff all five lie within 0.2 m (:435-452)
+    sq = o.get("lm_surf_total_ds")[:, :3]
+    j, d4 = five_nn(cKDTree(surf_map[:, :3].astype(np.float64)), surf_map[:, :3], sq)
+    sel, want = [], []
+    for i in np.nonzero(d4 < 1.0)[0]:
+        nb = surf_map[j[i], :3].astype(np.float64)
+        n = np.linalg.lstsq(nb, -np.ones(5), rcond=None)[0]
+        dd = 1.0 / np.linalg.norm(n)
+        n = n / np.linalg.norm(n)
+        if (np.abs(nb @ n + dd) > 0.2).any():
+            continue
+        sel.append(i)
+        want.append(np.concatenate([sq[i], n, [dd]]))
+    want = np.array(want)
+    osel = o.get("lm_surf_sel")
+    # a plane test that lands within rounding of 0.2 m may differ between two least-squares routines: allow a handful
+    common = np.intersect1d(osel, np.array(sel, np.int32))
+    assert len(common) >= len(osel) - 2 and len(common) >= len(sel) - 2
+    got = plane[np.isin(osel, common)]
+    want = want[np.isin(np.array(sel), common)]
+    assert np.array_equal(got[:, 1:4], want[:, :3])
+    assert np.abs(got[:, 4:7] - want[:, 3:6]).max() < 1e-7 and np.abs(got[:, 13] - want[:, 6]).max() < 1e-6
+
+
+def test_oracle_scan_to_scan_surf_association_matches_numpy_restatement(alego, ob):
+    """LaserOdometry's surf association (laserOdometry.cpp:337-407): 1-NN in surf_last_ (float squared distance, gate 25), then the
+    walk over the neighbouring rings in storage order — best same-ring and best other-ring point, strict '<' so the first minimum
+    in walk order stays.  Restated with brute-force numpy on the second sweep (params_ = 0: transformToStart is the identity)."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 8
+    w = alego.SynthWorld(seed=seed)
+    o = ob.Oracle(P, lm_every=0)
+    for t in range(2):
+        o.ip(w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=60 + t))
+        o.lo_features()
+        if t == 1:
+            flat = o.get("flat")[:, :3].copy()
+            target = o.get("surf_last").copy()  # the first sweep's less_flat cloud
+        o.lo_scan2scan()
+    corr = o.get("lo_surf_corr")
+    assert len(corr) > 50
+    tx = target[:, :3]
+    ring = target[:, 3].astype(np.int64)  # int(intensity) (:347)
+    assert (np.diff(ring) >= 0).all()     # ring-major storage, which is what makes the walk's early `break` a range
+    want = []
+    for j, q in enumerate(flat):
+        d = np.zeros(len(tx), np.float32)
+        for c in range(3):
+            t_ = q[c] - tx[:, c]
+            d = d + t_ * t_
+        closest = int(np.argmin(d))
+        if not d[closest] < 25.0:
+            continue
+        rc = ring[closest]
+        diff = (tx - q).astype(np.float64)  # float subtraction, then pow(double, 2) (:357)
+        pd = diff[:, 0] ** 2 + diff[:, 1] ** 2 + diff[:, 2] ** 2
+        fwd = [k for k in range(closest + 1, len(tx)) if ring[k] <= rc + 2]
+        bwd = [k for k in range(closest - 1, -1, -1) if ring[k] >= rc - 2]
+        walk = np.array(fwd + bwd, np.int64)
+        best = []
+        for same in (True, False):
+            cand = walk[(ring[walk] == rc) == same]
+            cand = cand[pd[cand] < 25.0]
+            best.append(int(cand[np.argmin(pd[cand])]) if len(cand) else -1)
+        if best[0] >= 0 and best[1] >= 0:
+            want.append([j, closest, best[0], best[1]])
+    assert np.array_equal(corr, np.array(want, np.int32))
