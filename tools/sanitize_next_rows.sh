@@ -6,7 +6,7 @@ TAG=${1:-san}
 mkdir -p gpurun_out
 for TOOL in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $TOOL --error-exitcode 9 \
-      python -m pytest tests/test_next_rows.py tests/test_golden.py -m gpu -x -q -k "icp or distortion or bootstrap or n2 or n4" \
+      python -m pytest tests/test_next_rows.py tests/test_next_rows_golden.py -m gpu -x -q \
       > gpurun_out/${TAG}_${TOOL}.log 2>&1
   echo "$TOOL rc=$?"
   grep -E "ERROR SUMMARY|passed|failed|Race|Invalid" gpurun_out/${TAG}_${TOOL}.log | tail -5
