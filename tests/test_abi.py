@@ -67,3 +67,27 @@ def test_next_row_struct_layouts(alego):
     assert ctypes.sizeof(alego.AlegoImuQueue) == 4 * 4 + 10 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(alego.AlegoIcpResult) == 16 * 4 + 8 + 4 * 4
     assert alego.AlegoIcpResult.fitness_score.offset == 64 and alego.AlegoIcpResult.has_converged.offset == 72
+
+
+def test_every_entry_point_refuses_a_null_handle(alego):
+    """Errors are return codes, nothing throws or crashes across the boundary: every exported function called with a
+    null handle and zeroed arguments returns ALEGO_BAD_ARG (alego_last_error: its fixed string)."""
+    L = alego.lib()
+    skip = {"alego_host_alloc", "alego_host_free", "alego_destroy", "alego_default_params", "alego_create"}
+    for name in alego.EXPORTED_SYMBOLS:
+        if name in skip:
+            continue
+        fn = getattr(L, name)
+        args = []
+        for t in fn.argtypes:
+            if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t):
+                args.append(0)
+            elif t in (ctypes.c_double, ctypes.c_float):
+                args.append(0.0)
+            else:
+                args.append(None)
+        r = fn(*args)
+        if name == "alego_last_error":
+            assert r == b"null handle"
+        else:
+            assert r == alego.BAD_ARG, (name, r)
