@@ -139,3 +139,49 @@ def test_alego_run_closed_loop_keyframes(alego, tmp_path):
         moved = moved or abs(prm[0]) > 0.05
     assert moved
     a.close()
+
+
+def test_pointcloud2_decoder_properties(alego):
+    """Property test (hypothesis) of alego::decode_pointcloud2: for any record layout the decoded floats are exactly the bytes at the
+    field offsets; any view whose geometry does not fit (point_step too small for a field, row_step shorter than a row, capacity too
+    small) is refused with -1 and nothing is written."""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    L = C.CDLL(alego.HOST_PATH)
+    L.alego_host_decode_pointcloud2.restype = C.c_long
+    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 40), st.integers(0, 4), st.integers(1, 48), st.integers(0, 9), st.lists(st.integers(0, 44), min_size=4, max_size=4),
+           st.booleans(), st.sampled_from([3, 4]), st.integers(0, 2 ** 32 - 1), st.integers(-3, 3))
+    def run(width, height, step, pad, offs, big, stride, seed, cap_delta):
+        rng = np.random.default_rng(seed)
+        row_step = width * step + pad
+        raw = rng.integers(0, 256, max(height * row_step, 1), dtype=np.uint8)
+        # random bytes include NaN / inf / denormal patterns: they must pass through unchanged
+        n = width * height
+        cap = max(n + cap_delta, 0)
+        out = np.full((max(cap, 1), stride), -7.0, np.float32)
+        off_i = offs[3] if seed % 3 else -1
+        got = L.alego_host_decode_pointcloud2(raw.ctypes.data, width, height, step, row_step, offs[0], offs[1], offs[2], off_i, int(big),
+                                              out.ctypes.data, stride, cap)
+        fits = step >= max(offs[0], offs[1], offs[2], max(off_i, 0)) + 4
+        if n == 0:
+            assert got == 0
+            return
+        if not fits or n > cap:
+            assert got == -1 and (out == -7.0).all()
+            return
+        assert got == n
+        dt = ">f4" if big else "<f4"
+        for r in range(height):
+            for c in (0, width - 1):
+                base = r * row_step + c * step
+                for k in range(3):
+                    want = raw[base + offs[k]:base + offs[k] + 4].view(dt)[0]
+                    assert out[r * width + c, k].tobytes() == np.float32(want).tobytes()
+                if stride == 4:
+                    want = raw[base + off_i:base + off_i + 4].view(dt)[0] if off_i >= 0 else np.float32(0)
+                    assert out[r * width + c, 3].tobytes() == np.float32(want).tobytes()
+
+    run()
