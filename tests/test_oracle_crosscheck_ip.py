@@ -318,3 +318,118 @@ def test_oracle_scan_to_scan_surf_association_matches_numpy_restatement(alego, o
         if best[0] >= 0 and best[1] >= 0:
             want.append([j, closest, best[0], best[1]])
     assert np.array_equal(corr, np.array(want, np.int32))
+
+
+def numpy_ceres_lm(f14, x0, max_iters, a, ob):
+    """Ceres' trust-region Levenberg-Marquardt (1.13/1.14 trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, corrector.cc,
+    loss_function.cc; defaults of Solver::Options) restated with numpy: HuberLoss(a) corrector, Jacobi scaling, damped least squares
+    through numpy.linalg.lstsq on the augmented system instead of a hand-written QR.  Residuals / Jacobians come from the oracle's
+    per-residual evaluator (cross-checked separately against finite differences)."""
+    def evaluate(x, want_jac=True):
+        rs, Js = [], []
+        for f in f14:
+            r, J = ob.eval_residual(f, x)
+            rs.append(r)
+            Js.append(J)
+        r, J = np.array(rs), np.array(Js)
+        s = r * r
+        out = s > a * a
+        rho = np.where(out, 2 * a * np.sqrt(np.where(out, s, 1.0)) - a * a, s)
+        w = np.sqrt(np.where(out, a / np.sqrt(np.where(out, s, 1.0)), 1.0))  # rho'' <= 0: residual and Jacobian scale by sqrt(rho')
+        return 0.5 * rho.sum(), r * w, (J * w[:, None] if want_jac else None)
+
+    x = np.array(x0, np.float64)
+    cost, r, J = evaluate(x)
+    initial = cost
+    scale = 1.0 / (1.0 + np.sqrt((J * J).sum(0)))
+    J = J * scale
+    radius, decrease, reuse, it, ok_steps, invalid = 1e4, 2.0, False, 0, 0, 0
+    diag = None
+    while it < max_iters and radius > 1e-32:
+        it += 1
+        if not reuse:
+            diag = np.clip((J * J).sum(0), 1e-6, 1e32)
+        D = np.sqrt(diag / radius)
+        y = np.linalg.lstsq(np.vstack([J, np.diag(D)]), np.concatenate([r, np.zeros(6)]), rcond=None)[0]
+        step = -y
+        reuse = True
+        Jd = J @ step
+        model_change = -(Jd * (r + Jd / 2)).sum()
+        if not model_change > 0:
+            invalid += 1
+            if invalid >= 5:
+                break
+            radius *= 0.5
+            continue
+        invalid = 0
+        xc = x + step * scale
+        cand = evaluate(xc, False)[0]
+        if np.linalg.norm(x - xc) <= 1e-8 * (np.linalg.norm(x) + 1e-8):
+            break
+        if abs(cost - cand) <= 1e-6 * cost:
+            break
+        rho = (cost - cand) / model_change
+        if rho > 1e-3:
+            x = xc
+            cost, r, Ju = evaluate(x)
+            grad = Ju.T @ r
+            J = Ju * scale
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            decrease, reuse = 2.0, False
+            ok_steps += 1
+            if np.abs(grad).max() <= 1e-10:
+                break
+        else:
+            radius /= decrease
+            decrease *= 2.0
+    return x, {"iterations": it, "initial_cost": initial, "final_cost": cost, "successful": ok_steps}
+
+
+def test_oracle_lm_solver_matches_numpy_ceres_restatement(alego, ob):
+    """The oracle's Ceres-like solver against the numpy restatement above on real scan-to-map problems (edge + plane blocks of a
+    mapped sweep, HuberLoss(0.1), 20 iterations) from several start poses: same iteration count, same accepted steps, same
+    minimiser and costs."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 7
+    w = alego.SynthWorld(seed=seed)
+    cm, sm = w.make_map(5000, 30000, seed=seed, radius=60.0)
+    o = ob.Oracle(P, lm_every=1, stable_voxel=True)
+    o.lm_set_map(cm, sm)
+    o.pipeline_step(w.render(P, alego.trajectory_pose(0, seed=seed), noise_seed=seed))
+    f14 = o.get("lm_resids")[::6].copy()  # every 6th block keeps the python loop short; still ~400 residuals of both kinds
+    assert (f14[:, 0] == 2).sum() > 5 and (f14[:, 0] == 3).sum() > 100
+    rng = np.random.default_rng(1)
+    for trial in range(3):
+        x0 = np.zeros(6) if trial == 0 else rng.normal(0, 1, 6) * np.array([0.3, 0.3, 0.1, 0.01, 0.01, 0.03])
+        for iters in (20, 4):
+            xo, so = ob.solve(f14, x0, iters, 0.1)
+            xn, sn = numpy_ceres_lm(f14, x0, iters, 0.1, ob)
+            assert so["iterations"] == sn["iterations"] and so["successful"] == sn["successful"], (trial, iters, so, sn)
+            assert np.abs(xo - xn).max() < 1e-9, (trial, iters, xo, xn)
+            assert abs(so["initial_cost"] - sn["initial_cost"]) <= 1e-12 * sn["initial_cost"]
+            assert abs(so["final_cost"] - sn["final_cost"]) <= 1e-9 * sn["final_cost"]
+            assert so["final_cost"] < so["initial_cost"]
+
+
+def test_oracle_lo_solver_with_rank_deficient_jacobian_matches_numpy(alego, ob):
+    """LaserOdometry's problems (laserOdometry.cpp:403-492): SurfCostFunction touches only z, CornerCostFunction only x, y and yaw, so
+    the Jacobian has all-zero columns (roll, pitch — and x, y, yaw in the surf-only solve) that only Ceres' min_lm_diagonal clamp
+    keeps solvable.  Same comparison as above on the residual blocks of a second sweep."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 8
+    w = alego.SynthWorld(seed=seed)
+    o = ob.Oracle(P, lm_every=0)
+    for t in range(2):
+        o.ip(w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=60 + t))
+        o.lo_features()
+        o.lo_scan2scan()
+    f14 = o.get("lo_resids")
+    surf, corner = f14[f14[:, 0] == 1], f14[f14[:, 0] == 0]
+    assert len(surf) > 50 and len(corner) > 10
+    for blocks in (surf[::2], np.concatenate([surf[::2], corner])):  # the first solve, then the joint one (:418, :492)
+        xo, so = ob.solve(blocks, np.zeros(6), 5, 0.1)
+        xn, sn = numpy_ceres_lm(blocks, np.zeros(6), 5, 0.1, ob)
+        assert so["iterations"] == sn["iterations"] and so["successful"] == sn["successful"], (so, sn)
+        assert np.abs(xo - xn).max() < 1e-9, (xo, xn)
+        assert abs(xo[3]) < 1e-9 and abs(xo[4]) < 1e-9  # roll and pitch never move (up to the rounding of the damped solve)
+    assert xo[2] != 0.0 and xo[0] != 0.0
