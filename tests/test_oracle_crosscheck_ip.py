@@ -433,3 +433,31 @@ def test_oracle_lo_solver_with_rank_deficient_jacobian_matches_numpy(alego, ob):
         assert np.abs(xo - xn).max() < 1e-9, (xo, xn)
         assert abs(xo[3]) < 1e-9 and abs(xo[4]) < 1e-9  # roll and pitch never move (up to the rounding of the damped solve)
     assert xo[2] != 0.0 and xo[0] != 0.0
+
+
+def test_oracle_pose_bookkeeping_matches_scipy_rotations(alego, ob):
+    """Pose integration around the solves: LaserOdometry accumulates translation and yaw only (laserOdometry.cpp:504-508);
+    LaserMapping's transformUpdate turns params_ into map2laser = Rz Ry Rx, t and map2odom = map2laser o odom2laser^-1
+    (laserMapping.cpp:481-489).  Recomputed from the oracle's per-sweep params with scipy's Rotation."""
+    from scipy.spatial.transform import Rotation
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 3
+    w = alego.SynthWorld(seed=seed)
+    cm, sm = w.make_map(5000, 30000, seed=seed, radius=60.0)
+    o = ob.Oracle(P, lm_every=1, stable_voxel=True)
+    o.lm_set_map(cm, sm)
+    t_w, r_w = np.zeros(3), np.eye(3)
+    for t in range(4):
+        o.pipeline_step(w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=20 + t))
+        lo = o.get("lo_params")
+        if t > 0:  # the first sweep only initialises the targets (:316-324)
+            t_w = t_w + r_w @ lo[:3]
+            r_w = r_w @ Rotation.from_euler("z", lo[5]).as_matrix()
+        assert np.abs(o.get("t_w_cur") - t_w).max() < 1e-12 and np.abs(o.get("r_w_cur").reshape(3, 3) - r_w).max() < 1e-12, t
+        lm = o.get("lm_params")
+        r_m2l = Rotation.from_euler("ZYX", lm[5:2:-1]).as_matrix()  # Rz(yaw) Ry(pitch) Rx(roll)
+        assert np.abs(o.get("r_map2laser").reshape(3, 3) - r_m2l).max() < 1e-12 and np.abs(o.get("t_map2laser") - lm[:3]).max() < 1e-12
+        r_m2o = r_m2l @ r_w.T
+        assert np.abs(o.get("r_map2odom").reshape(3, 3) - r_m2o).max() < 1e-12
+        assert np.abs(o.get("t_map2odom") - (lm[:3] - r_m2o @ t_w)).max() < 1e-12
+    assert np.linalg.norm(t_w) > 0.2  # the sequence really moved
