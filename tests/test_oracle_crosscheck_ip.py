@@ -461,3 +461,49 @@ def test_oracle_pose_bookkeeping_matches_scipy_rotations(alego, ob):
         assert np.abs(o.get("r_map2odom").reshape(3, 3) - r_m2o).max() < 1e-12
         assert np.abs(o.get("t_map2odom") - (lm[:3] - r_m2o @ t_w)).max() < 1e-12
     assert np.linalg.norm(t_w) > 0.2  # the sequence really moved
+
+
+def test_oracle_scan_to_scan_corner_association_matches_numpy_restatement(alego, ob):
+    """LaserOdometry's corner association (laserOdometry.cpp:427-481) after the surf solve has moved params_: transformToStart
+    (:728-740, double rotation + translation, float result), 1-NN in corner_last_, then the best point on a HIGHER ring walking
+    forward (at most two rings up) or on a LOWER ring walking backward, one running minimum over both walks."""
+    from scipy.spatial.transform import Rotation
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 8
+    w = alego.SynthWorld(seed=seed)
+    o = ob.Oracle(P, lm_every=0)
+    for t in range(2):
+        o.ip(w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=60 + t))
+        o.lo_features()
+        if t == 1:
+            sharp = o.get("sharp")[:, :3].copy()
+            target = o.get("corner_last").copy()
+        o.lo_scan2scan()
+    resid = o.get("lo_resids")
+    surf = resid[resid[:, 0] == 1]
+    assert len(surf) >= 10
+    x, _ = ob.solve(surf, np.zeros(6), P.lo_surf_iters, P.huber_delta)  # params_ after the first Solve (:418)
+    Rm = Rotation.from_euler("ZYX", x[5:2:-1]).as_matrix()
+    sel = (sharp.astype(np.float64) @ Rm.T + x[:3]).astype(np.float32)
+    tx = target[:, :3]
+    ring = target[:, 3].astype(np.int64)
+    want = []
+    for j, q in enumerate(sel):
+        d = np.zeros(len(tx), np.float32)
+        for c in range(3):
+            t_ = q[c] - tx[:, c]
+            d = d + t_ * t_
+        closest = int(np.argmin(d))
+        if not d[closest] < 25.0:
+            continue
+        rc = ring[closest]
+        diff = (tx - q).astype(np.float64)
+        pd = diff[:, 0] ** 2 + diff[:, 1] ** 2 + diff[:, 2] ** 2
+        fwd = [k for k in range(closest + 1, len(tx)) if rc < ring[k] <= rc + 2]
+        bwd = [k for k in range(closest - 1, -1, -1) if rc - 2 <= ring[k] < rc]
+        walk = np.array(fwd + bwd, np.int64)
+        walk = walk[pd[walk] < 25.0] if len(walk) else walk
+        if len(walk):
+            want.append([j, closest, int(walk[np.argmin(pd[walk])])])
+    got = o.get("lo_corner_corr")
+    assert len(got) > 10 and np.array_equal(got, np.array(want, np.int32))
