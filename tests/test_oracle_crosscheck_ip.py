@@ -507,3 +507,25 @@ def test_oracle_scan_to_scan_corner_association_matches_numpy_restatement(alego,
             want.append([j, closest, int(walk[np.argmin(pd[walk])])])
     got = o.get("lo_corner_corr")
     assert len(got) > 10 and np.array_equal(got, np.array(want, np.int32))
+
+
+def test_oracle_downsample_current_scan_composition(alego, ob):
+    """downsampleCurrentScan (laserMapping.cpp:325-346): corner 0.4, surf 0.8, outlier 1.0, then surf_ds + outlier_ds through the
+    0.8 filter again — recomposed from the stand-alone VoxelGrid (itself cross-checked against a numpy restatement) on the clouds
+    LaserOdometry and ImageProjection hand over (/corner_last = less_sharp, /surf_last = less_flat, /outlier)."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seed = 2
+    w = alego.SynthWorld(seed=seed)
+    cm, sm = w.make_map(3000, 10000, seed=seed, radius=50.0)
+    for stable in (False, True):
+        o = ob.Oracle(P, lm_every=1, stable_voxel=stable)
+        o.lm_set_map(cm, sm)
+        o.pipeline_step(w.render(P, alego.trajectory_pose(0, seed=seed), noise_seed=5))
+        corner, surf, outlier = o.get("less_sharp"), o.get("less_flat_stable" if stable else "less_flat"), o.get("outlier_cloud")
+        c_ds, _ = ob.voxel_grid(corner, P.lm_corner_leaf, stable)
+        s_ds, _ = ob.voxel_grid(surf, P.lm_surf_leaf, stable)
+        o_ds, _ = ob.voxel_grid(outlier, P.lm_outlier_leaf, stable)
+        tot_ds, _ = ob.voxel_grid(np.concatenate([s_ds, o_ds]), P.lm_surf_leaf, stable)
+        assert np.array_equal(o.get("lm_corner_ds"), c_ds) and np.array_equal(o.get("lm_surf_ds"), s_ds)
+        assert np.array_equal(o.get("lm_outlier_ds"), o_ds) and np.array_equal(o.get("lm_surf_total_ds"), tot_ds)
+        assert len(c_ds) > 50 and len(tot_ds) > 500 and len(o_ds) > 10
