@@ -6,6 +6,10 @@ numpy with a different structure from oracle/alego_oracle.cpp — segmentation b
 (scipy.sparse.csgraph) instead of the reference's BFS, compaction by boolean masks and cumulative sums instead of the running
 counter, vectorised float32 stencils — so that a transcription slip in either shows up as a difference.  PARITY STAYS UNPINNED by
 the reference itself (it has no tests or vectors); this narrows the gap to "two independent readings agree".
+
+Further down, in the same spirit: LaserMapping's association (cKDTree + eigh + lstsq), LaserOdometry's surf and corner associations
+(brute force), Ceres' trust-region LM (numpy.linalg.lstsq on the damped system), the pose bookkeeping around the solves (scipy
+Rotation) and the composition of downsampleCurrentScan.
 """
 import numpy as np
 import pytest
