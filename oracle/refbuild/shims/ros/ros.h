@@ -1,0 +1,116 @@
+// Stand-in for roscpp (+ the bits of boost it drags in): enough for /root/reference's nodelets to compile UNMODIFIED and be driven
+// synchronously by oracle/refbuild/ref_*.cpp.  TEST INFRASTRUCTURE (oracle/_ref build only).
+// Publishers do not transport anything: publish() records the message per topic in alego_ref::bus() and calls an optional hook while
+// the publishing callback is still on the stack (that is how the driver reads ImageProjection's private images before pcCB clears them).
+#ifndef ALEGO_REF_SHIM_ROS_H
+#define ALEGO_REF_SHIM_ROS_H
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <chrono>
+#include <thread>
+
+namespace boost {
+using std::shared_ptr;
+template <typename F, typename... A>
+auto bind(F &&f, A &&... a) -> decltype(std::bind(std::forward<F>(f), std::forward<A>(a)...)) {
+  return std::bind(std::forward<F>(f), std::forward<A>(a)...);
+}
+}  // namespace boost
+using std::placeholders::_1;  // boost/bind.hpp puts its placeholders in the global namespace
+using std::placeholders::_2;
+
+namespace alego_ref {
+struct Bus {
+  std::map<std::string, std::shared_ptr<const void>> last;  // most recent message per topic
+  std::map<std::string, int> count;
+  std::function<void(const std::string &)> hook;            // called inside publish()
+  bool ok = true;                                           // what ros::ok() returns
+  bool park_sleepers = false;                               // ros::Rate::sleep() never returns (parks stray worker threads)
+  int subscribers = 1;                                      // what Publisher::getNumSubscribers() returns
+  std::function<bool()> ok_fn;                              // if set, overrides `ok`
+};
+inline Bus &bus() { static Bus b; return b; }
+}  // namespace alego_ref
+
+namespace ros {
+
+struct Time {
+  double sec_ = 0;
+  Time() {}
+  explicit Time(double s) : sec_(s) {}
+  double toSec() const { return sec_; }
+  Time &fromSec(double s) { sec_ = s; return *this; }
+  static Time now() { return Time(); }
+};
+struct Duration {
+  double d_;
+  explicit Duration(double d = 0) : d_(d) {}
+  bool sleep() const { return true; }
+};
+inline bool ok() { alego_ref::Bus &b = alego_ref::bus(); return b.ok_fn ? b.ok_fn() : b.ok; }
+inline void spinOnce() {}
+struct Rate {
+  explicit Rate(double) {}
+  bool sleep() {
+    while (alego_ref::bus().park_sleepers) std::this_thread::sleep_for(std::chrono::hours(1));
+    return true;
+  }
+};
+
+class Publisher {
+ public:
+  Publisher() {}
+  explicit Publisher(const std::string &topic) : topic_(topic) {}
+  int getNumSubscribers() const { return alego_ref::bus().subscribers; }
+  template <typename M>
+  void publish(const std::shared_ptr<M> &msg) const {
+    alego_ref::Bus &b = alego_ref::bus();
+    b.last[topic_] = std::static_pointer_cast<const void>(std::shared_ptr<const M>(msg));
+    ++b.count[topic_];
+    if (b.hook) b.hook(topic_);
+  }
+  const std::string &getTopic() const { return topic_; }
+
+ private:
+  std::string topic_;
+};
+struct Subscriber {};
+struct ServiceServer {};
+
+class NodeHandle {
+ public:
+  template <typename M>
+  Publisher advertise(const std::string &topic, int) { return Publisher(topic); }
+  template <typename M, typename F>
+  Subscriber subscribe(const std::string &, int, F) { return Subscriber(); }
+  template <typename... A>
+  ServiceServer advertiseService(const std::string &, A...) { return ServiceServer(); }
+};
+
+}  // namespace ros
+
+namespace std_msgs {
+struct Header {
+  uint32_t seq = 0;
+  ros::Time stamp;
+  std::string frame_id;
+};
+}  // namespace std_msgs
+
+#define ALEGO_REF_NOLOG(...) do { } while (0)
+#define ROS_INFO(...) ALEGO_REF_NOLOG()
+#define ROS_WARN(...) ALEGO_REF_NOLOG()
+#define ROS_ERROR(...) ALEGO_REF_NOLOG()
+#define ROS_INFO_STREAM(x) ALEGO_REF_NOLOG()
+#define ROS_WARN_STREAM(x) ALEGO_REF_NOLOG()
+#define NODELET_INFO(...) ALEGO_REF_NOLOG()
+#define NODELET_WARN(...) ALEGO_REF_NOLOG()
+#define NODELET_ERROR(...) ALEGO_REF_NOLOG()
+#define NODELET_INFO_STREAM(x) ALEGO_REF_NOLOG()
+#define NODELET_WARN_STREAM(x) ALEGO_REF_NOLOG()
+#define NODELET_WARN_COND(c, ...) ALEGO_REF_NOLOG()
+#define NODELET_WARN_ONCE(...) ALEGO_REF_NOLOG()
+#endif
