@@ -345,7 +345,11 @@ lo_solve_kernel(int phase, const float *__restrict__ surf_res, const int *__rest
   __shared__ int s_cnt[2];
   __shared__ int s_red[34];
   AlegoSolveReport *rep = report + b;
-  if (!lo_init[b]) {  // first frame of the sequence: only the targets are initialised (:316-324)
+  // block-uniform decision: thread 0 stores lo_init[b] = 1 below, so every thread must branch on the value read BEFORE that store
+  __shared__ int s_init;
+  if (threadIdx.x == 0) s_init = lo_init[b];
+  __syncthreads();
+  if (!s_init) {  // first frame of the sequence: only the targets are initialised (:316-324)
     if (phase == 2 && threadIdx.x == 0) {
       lo_init[b] = 1;
       rep->status = ALEGO_OK; rep->n_corner = 0; rep->n_surf = 0; rep->iterations = 0; rep->initial_cost = 0; rep->final_cost = 0;

@@ -39,13 +39,18 @@ long decode_pointcloud2(const PointCloud2View &m, float *out, int stride, size_t
   if (!out || (stride != 3 && stride != 4)) return -1;
   const size_t n = (size_t)m.width * m.height;
   if (n == 0) return 0;
-  const uint32_t row_step = m.row_step ? m.row_step : m.width * m.point_step;
-  const uint32_t last = std::max(std::max(m.off_x, m.off_y), std::max(m.off_z, (uint32_t)std::max(m.off_intensity, 0)));
-  if (!m.data || m.point_step < last + 4 || row_step < m.width * m.point_step || n > capacity_points) return -1;
+  // all geometry in 64-bit: width * point_step and offset + 4 wrap in uint32 for crafted headers
+  const uint64_t row_bytes = (uint64_t)m.width * m.point_step;
+  const uint64_t row_step = m.row_step ? m.row_step : row_bytes;
+  const uint64_t offs[4] = {m.off_x, m.off_y, m.off_z, (uint64_t)std::max(m.off_intensity, 0)};
+  if (!m.data || n > capacity_points || row_step < row_bytes) return -1;
+  for (uint64_t o : offs)
+    if (o + 4 > m.point_step) return -1;
+  if ((uint64_t)(m.height - 1) * row_step + row_bytes > (uint64_t)m.data_size) return -1;  // truncated / malformed message
   const bool swap = m.is_bigendian != host_is_bigendian();
   float *o = out;
   for (uint32_t r = 0; r < m.height; ++r) {
-    const uint8_t *p = m.data + (size_t)r * row_step;
+    const uint8_t *p = m.data + (size_t)(r * row_step);
     for (uint32_t c = 0; c < m.width; ++c, p += m.point_step, o += stride) {
       o[0] = load_f32(p + m.off_x, swap);
       o[1] = load_f32(p + m.off_y, swap);
@@ -302,11 +307,11 @@ int LaserMapping::pose(int seq, double params[6], double t_map2laser[3], double 
 }  // namespace alego
 
 extern "C" {
-long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+long alego_host_decode_pointcloud2(const uint8_t *data, size_t data_size, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
                                    uint32_t off_x, uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float *out,
                                    int stride, size_t capacity_points) {
   alego::PointCloud2View m;
-  m.data = data; m.width = width; m.height = height; m.point_step = point_step; m.row_step = row_step;
+  m.data = data; m.data_size = data_size; m.width = width; m.height = height; m.point_step = point_step; m.row_step = row_step;
   m.off_x = off_x; m.off_y = off_y; m.off_z = off_z; m.off_intensity = off_intensity; m.is_bigendian = is_bigendian != 0;
   return alego::decode_pointcloud2(m, out, stride, capacity_points);
 }

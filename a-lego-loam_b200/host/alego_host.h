@@ -41,6 +41,7 @@ typedef std::vector<PointXYZI> PointCloud;
 // with FLOAT32 fields x / y / z / intensity at the given byte offsets (off_intensity < 0: no such field).
 struct PointCloud2View {
   const uint8_t *data = nullptr;
+  size_t data_size = 0;  // bytes behind `data` (msg->data.size()): a view whose geometry reaches past it is refused
   uint32_t width = 0, height = 1, point_step = 0, row_step = 0;
   uint32_t off_x = 0, off_y = 4, off_z = 8;
   int32_t off_intensity = -1;
@@ -48,7 +49,8 @@ struct PointCloud2View {
 };
 // pcl::fromROSMsg for this path: decode into `stride` floats per point (3: x, y, z — what the kernels read; 4: + intensity,
 // 0 when the message has none).  NaN / inf stay in place (removeNaNFromPointCloud happens on the device).  Returns the number
-// of points written, or -1 when the view is inconsistent or `capacity_points` is too small.
+// of points written, or -1 when the view is inconsistent (a field does not fit in point_step, a row does not fit in row_step, the
+// last row ends past data_size — all checked in 64-bit arithmetic) or `capacity_points` is too small; nothing is written then.
 long decode_pointcloud2(const PointCloud2View &msg, float *out, int stride, size_t capacity_points);
 // pcl::toROSMsg layout of a PointXYZI cloud (/segmented_cloud, /outlier, imageProjection.cpp:318-336): x, y, z at 0, 4, 8,
 // intensity at 16, point_step 32, little endian.  `data` needs 32 * n bytes; returns the bytes written.
@@ -174,7 +176,7 @@ class LaserMapping {
 
 // C entry points of the two wire-format helpers (ctypes tests, other-language shells)
 extern "C" {
-long alego_host_decode_pointcloud2(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+long alego_host_decode_pointcloud2(const uint8_t *data, size_t data_size, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
                                    uint32_t off_x, uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float *out,
                                    int stride, size_t capacity_points);
 size_t alego_host_encode_pointcloud2_xyzi(const float *xyzi, size_t n, uint8_t *data);

@@ -142,6 +142,7 @@ class ImageProjection : public nodelet::Nodelet {
   void pcCB(const sensor_msgs::PointCloud2ConstPtr &msg) {  // imageProjection.cpp:49-208
     alego::PointCloud2View v;
     v.data = msg->data.data();
+    v.data_size = msg->data.size();
     v.width = msg->width; v.height = msg->height; v.point_step = msg->point_step; v.row_step = msg->row_step;
     const int ox = field_offset(*msg, "x"), oy = field_offset(*msg, "y"), oz = field_offset(*msg, "z");
     if (ox < 0 || oy < 0 || oz < 0) { NODELET_WARN("point cloud without float32 x / y / z fields"); return; }

@@ -25,7 +25,7 @@ def test_pointcloud2_wire_format_helpers(alego):
     import ctypes as C
     L = C.CDLL(alego.HOST_PATH)
     L.alego_host_decode_pointcloud2.restype = C.c_long
-    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p, C.c_size_t] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
     L.alego_host_encode_pointcloud2_xyzi.restype = C.c_size_t
     L.alego_host_encode_pointcloud2_xyzi.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     rng = np.random.default_rng(1)
@@ -43,23 +43,28 @@ def test_pointcloud2_wire_format_helpers(alego):
             rec[:, 20:22] = 7
         for stride in (3, 4):
             out = np.zeros((W * H, stride), np.float32)
-            n = L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data,
+            n = L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data,
                                                 stride, len(out))
             assert n == W * H
             assert np.array_equal(out, xyzi.reshape(-1, 4)[:, :stride], equal_nan=True)
         out = np.zeros((W * H, 4), np.float32)   # a message without an intensity field decodes to intensity 0
-        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, -1, int(big), out.ctypes.data, 4, len(out)) == W * H
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, step, W * step + pad, 0, 4, 8, -1, int(big), out.ctypes.data, 4, len(out)) == W * H
         assert (out[:, 3] == 0).all()
         # inconsistent views are refused: capacity too small, point_step smaller than a field, row_step smaller than a row
-        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, 5) == -1
-        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, 10, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
-        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, W, H, step, 10, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, 5) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, 10, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, step, 10, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+        # truncated message (data shorter than height * row_step says), and headers crafted to wrap 32-bit arithmetic
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes - pad - 1, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes - pad, W, H, step, W * step + pad, 0, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == W * H
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, 2 ** 31, 2, 2, 0, 0, 4, 8, 16, int(big), out.ctypes.data, 4, 2 ** 40) == -1
+        assert L.alego_host_decode_pointcloud2(raw.ctypes.data, raw.nbytes, W, H, step, W * step + pad, 2 ** 32 - 4, 4, 8, 16, int(big), out.ctypes.data, 4, len(out)) == -1
     # publisher side: PCL's PointXYZI layout (x y z @0,4,8, intensity @16, 32-byte records), and it decodes back
     flat = np.ascontiguousarray(xyzi.reshape(-1, 4))
     msg = np.zeros(len(flat) * 32, np.uint8)
     assert L.alego_host_encode_pointcloud2_xyzi(flat.ctypes.data, len(flat), msg.ctypes.data) == len(flat) * 32
     back = np.zeros_like(flat)
-    assert L.alego_host_decode_pointcloud2(msg.ctypes.data, len(flat), 1, 32, 0, 0, 4, 8, 16, 0, back.ctypes.data, 4, len(back)) == len(flat)
+    assert L.alego_host_decode_pointcloud2(msg.ctypes.data, msg.nbytes, len(flat), 1, 32, 0, 0, 4, 8, 16, 0, back.ctypes.data, 4, len(back)) == len(flat)
     assert np.array_equal(back, flat, equal_nan=True)
 
 
@@ -149,7 +154,7 @@ def test_pointcloud2_decoder_properties(alego):
     from hypothesis import given, settings, strategies as st
     L = C.CDLL(alego.HOST_PATH)
     L.alego_host_decode_pointcloud2.restype = C.c_long
-    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+    L.alego_host_decode_pointcloud2.argtypes = [C.c_void_p, C.c_size_t] + [C.c_uint32] * 7 + [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
 
     @settings(max_examples=200, deadline=None)
     @given(st.integers(0, 40), st.integers(0, 4), st.integers(1, 48), st.integers(0, 9), st.lists(st.integers(0, 44), min_size=4, max_size=4),
@@ -163,9 +168,11 @@ def test_pointcloud2_decoder_properties(alego):
         cap = max(n + cap_delta, 0)
         out = np.full((max(cap, 1), stride), -7.0, np.float32)
         off_i = offs[3] if seed % 3 else -1
-        got = L.alego_host_decode_pointcloud2(raw.ctypes.data, width, height, step, row_step, offs[0], offs[1], offs[2], off_i, int(big),
+        need = (height - 1) * row_step + width * step if n else 0
+        size = max(need - (seed % 5 == 0), 0)  # every fifth example: one byte short of what the geometry needs
+        got = L.alego_host_decode_pointcloud2(raw.ctypes.data, size, width, height, step, row_step, offs[0], offs[1], offs[2], off_i, int(big),
                                               out.ctypes.data, stride, cap)
-        fits = step >= max(offs[0], offs[1], offs[2], max(off_i, 0)) + 4
+        fits = step >= max(offs[0], offs[1], offs[2], max(off_i, 0)) + 4 and size >= need
         if n == 0:
             assert got == 0
             return
