@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py — scans/sec of the A-LeGO-LOAM hot path (ImageProjection -> LaserOdometry -> LaserMapping) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--preset ...] [--total-seq S]
 
-One "step" = one sweep of every sequence of the batch through IP -> LO -> LM.  Each GPU (one process per GPU,
-torchrun for N > 1) owns `--n-seq` INDEPENDENT sequences (weak scaling; no collective on the data path — the
-sequences share nothing; torch.distributed is only used for the barrier and the max-over-ranks
-of the device-timed region).  Prints ONE JSON line (rank 0).
+One "step" = one sweep of every sequence of the batch through IP -> LO -> LM.  Each GPU (one process per GPU, torchrun for N > 1)
+owns `--n-seq` INDEPENDENT sequences (weak scaling; no collective on the data path — the sequences share nothing, SURVEY.md §8e;
+torch.distributed only carries the barrier, the max-over-ranks of the device-timed region and the per-rank timing gather).
+`--total-seq S` instead fixes the whole job at S sequences split round-robin over the ranks (strong scaling, BASELINE config 5:
+8 independent 64x2048 sequences on 1/2/4/8 GPUs).  Prints ONE JSON line (rank 0).
 
-  value      scans/s with the sweeps already resident in HBM when the timed region starts
-  e2e        scans/s through alego_pipeline_step with HOST (pinned) buffers: H2D of every sweep and D2H of the
-             poses inside the timed region
-  roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
-  kernels    every kernel's share of the step (CUDA events, same workload, separate pass)
-  cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on a bounded sample, 1 core
+  value         scans/s with the sweeps already resident in HBM when the timed region starts
+  e2e           scans/s through alego_pipeline_submit/_collect with HOST (pinned) buffers: H2D of every sweep and D2H of the poses
+                inside the timed region
+  roofline      dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  kernels       every kernel's share of the step (CUDA events, same workload, separate pass)
+  parity_check  AFTER the timed regions: the poses / feature indices the timed passes left behind, for one batch slot of every
+                unique sequence, against the CPU reference chain run over the same sweeps
+  cpu_baseline  the reference's CPU path on a bounded sample, 1 core, with its own per-stage timers (LM ms/iter included)
 
---impl reference times the reference's CPU path (the oracle port — the reference itself cannot be built here,
-see DESIGN.md) on all host cores, independent sequences in parallel processes.
+--impl reference times the reference's CPU path on all host cores, one independent sequence per core, every step a bounded sample
+(`--ref-sweeps` consecutive sweeps per core).  CPU path = oracle/_ref (the reference's own sources compiled against stand-in
+third-party headers, kind "reference") when those libraries exist, else the port oracle (kind "port").
 """
 import argparse
 import json
@@ -25,6 +29,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -33,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 PRESETS = {"vlp16_1800": 0, "hdl64_1800": 1, "hdl64_2048": 2}
 N_UNIQUE = 8  # distinct synthetic sequences (worlds + trajectories); batch slots reuse them round-robin
+METRIC = "scans/sec on 64x1800 sweeps IP+LO+LM"
 
 
 def parse():
@@ -42,24 +48,44 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default="hdl64_1800", choices=sorted(PRESETS))
-    ap.add_argument("--n-seq", type=int, default=256, help="independent sequences per GPU")
+    ap.add_argument("--n-seq", type=int, default=256, help="independent sequences per GPU (weak scaling)")
+    ap.add_argument("--total-seq", type=int, default=0, help="if > 0: sequences of the WHOLE job, split over the ranks (strong scaling)")
     ap.add_argument("--lm-every", type=int, default=1, help="LaserMapping on every k-th sweep (reference: 2)")
     ap.add_argument("--map-corner", type=int, default=50000)
     ap.add_argument("--map-surf", type=int, default=200000)
-    ap.add_argument("--cpu-sweeps", type=int, default=40, help="bounded CPU sample: sweeps per sequence")
+    ap.add_argument("--cpu-sweeps", type=int, default=60, help="bounded CPU sample of the cpu_baseline leg: sweeps of one sequence")
+    ap.add_argument("--ref-sweeps", type=int, default=4, help="--impl reference: consecutive sweeps per core per step")
     ap.add_argument("--point-stride", type=int, default=3, choices=[3, 4],
                     help="floats per input point: 3 = packed x,y,z (the path never reads the sensor intensity), 4 = x,y,z,intensity")
     ap.add_argument("--map-order", default="voxel", choices=["voxel", "generator"],
                     help="order of the local-map clouds: 'voxel' = ascending PCL VoxelGrid index (x fastest), the order of the "
                          "reference's corner_from_map_ds_ / surf_from_map_ds_ (VoxelGrid outputs, laserMapping.cpp:316-319); "
                          "'generator' = the synthetic generator's structure-by-structure order")
+    ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the pass (launch-latency regime: few sequences per GPU)")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(args):
     return "%s IP+LO+LM, local map %dk corner + %dk surf re-indexed every mapped sweep, lm_every=%d" % (
         args.preset, args.map_corner // 1000, args.map_surf // 1000, args.lm_every)
+
+
+def config_block(args, P):
+    """The workload description BOTH arms print (only values that follow from the command line, so the two lines carry the same
+    dict; everything measured at run time goes to "run")."""
+    world = max(args.gpus, 1)
+    total = args.total_seq if args.total_seq > 0 else args.n_seq * world
+    return {"workload": workload_name(args), "preset": args.preset, "image": "%dx%d" % (P.n_scan, P.horizon_scan),
+            "sequences_total": total, "scans_per_step": total, "scaling_mode": "strong" if args.total_seq > 0 else "weak",
+            "point_stride_floats": args.point_stride, "map_order": args.map_order,
+            "l2_policy": "inputs larger than L2 at the default batch (one step = %d sweeps of ~%.1f MB each); below ~100 sequences per "
+                         "GPU every step still reads fresh sweeps, never the previous step's" % (
+                             total // world, P.n_scan * P.horizon_scan * 0.93 * 4 * args.point_stride / 1e6),
+            "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters),
+            "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)}
 
 
 def voxel_order(cloud, leaf):
@@ -74,18 +100,23 @@ def voxel_order(cloud, leaf):
     return np.ascontiguousarray(cloud[np.argsort(key, kind="stable")])
 
 
-def make_sequences(alego, P, n_steps, n_corner, n_surf, rank=0, map_order="voxel"):
-    """N_UNIQUE seeded sequences: n_steps consecutive sweeps each + a local map consistent with the world."""
-    seqs = []
-    for u in range(N_UNIQUE):
-        seed = 100 + 17 * rank + u
+def make_sequences(alego, P, n_sweeps, n_corner, n_surf, ids=None, map_order="voxel"):
+    """Seeded sequences (world + trajectory + local map consistent with the world), n_sweeps consecutive sweeps each.  `ids` are
+    GLOBAL sequence ids; the seed depends on the id only (sharding.sequence_seed), never on the rank or the world size."""
+    from alego_b200 import sharding
+    ids = list(range(N_UNIQUE)) if ids is None else list(ids)
+
+    def one(gid):
+        seed = sharding.sequence_seed(gid)
         w = alego.SynthWorld(seed=seed)
-        sweeps = [w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=1000 * seed + t) for t in range(n_steps)]
+        sweeps = [w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=1000 * seed + t) for t in range(n_sweeps)]
         corner, surf = w.make_map(n_corner, n_surf, seed=seed, radius=100.0)
         if map_order == "voxel":
             corner, surf = voxel_order(corner, P.lm_corner_leaf), voxel_order(surf, P.lm_surf_leaf)
-        seqs.append({"sweeps": sweeps, "map_corner": corner, "map_surf": surf})
-    return seqs
+        return {"id": gid, "sweeps": sweeps, "map_corner": corner, "map_surf": surf}
+
+    with ThreadPoolExecutor(max_workers=min(len(ids), os.cpu_count() or 1)) as ex:  # the generator is C++ behind ctypes (no GIL)
+        return list(ex.map(one, ids))
 
 
 class ClockSampler:
@@ -155,68 +186,192 @@ def ncu_traffic(kernel, n_seq, preset, stride):
     return None, None
 
 
-def cpu_oracle_run(P_bytes, preset_id, sweeps, map_corner, map_surf, lm_every):
-    """Time the oracle on one sequence (single thread). Returns seconds for len(sweeps) sweeps."""
-    from oracle import binding as ob
+# ------------------------------------------------------------------------------------------------------------------------------
+# The reference's CPU path (checker / baseline only — never on the product path)
+# ------------------------------------------------------------------------------------------------------------------------------
+def cpu_kind(args):
+    """"reference" = oracle/_ref (the reference's own translation units, compiled here against stand-in third-party headers);
+    "port" = oracle/alego_oracle.cpp."""
+    if args.cpu_kind != "auto":
+        return args.cpu_kind
+    from oracle import ref_binding
+    return "reference" if ref_binding.available(args.preset) else "port"
+
+
+class CpuChain:
+    """IP -> LO -> LM of ONE sequence on the CPU against a fixed local map, LaserMapping on every lm_every-th sweep — what
+    alego_pipeline_step does on the device.  kind "reference": the three nodelets of oracle/_ref chained like their topics;
+    kind "port": the oracle's pipeline_step."""
+
+    def __init__(self, kind, P, preset, map_corner, map_surf, lm_every):
+        self.kind, self.lm_every, self.count = kind, lm_every, 0
+        self.cm, self.sm = map_corner, map_surf
+        self.stage_ms = np.zeros(3)      # IP, LO (features + scan-to-scan), LM — accumulated
+        self.lm_detail_ms = np.zeros(4)  # the reference's own TicToc: downsample, kd-tree build, association, solver
+        self.lm_iters = 0
+        self.lm_calls = 0
+        if kind == "reference":
+            from oracle import ref_binding as rb
+            self.ip, self.lo, self.lm = rb.RefImageProjection(preset), rb.RefLaserOdometry(preset), rb.RefLaserMapping(preset)
+        else:
+            from oracle import binding as ob
+            self.o = ob.Oracle(P, lm_every=lm_every, stable_voxel=False)
+            self.o.lm_set_map(map_corner, map_surf)
+
+    def step(self, scan):
+        if self.kind == "port":
+            self.o.pipeline_step(scan)
+            t = self.o.get("timings_ms")
+            self.stage_ms += [t[0], t[1] + t[2], t[3] if self.lm_every and self.count % self.lm_every == 0 else 0.0]
+            if self.lm_every and self.count % self.lm_every == 0:
+                self.lm_iters += self.o.report("lm")["iterations"]
+                self.lm_calls += 1
+            self.count += 1
+            return
+        t0 = time.perf_counter()
+        self.ip.process(scan)
+        t1 = time.perf_counter()
+        self.lo.process(self.ip)
+        t2 = time.perf_counter()
+        if self.lm_every and self.count % self.lm_every == 0:
+            odom = self.lo.get("odom_lidar") if self.count > 0 else np.array([0, 0, 0, 1.0, 0, 0, 0])
+            self.lm.scan2map(self.cm, self.sm, self.lo.get("corner_last"), self.lo.get("surf_last"), self.ip.get("outlier_cloud"),
+                             odom[:3], odom[3:])
+            self.lm_detail_ms += self.lm.get("lm_timing_ms")
+            self.lm_iters += int(self.lm.get("lm_solve_iterations").sum())
+            self.lm_calls += 1
+        t3 = time.perf_counter()
+        self.stage_ms += [(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3]
+        self.count += 1
+
+    def state(self):
+        """what the parity check compares: LaserOdometry's and LaserMapping's parameter blocks"""
+        if self.kind == "port":
+            return {"lo_params": self.o.get("lo_params"), "lm_params": self.o.get("lm_params"),
+                    "less_sharp": self.o.get("less_sharp"), "n_seg": len(self.o.get("segmentedCloudColInd"))}
+        return {"lo_params": self.lo.get("lo_params"), "lm_params": self.lm.get("lm_params") if self.lm_calls else np.zeros(6),
+                "less_sharp": self.lo.get("less_sharp"), "n_seg": len(self.ip.get("segmentedCloudColInd"))}
+
+
+def pingpong(n, t):
+    """index into n consecutive sweeps walked forwards, then backwards, ... (consecutive sweeps stay consecutive)"""
+    if n <= 1:
+        return 0
+    period = 2 * (n - 1)
+    t %= period
+    return t if t < n else period - t
+
+
+def cpu_baseline_block(args, P, seq, kind):
+    """rank 0, N = 1: the CPU chain on ONE core over a bounded sample of sequence 0, with per-stage times and the reference's own
+    LaserMapping timers next to the device's lm block."""
+    chain = CpuChain(kind, P, args.preset, seq["map_corner"], seq["map_surf"], args.lm_every)
+    n = len(seq["sweeps"])
+    t0 = time.perf_counter()
+    for t in range(args.cpu_sweeps):
+        chain.step(seq["sweeps"][pingpong(n, t)])
+    dt = time.perf_counter() - t0
+    per = chain.stage_ms / max(chain.count, 1)
+    out = {"value": chain.count / dt, "unit": "scans/s", "cores": 1, "kind": kind,
+           "sample": "%d consecutive sweeps of sequence 0 through IP+LO+LM (%s), 1 thread" % (
+               chain.count, "oracle/_ref: the reference's own sources, stand-in PCL/Ceres" if kind == "reference" else "port oracle"),
+           "stage_ms_per_scan": {"ip": round(per[0], 3), "lo": round(per[1], 3), "lm": round(per[2], 3)},
+           # the reference runs its three stages as three nodes / threads (laserOdometry.cpp:76, laserMapping.cpp:95): pipelined over
+           # 3 cores one sequence advances at 1 / max(stage)
+           "three_core_pipelined_scans_per_s": round(1e3 / max(per.max(), 1e-9), 2)}
+    if chain.lm_calls:
+        lm = {"iters_per_scan2map": chain.lm_iters / chain.lm_calls}
+        if kind == "reference":
+            d = chain.lm_detail_ms / chain.lm_calls
+            lm.update({"downsample_ms": round(d[0], 3), "kdtree_build_ms": round(d[1], 3), "association_ms": round(d[2], 3),
+                       "solver_ms": round(d[3], 3), "ms_per_iter": round(chain.lm_detail_ms[3] / max(chain.lm_iters, 1), 4),
+                       "source": "the reference's own TicToc log lines (laserMapping.cpp:344,358,464,476), mean per scan2MapOptimization"})
+        else:
+            lm.update({"scan2map_ms": round(chain.stage_ms[2] / chain.lm_calls, 3),
+                       "ms_per_iter_upper_bound": round(chain.stage_ms[2] / max(chain.lm_iters, 1), 4)})
+        out["lm"] = lm
+    return out
+
+
+def _ref_worker(conn, kind, P_bytes, preset, seq, lm_every, n_sweeps):
+    """one host core of --impl reference: an independent sequence, n_sweeps consecutive sweeps per step"""
     import alego_pkg
     alego = alego_pkg.load()
     P = alego.AlegoParams.from_buffer_copy(P_bytes)
-    o = ob.Oracle(P, lm_every=lm_every, stable_voxel=False)
-    o.lm_set_map(map_corner, map_surf)
-    t0 = time.perf_counter()
-    for s in sweeps:
-        o.pipeline_step(s)
-    dt = time.perf_counter() - t0
-    return dt, o.get("timings_ms").tolist()
+    chain = CpuChain(kind, P, preset, seq["map_corner"], seq["map_surf"], lm_every)
+    n, t = len(seq["sweeps"]), 0
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd == "stop":
+            break
+        t0 = time.perf_counter()
+        for _ in range(n_sweeps):
+            chain.step(seq["sweeps"][pingpong(n, t)])
+            t += 1
+        conn.send(time.perf_counter() - t0)
+    conn.send((chain.stage_ms.tolist(), chain.count, chain.lm_detail_ms.tolist(), chain.lm_iters, chain.lm_calls))
 
 
-def _cpu_worker(args):
-    return cpu_oracle_run(*args)
-
-
-def run_reference(args, alego, P, rank, world):
-    """--impl reference: the CPU path on all host cores; every core runs an independent sequence."""
+def run_reference(args, alego, P, rank):
+    """--impl reference: the CPU path on all host cores; every core runs an independent sequence; EXACTLY W + K steps, each a
+    bounded sample of `--ref-sweeps` consecutive sweeps per core."""
     if rank != 0:
         return
     import multiprocessing as mp
+    kind = cpu_kind(args)
     cores = os.cpu_count() or 1
-    n_sweeps = max(4, min(args.cpu_sweeps, 12))
-    seqs = make_sequences(alego, P, n_sweeps, args.map_corner, args.map_surf, map_order=args.map_order)
-    jobs = [(bytes(P), PRESETS[args.preset], seqs[c % N_UNIQUE]["sweeps"], seqs[c % N_UNIQUE]["map_corner"], seqs[c % N_UNIQUE]["map_surf"],
-             args.lm_every) for c in range(cores)]
+    K, W, n_sw = args.steps, args.warmup, args.ref_sweeps
+    seqs = make_sequences(alego, P, 12, args.map_corner, args.map_surf, map_order=args.map_order)
     ctx = mp.get_context("fork")
-    step_times = []
-    with ctx.Pool(cores) as pool:
-        for it in range(args.warmup + args.steps):
-            if it >= max(1, min(args.warmup, 1)) + min(args.steps, 3):  # bounded: the whole run stays within minutes
-                break
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, jobs)
-            dt = time.perf_counter() - t0
-            if it >= min(args.warmup, 1):
-                step_times.append(dt)
-    per_step = float(np.mean(step_times))
-    value = cores * n_sweeps / per_step
+    pipes, procs = [], []
+    for c in range(cores):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, kind, bytes(P), args.preset, seqs[c % N_UNIQUE], args.lm_every, n_sw), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+    for a in pipes:
+        a.recv()
+    step_s = []
+    for it in range(W + K):
+        t0 = time.perf_counter()
+        for a in pipes:
+            a.send("go")
+        for a in pipes:
+            a.recv()
+        if it >= W:
+            step_s.append(time.perf_counter() - t0)
+    for a in pipes:
+        a.send("stop")
+    stats = [a.recv() for a in pipes]
+    for p in procs:
+        p.join(timeout=10)
+    total_s = float(np.sum(step_s))
+    value = cores * n_sw * K / total_s
+    stage = np.sum([s[0] for s in stats], axis=0) / max(sum(s[1] for s in stats), 1)
     line = {
-        "impl": "reference", "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": total_s / K * 1e3, "higher_is_better": True, "scaling": "strong" if args.total_seq > 0 else "weak",
         "vs_baseline": None, "dtype": "f32 geometry / f64 solver", "data": "synthetic",
-        "config": {"workload": workload_name(args), "map_order": args.map_order,
-                   "scans_per_step": cores * n_sweeps, "timed_steps_executed": len(step_times),
-                   "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
-        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
-                         "sample": "%d cores x %d consecutive sweeps (one independent sequence per core) per step" % (cores, n_sweeps)},
+        "config": config_block(args, P),
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind,
+                         "sample": "every step = %d host cores x %d consecutive sweeps (one independent sequence per core, state carried "
+                                   "from step to step); %d warm-up + %d timed steps" % (cores, n_sw, W, K),
+                         "stage_ms_per_scan": {"ip": round(stage[0], 3), "lo": round(stage[1], 3), "lm": round(stage[2], 3)}},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-# algorithmic bytes per launch of the kernels that have a streaming model (SURVEY.md §8 d4, DESIGN.md §5)
+# ------------------------------------------------------------------------------------------------------------------------------
+# byte models (SURVEY.md §8 d4, DESIGN.md §4) and the LM half of the metric
+# ------------------------------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(name, st):
-    pts, cells, kept, B = st["points"], st["cells"], st["kept"], st["B"]
+    pts, cells, kept = st["points"], st["cells"], st["kept"]
     pb = 4.0 * st["stride"]  # bytes per input point
-    gfrac = st["ground_rows"] / st["R"]
+    qc, qs = st.get("lm_corner_queries", 0.0), st.get("lm_surf_queries", 0.0)
     table = {
         "ip_project": (pb + 4.0) * pts,                # read the point + 4 B winner atomic
         # winner + gathered point -> cloud(16) + range(4) + ground(1) + cell flags(1)
@@ -224,17 +379,23 @@ def algorithmic_bytes(name, st):
         "ccl_rows": (1 + 4 + 8) * cells,               # flags -> parent + zeroed component statistics
         "ccl_merge": 5.0 * cells,                      # flags + the parent entries of joined cells (minimum)
         "ccl_flatten": 8.0 * cells,
+        "ccl_strip": 8.0 * cells,                      # §8 d4's 8 B / cell for the whole labelling (K3+K4)
         "ip_rowcount": 13.0 * cells,
         "ip_compact": 13.0 * cells + (16 + 4 + 25.0) * kept,
         "ip_label": 8.0 * cells,
         "lo_curv_occl": 21.0 * kept,                   # 4+4 read, 4+1+4+4 written per segmented point
-        # counting sort of the local map into the hashed grid, rebuilt every mapped sweep (the reference's kd-tree builds)
+        # counting sort of the local map into the grid, rebuilt every mapped sweep (the reference's kd-tree builds)
         "grid_count_map_surf": 20.0 * st["map_surf_pts"],    # 16 B point + 4 B counter
         "grid_fill_map_surf": 36.0 * st["map_surf_pts"],     # 16 B point + 4 B cursor + 16 B sorted copy
         "grid_count_map_corner": 20.0 * st["map_corner_pts"],
         "grid_fill_map_corner": 36.0 * st["map_corner_pts"],
+        # §8 d4 K14/K15: 16 B query + 5 x 16 B neighbours + 40 B result per query (candidate buckets come on top: see "traffic")
+        "lm_knn_corner": 136.0 * qc, "lm_knn_surf": 136.0 * qs,
+        # §8 d4 K16: 56 B per residual block per pass, 2 passes per LM iteration
+        "lm_solve": 56.0 * 2.0 * st.get("lm_resid_iters", 0.0),
     }
-    return table.get(name)
+    v = table.get(name)
+    return v if v else None
 
 
 def lm_block(kernels, lm_reports, lo_reports, B):
@@ -245,6 +406,7 @@ def lm_block(kernels, lm_reports, lo_reports, B):
     it = float(np.mean([r["iterations"] for r in lm_reports])) if lm_reports else 0.0
     solve_ms = kernels.get("lm_solve", {}).get("ms_per_launch")
     assoc_ms = sum(kernels[k]["ms_per_launch"] for k in ("lm_knn_corner", "lm_fit_corner", "lm_knn_surf", "lm_fit_surf") if k in kernels)
+    index_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for k, v in kernels.items() if k.startswith("grid_") and "_map_" in k)
     out = {"iters_per_scan2map": it, "edge_correspondences": float(np.mean([r["n_corner"] for r in lm_reports])) if lm_reports else 0.0,
            "plane_correspondences": float(np.mean([r["n_surf"] for r in lm_reports])) if lm_reports else 0.0,
            "lo_iters_per_scan": float(np.mean([r["iterations"] for r in lo_reports])) if lo_reports else 0.0}
@@ -252,8 +414,38 @@ def lm_block(kernels, lm_reports, lo_reports, B):
         out["ms_per_iter"] = solve_ms / it
         out["ms_per_iter_amortised_per_sequence"] = solve_ms / it / B
         out["association_ms_per_batch"] = assoc_ms
+        out["map_index_build_ms_per_batch"] = index_ms
         out["unit"] = "ms per LM iteration (latency with %d sequences in lock-step); amortised = / %d" % (B, B)
     return out
+
+
+def parity_check(alego, args, P, kind, seqs_by_slot, slots, snapshots, n_steps):
+    """Outside every timed region: the CPU chain over the SAME sweeps the three passes consumed (3 x n_steps consecutive sweeps per
+    sequence), compared at the end of each pass with what the device left behind in the chosen batch slots."""
+    def one(slot):
+        seq = seqs_by_slot[slot]
+        chain = CpuChain(kind, P, args.preset, seq["map_corner"], seq["map_surf"], args.lm_every)
+        res = []
+        for t in range(3 * n_steps):
+            chain.step(seq["sweeps"][t])
+            if (t + 1) % n_steps == 0:
+                res.append(chain.state())
+        return res
+
+    with ThreadPoolExecutor(max_workers=min(len(slots), os.cpu_count() or 1)) as ex:  # ctypes calls release the GIL
+        cpu = list(ex.map(one, slots))
+    worst_lo, worst_lm, idx_equal, n = 0.0, 0.0, True, 0
+    for k, slot in enumerate(slots):
+        for p in range(3):
+            dev, ref = snapshots[p][slot], cpu[k][p]
+            worst_lo = max(worst_lo, float(np.abs(dev["lo_params"] - ref["lo_params"]).max()))
+            worst_lm = max(worst_lm, float(np.abs(dev["lm_params"] - ref["lm_params"]).max()))
+            idx_equal = idx_equal and dev["n_seg"] == ref["n_seg"] and np.array_equal(dev["less_sharp"], ref["less_sharp"])
+            n += 1
+    return {"slots": [int(s) for s in slots], "comparisons": n, "passes": ["hbm-resident", "e2e submit/collect", "per-kernel profile"],
+            "sweeps_per_sequence": 3 * n_steps, "against": kind, "max_lo_pose_err": worst_lo, "max_lm_pose_err": worst_lm,
+            "max_pose_err": max(worst_lo, worst_lm), "less_sharp_and_segmentation_equal": bool(idx_equal), "tolerance": 1e-4,
+            "ok": bool(idx_equal and max(worst_lo, worst_lm) < 1e-4)}
 
 
 def main():
@@ -263,28 +455,31 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import alego_pkg
     alego = alego_pkg.load()
+    from alego_b200 import sharding
     P = alego.default_params(PRESETS[args.preset])
 
     if args.impl == "reference":
-        run_reference(args, alego, P, rank, world)
+        run_reference(args, alego, P, rank)
         return
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+    n_visible = torch.cuda.device_count()
+    device = sharding.device_for_local_rank(local_rank, n_visible, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    torch.cuda.set_device(device)
     numa = None
     try:  # keep the rank (and the pinned sweep buffers it first-touches) on the CPUs next to its GPU
         import pynvml
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device))
         numa = sorted(os.sched_getaffinity(0))
         numa = "cpus %d-%d (%d)" % (numa[0], numa[-1], len(numa))
     except Exception as e:  # best effort
         numa = "unbound (%s)" % type(e).__name__
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     def barrier():
         torch.cuda.synchronize()
@@ -292,15 +487,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W, B = args.steps, max(args.warmup, 3), args.n_seq
+    K, W = args.steps, max(args.warmup, 3)
     n_steps = W + K
-    seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, rank=rank, map_order=args.map_order)
-    g = alego.Alego(P, n_seq=B, device=local_rank)
-    g.pipeline_config(lm_every=args.lm_every, rebuild_map_index_every_step=True)
+    if args.total_seq > 0:  # strong scaling: the job's sequences split round-robin, each rank renders its own
+        my_ids = sharding.sequences_of_rank(args.total_seq, rank, world)
+        B = len(my_ids)
+        if B == 0:
+            raise SystemExit("bench.py: --total-seq %d leaves rank %d without a sequence" % (args.total_seq, rank))
+        unique_ids = my_ids[:N_UNIQUE] if len(my_ids) > N_UNIQUE else my_ids
+    else:           # weak scaling: every rank runs the same N_UNIQUE worlds (identical work per rank: the max over ranks is not a seed lottery)
+        B = args.n_seq
+        unique_ids = list(range(min(N_UNIQUE, B)))
+    U = len(unique_ids)
+    seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, ids=unique_ids, map_order=args.map_order)
+    g = alego.Alego(P, n_seq=B, device=device)
+    g.pipeline_config(lm_every=args.lm_every, rebuild_map_index_every_step=True, graphs=args.graphs)
     g.set_point_stride(args.point_stride)
     PS = args.point_stride
     for b in range(B):
-        s = seqs[b % N_UNIQUE]
+        s = seqs[b % U]
         g.lm_set_map(b, s["map_corner"], s["map_surf"])
     Nmax = g.max_points
     # pinned host sweep buffers, refilled per pass: A = sweeps [0,n), B = [n,2n), C = [2n,3n) of every sequence,
@@ -311,11 +516,32 @@ def main():
 
     def fill(first_sweep):
         for t in range(n_steps):
-            for u in range(min(N_UNIQUE, B)):
+            for u in range(U):
                 sw = seqs[u]["sweeps"][first_sweep + t]
-                host[t][u::N_UNIQUE, :len(sw)] = sw[:, :PS]
-                host_n[t][u::N_UNIQUE] = len(sw)
+                host[t][u::U, :len(sw)] = sw[:, :PS]
+                host_n[t][u::U] = len(sw)
             pts_per_step.append(int(host_n[t].sum()))
+
+    # batch slots whose results are compared with the CPU chain afterwards: one per unique sequence, from the MIDDLE of the batch
+    # (a kernel whose bounded-grid stride loop breaks at large B would show there, not in slot 0)
+    slots = [u + U * ((B // U) // 2) for u in range(U)] if B >= U else list(range(B))
+    slots = [s for s in slots if s < B]
+    snapshots = []
+
+    def snapshot():
+        g.synchronize()
+        snap = {}
+        for s in slots:
+            snap[s] = {"lo_params": g.debug("lo_params", s).copy(), "lm_params": g.debug("lm_params", s).copy(),
+                       "less_sharp": g.debug("less_sharp", s).copy(), "n_seg": len(g.debug("segmentedCloudColInd", s))}
+        # every slot of a unique sequence must carry the same answer (bit for bit: nothing on the path depends on the slot index)
+        same = True
+        for u in range(U):
+            ref = g.debug("lm_params", u)
+            for b in list(range(u, B, U))[:: max(1, (B // U) // 8)]:
+                same = same and np.array_equal(g.debug("lm_params", b), ref) and np.array_equal(g.debug("lo_params", b), g.debug("lo_params", u))
+        snap["_slots_identical"] = bool(same)
+        snapshots.append(snap)
 
     # ---------------- pass A: inputs resident in HBM ----------------
     fill(0)
@@ -325,7 +551,7 @@ def main():
         g.stage_select(t)
         g.pipeline_step(None, None, want_poses=False)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(device)
     l0 = g.launch_count()
     t_wall0 = time.time()
     g.timer_mark(0)
@@ -334,17 +560,17 @@ def main():
         g.pipeline_step(None, None, want_poses=False)
     g.timer_mark(1)
     barrier()
-    t_wall1 = time.time()
     ms_dev = g.timer_elapsed_ms(0, 1)
     launches = g.launch_count() - l0
+    snapshot()
 
     # H2D probe: what this box's PCIe link gives a plain pinned-memory copy of one step's sweeps (context for e2e, which is
-    # link-bound once the pass itself is faster than the copy)
+    # link-bound once the pass itself is faster than the copy).  All ranks probe at the same time, like the e2e pass does.
     probe_src = torch.empty(int(host[0].nbytes), dtype=torch.uint8).pin_memory()
     probe_dst = torch.empty(int(host[0].nbytes), dtype=torch.uint8, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     probe_dst.copy_(probe_src, non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record()
     for _ in range(4):
         probe_dst.copy_(probe_src, non_blocking=True)
@@ -371,13 +597,15 @@ def main():
     for _ in range(min(K, DEPTH)):
         poses = g.pipeline_collect()
     g.timer_mark(3)
-    barrier()
+    torch.cuda.synchronize()
     ms_e2e_host = (time.perf_counter() - t_host0) * 1e3
+    barrier()
     # device events on the compute stream bracket the region; the first H2D runs on the copy stream, so the (slightly
     # larger) host wall clock between the two synchronisation points is taken when it exceeds the event time
     ms_e2e_dev = g.timer_elapsed_ms(2, 3)
     ms_e2e = max(ms_e2e_dev, ms_e2e_host)
     clocks = sampler.stop(t_wall0, time.time())  # SM clocks / throttle reasons from the start of pass A to the end of pass B
+    snapshot()
 
     # ---------------- pass C: per-kernel CUDA events on the same workload ----------------
     fill(2 * n_steps)
@@ -394,23 +622,29 @@ def main():
     g.synchronize()
     prof = g.profile()
     g.profile_enable(False)
-    kept = float(np.mean([len(g.debug("segmentedCloudColInd", b)) for b in range(min(B, N_UNIQUE))])) * B
-    lm_reports = [g.solve_report("lm", b) for b in range(min(B, N_UNIQUE))]
-    lo_reports = [g.solve_report("lo", b) for b in range(min(B, N_UNIQUE))]
+    snapshot()
+    kept = float(np.mean([len(g.debug("segmentedCloudColInd", b)) for b in range(U)])) * B
+    lm_reports = [g.solve_report("lm", b) for b in range(U)]
+    lo_reports = [g.solve_report("lo", b) for b in range(U)]
+    lm_queries = (float(np.mean([len(g.debug("lm_corner_ds", b)) for b in range(U)])) * B,
+                  float(np.mean([len(g.debug("lm_surf_total_ds", b)) for b in range(U)])) * B)
 
-    times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(times[0]), float(times[1])
+    # max over ranks for the headline; every rank's own figures for attribution
+    ms_dev_max, ms_e2e_max = sharding.reduce_max_ms([ms_dev, ms_e2e], dist if world > 1 else None, device="cuda")
+    per_rank = sharding.gather_rank_stats({"rank": rank, "device": device, "ms_dev_per_step": ms_dev / K, "ms_e2e_per_step": ms_e2e / K,
+                                           "h2d_probe_gbs": round(h2d_probe_gbs, 1), "cpu_affinity": numa, "n_seq": B},
+                                          dist if world > 1 else None)
 
     if rank == 0:
-        scans = B * K * world
-        value = scans / (ms_dev * 1e-3)
-        e2e_value = scans / (ms_e2e * 1e-3)
+        total_seq = sum(r["n_seq"] for r in per_rank)
+        value = total_seq * K / (ms_dev_max * 1e-3)
+        e2e_value = total_seq * K / (ms_e2e_max * 1e-3)
         st = {"points": float(np.mean(pts_per_step)), "cells": float(B * P.n_scan * P.horizon_scan), "kept": kept, "B": B,
               "ground_rows": min(P.ground_scan_id + 1, P.n_scan), "R": P.n_scan, "stride": PS,
               "map_surf_pts": float(B * np.mean([len(q["map_surf"]) for q in seqs])),
-              "map_corner_pts": float(B * np.mean([len(q["map_corner"]) for q in seqs]))}
+              "map_corner_pts": float(B * np.mean([len(q["map_corner"]) for q in seqs])),
+              "lm_corner_queries": lm_queries[0], "lm_surf_queries": lm_queries[1],
+              "lm_resid_iters": B * float(np.mean([(r["n_corner"] + r["n_surf"]) * r["iterations"] for r in lm_reports]))}
         total_kernel_ms = sum(ms for _, ms in prof.values())
         kernels = {}
         for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
@@ -431,18 +665,22 @@ def main():
                     "named": {k: {"achieved": kernels[k]["algorithmic_gbs"], "frac": round(kernels[k]["algorithmic_gbs"] / peak, 4),
                                   "algorithmic_bytes_per_launch": algorithmic_bytes(k, st), "traffic": ncu_traffic(k, B, args.preset, PS)[0]}
                               for k in ("ip_project", "ip_image", "lo_curv_occl") if k in kernels}}
+        dev_ms = [r["ms_dev_per_step"] for r in per_rank]
+        e2e_ms = [r["ms_e2e_per_step"] for r in per_rank]
         line = {
-            "metric": "scans/sec on 64x1800 sweeps IP+LO+LM", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 geometry / f64 solver", "data": "synthetic (seeded ray-cast sweeps, %d unique sequences reused round-robin over the batch)" % N_UNIQUE,
-            "config": {"workload": workload_name(args),
-                       "n_seq_per_gpu": B, "scans_per_step": B * world, "points_per_scan": st["points"] / B,
-                       "point_stride_floats": PS, "map_order": args.map_order, "rank0_cpu_affinity": numa,
-                       "l2_policy": "inputs larger than L2 (%.0f MB of sweeps per step per GPU)" % (st["points"] * 4 * PS / 1e6),
-                       "lm_iters": "%d outer x <=%d LM" % (P.lm_outer_iters, P.lm_max_iters), "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)},
+            "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev_max / K, "higher_is_better": True, "scaling": "strong" if args.total_seq > 0 else "weak", "vs_baseline": None,
+            "dtype": "f32 geometry / f64 solver", "data": "synthetic (seeded ray-cast sweeps, %d unique sequences reused round-robin over the batch; "
+                                                          "the same sequences on every rank)" % U,
+            "config": config_block(args, P),
+            "run": {"n_seq_per_gpu": B, "points_per_scan": st["points"] / B, "graphs": bool(args.graphs),
+                    "sweep_mb_per_step_per_gpu": round(st["points"] * 4 * PS / 1e6, 1),
+                    "ms_dev_per_step_min_median_max": [round(float(f(dev_ms)), 4) for f in (np.min, np.median, np.max)],
+                    "ms_e2e_per_step_min_median_max": [round(float(f(e2e_ms)), 4) for f in (np.min, np.median, np.max)],
+                    "per_rank": per_rank},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 4 * PS + B * 4), "d2h_bytes_per_step": B * 12 * 8,
-                    "ms_per_step": ms_e2e / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
+                    "ms_per_step": ms_e2e_max / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
                     "h2d_probe_gbs": round(h2d_probe_gbs, 1),
                     "api": "alego_pipeline_submit/_collect, pinned host sweeps, 3 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
             "gpu_launches": int(launches),
@@ -451,14 +689,14 @@ def main():
             "kernels": kernels,
             "kernel_ms_per_step": total_kernel_ms / K,
         }
+        kind = cpu_kind(args)
+        if not args.no_parity_check:
+            seqs_by_slot = {s: seqs[s % U] for s in slots}
+            pc = parity_check(alego, args, P, kind, seqs_by_slot, slots, snapshots, n_steps)
+            pc["all_slots_of_a_sequence_identical"] = all(s["_slots_identical"] for s in snapshots)
+            line["parity_check"] = pc
         if not args.no_cpu_baseline and world == 1:
-            n_sw = args.cpu_sweeps
-            s0 = seqs[0]
-            sw = [s0["sweeps"][t % len(s0["sweeps"])] for t in range(min(n_sw, len(s0["sweeps"])))]
-            dt, stage_ms = cpu_oracle_run(bytes(P), PRESETS[args.preset], sw, s0["map_corner"], s0["map_surf"], args.lm_every)
-            line["cpu_baseline"] = {"value": len(sw) / dt, "unit": "scans/s", "cores": 1, "kind": "port",
-                                    "sample": "%d consecutive sweeps of sequence 0 through the oracle (IP+LO+LM), 1 thread" % len(sw),
-                                    "last_sweep_stage_ms": {"ip": stage_ms[0], "features": stage_ms[1], "scan2scan": stage_ms[2], "scan2map": stage_ms[3]}}
+            line["cpu_baseline"] = cpu_baseline_block(args, P, seqs[0], kind)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

@@ -77,7 +77,7 @@ _DT = {
     "lm_corner_ds": np.float32, "lm_surf_ds": np.float32, "lm_outlier_ds": np.float32, "lm_surf_total_ds": np.float32,
     "t_map2laser": np.float64, "q_map2laser": np.float64, "t_map2odom": np.float64, "q_map2odom": np.float64,
     "corner_from_map_ds": np.float32, "surf_from_map_ds": np.float32, "keyposes_6d": np.float64, "n_keyframes": np.int32,
-    "lm_constants": np.float64,
+    "lm_constants": np.float64, "lm_timing_ms": np.float64,
 }
 _COLS = {"full_cloud": 4, "segmented_cloud": 4, "outlier_cloud": 4, "sharp": 4, "less_sharp": 4, "flat": 4, "less_flat": 4,
          "surf_last": 4, "corner_last": 4, "lo_trace": 7, "lm_trace": 7, "lm_corner_ds": 4, "lm_surf_ds": 4, "lm_outlier_ds": 4,

@@ -85,6 +85,17 @@ void capture(RefLm *h) {
   }
   out.put("lm_trace", trace);
   out.put("lm_solve_iterations", iters);
+  // the reference's own TicToc figures (laserMapping.cpp:344, 358, 464, 476): per scan2MapOptimization call
+  // [downsample ms, kd-tree build ms, association ms (sum over outer iterations), solver ms (sum)]
+  double tm[4] = {0, 0, 0, 0};
+  for (const std::string &l : alego_ref::bus().log) {
+    double v = 0;
+    if (std::sscanf(l.c_str(), "downsampleCurrentScan: %lf", &v) == 1) tm[0] += v;
+    else if (std::sscanf(l.c_str(), "build kdtree time: %lf", &v) == 1) tm[1] += v;
+    else if (std::sscanf(l.c_str(), "mapping data assosiation time %lf", &v) == 1) tm[2] += v;
+    else if (std::sscanf(l.c_str(), "mapping solver time %lf", &v) == 1) tm[3] += v;
+  }
+  out.put("lm_timing_ms", tm, 4);
 }
 }  // namespace
 
@@ -132,6 +143,8 @@ int ref_lm_scan2map(void *hv, const float *map_corner, int nmc, const float *map
   n.laser_outlier_ = make_cloud(outlier, no);
   n.laserOdomHandler(make_odom(t_odom, q_odom_wxyz, 0.0));
   ceres::solve_log().clear();
+  alego_ref::bus().log.clear();
+  alego_ref::bus().capture_log = true;
   alego_ref::MuteCout mute;
   n.transformAssociateToMap();
   n.downsampleCurrentScan();
@@ -151,6 +164,8 @@ int ref_lm_frame(void *hv, const float *corner, int nc, const float *surf, int n
   n.outlierLastHandler(make_msg(outlier, no, stamp));
   n.laserOdomHandler(make_odom(t_odom, q_odom_wxyz, stamp));
   ceres::solve_log().clear();
+  alego_ref::bus().log.clear();
+  alego_ref::bus().capture_log = true;
   alego_ref::MuteCout mute;
   alego_ref::Bus &bus = alego_ref::bus();
   bus.ok_fn = [&n]() { return n.new_laser_surf_; };  // cleared by mainLoop once the set is consumed (:110)

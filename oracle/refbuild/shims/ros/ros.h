@@ -4,7 +4,11 @@
 // the publishing callback is still on the stack (that is how the driver reads ImageProjection's private images before pcCB clears them).
 #ifndef ALEGO_REF_SHIM_ROS_H
 #define ALEGO_REF_SHIM_ROS_H
+#include <cstdarg>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
 #include <functional>
 #include <map>
 #include <memory>
@@ -31,8 +35,28 @@ struct Bus {
   bool park_sleepers = false;                               // ros::Rate::sleep() never returns (parks stray worker threads)
   int subscribers = 1;                                      // what Publisher::getNumSubscribers() returns
   std::function<bool()> ok_fn;                              // if set, overrides `ok`
+  bool capture_log = false;                                 // keep the reference's own timing log lines (see log_printf)
+  std::vector<std::string> log;
 };
 inline Bus &bus() { static Bus b; return b; }
+// The reference reports its stage timings (TicToc, utility.h:99-120) through NODELET_INFO.  Only the lines whose format string
+// starts with one of these prefixes are formatted and kept (several other log calls in the reference pass fewer arguments than
+// their format string names, so nothing else is ever handed to vsnprintf).
+inline void log_printf(const char *fmt, ...) {
+  Bus &b = bus();
+  if (!b.capture_log) return;
+  static const char *const keep[] = {"mapping data assosiation time", "mapping solver time", "build kdtree time", "downsampleCurrentScan:",
+                                     "mapping whole time"};
+  bool hit = false;
+  for (const char *k : keep) hit = hit || std::strncmp(fmt, k, std::strlen(k)) == 0;
+  if (!hit) return;
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  b.log.push_back(buf);
+}
 }  // namespace alego_ref
 
 namespace ros {
@@ -106,7 +130,7 @@ struct Header {
 #define ROS_ERROR(...) ALEGO_REF_NOLOG()
 #define ROS_INFO_STREAM(x) ALEGO_REF_NOLOG()
 #define ROS_WARN_STREAM(x) ALEGO_REF_NOLOG()
-#define NODELET_INFO(...) ALEGO_REF_NOLOG()
+#define NODELET_INFO(...) alego_ref::log_printf(__VA_ARGS__)
 #define NODELET_WARN(...) ALEGO_REF_NOLOG()
 #define NODELET_ERROR(...) ALEGO_REF_NOLOG()
 #define NODELET_INFO_STREAM(x) ALEGO_REF_NOLOG()

@@ -30,10 +30,11 @@ def _worker(rank, world, port, n_seq, q):
     seeds = [sharding.sequence_seed(s) for s in mine]
     # pretend device times: rank r took 10 + 5 r ms (value) and 20 - 3 r ms (e2e)
     red = sharding.reduce_max_ms([10.0 + 5 * rank, 20.0 - 3 * rank], dist)
+    stats = sharding.gather_rank_stats({"rank": rank, "device": sharding.device_for_local_rank(rank, 8, world), "ms": 10.0 + 5 * rank}, dist)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     dist.barrier()
-    q.put((rank, mine, seeds, red, gathered))
+    q.put((rank, mine, seeds, red, gathered, stats))
     dist.destroy_process_group()
 
 
@@ -50,12 +51,14 @@ def test_two_rank_sharding_and_time_reduction(n_seq):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, m0, s0, red0, g0), (r1, m1, s1, red1, g1) = out
+    (r0, m0, s0, red0, g0, st0), (r1, m1, s1, red1, g1, st1) = out
     assert sorted(m0 + m1) == list(range(n_seq)) and not set(m0) & set(m1)      # disjoint cover
     assert abs(len(m0) - len(m1)) <= 1                                          # balanced
     assert red0 == red1 == [15.0, 20.0]                                         # max over ranks, element-wise
     assert g0 == g1 == [m0, m1]
     assert len(set(s0 + s1)) == n_seq                                           # distinct worlds per sequence
+    # per-rank attribution: every rank sees every rank's figures, in rank order; two ranks on an 8-GPU node take GPUs 0 and 4
+    assert st0 == st1 == [{"rank": 0, "device": 0, "ms": 10.0}, {"rank": 1, "device": 4, "ms": 15.0}]
 
 
 def test_single_process_helpers():
@@ -72,3 +75,9 @@ def test_single_process_helpers():
     # seeds are a function of the global sequence id only (weak scaling adds sequences, it does not reshuffle them)
     assert [sharding.sequence_seed(s) for s in sharding.sequences_of_rank(8, 1, 2)] == [101, 103, 105, 107]
     assert sharding.whole_job_throughput(64, 10, 8, 500.0) == 64 * 10 * 8 / 0.5
+    # rank -> GPU: a permutation of the node's GPUs that alternates between its two halves
+    assert sharding.device_order(8) == [0, 4, 1, 5, 2, 6, 3, 7] and sharding.device_order(1) == [0] and sharding.device_order(2) == [0, 1]
+    assert sorted(sharding.device_order(7)) == list(range(7))
+    assert [sharding.device_for_local_rank(r, 8, 4) for r in range(4)] == [0, 4, 1, 5]
+    assert sharding.device_for_local_rank(3, 2, 4) == 1  # more ranks than GPUs: wrap
+    assert sharding.gather_rank_stats({"a": 1}) == [{"a": 1}]
