@@ -65,7 +65,22 @@ __global__ void lm_prepare_kernel(const int *use_ext, const Pose *lo_pose, Pose 
 
 #define LMV_THREADS 1024
 #define LMV_WARPS (LMV_THREADS / 32)
-#define LMV_SMEM (sizeof(VoxShared<LMV_WARPS>))
+// dynamic shared memory: the digit counters / centroid windows, then LMV_EXACT_RECORDS records of the list whose exact
+// std::sort order is being established (clouds up to that size are partitioned in shared memory, longer ones in global
+// memory); sized so that two CTAs still share an SM
+#define LMV_EXACT_RECORDS 4608
+#define LMV_VOX_BYTES ((sizeof(VoxShared<LMV_WARPS>) + 15) & ~(size_t)15)
+#define LMV_SMEM (LMV_VOX_BYTES + (size_t)LMV_EXACT_RECORDS * sizeof(u64))
+__device__ __forceinline__ VoxExact lmv_exact(uint8_t *smem, IsbShared *isb) {
+  VoxExact ex;
+  ex.e_smem = reinterpret_cast<u64 *>(smem + LMV_VOX_BYTES);
+  ex.e_cap = LMV_EXACT_RECORDS;
+  ex.pos = nullptr;  // positions and range lists come out of the idle second key buffer
+  ex.lists = nullptr;
+  ex.list_cap = 0;
+  ex.isb = isb;
+  return ex;
+}
 // kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launch)
 __global__ void __launch_bounds__(LMV_THREADS)
 lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s, float4 *ds_o,
@@ -73,6 +88,8 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
                 int sort_cap_c, int sort_cap_s, int sort_cap_o) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
   VoxShared<LMV_WARPS> *sh = reinterpret_cast<VoxShared<LMV_WARPS> *>(lmv_smem);
+  __shared__ IsbShared s_isb;
+  const VoxExact ex = lmv_exact(lmv_smem, &s_isb);
   const int b = blockIdx.x, kind = first_kind + blockIdx.y;
   const float4 *src;
   int n;
@@ -99,7 +116,7 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
   }
   n = min(n, sort_cap);
   // ping-pong key buffers [2][sort_cap] in global memory (L2 resident), digit counters in shared memory
-  const int n_out = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + sort_cap, dst, sh, nullptr, nullptr);
+  const int n_out = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + sort_cap, dst, sh, nullptr, nullptr, &ex);
   if (threadIdx.x == 0) lm_n[b * 8 + (kind == 3 ? 4 : kind)] = n_out;
 }
 
@@ -108,7 +125,9 @@ __global__ void __launch_bounds__(LMV_THREADS)
 voxel_single_kernel(const float4 *src, int n, float leaf, float4 *dst, u64 *keys, int *n_out) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
   VoxShared<LMV_WARPS> *sh = reinterpret_cast<VoxShared<LMV_WARPS> *>(lmv_smem);
-  const int m = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + n, dst, sh, nullptr, nullptr);
+  __shared__ IsbShared s_isb;
+  const VoxExact ex = lmv_exact(lmv_smem, &s_isb);
+  const int m = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + n, dst, sh, nullptr, nullptr, &ex);
   if (threadIdx.x == 0) *n_out = m;
 }
 

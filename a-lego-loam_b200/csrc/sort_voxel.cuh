@@ -7,8 +7,11 @@
 // ijk = int(floor(p*inv) - float(min_b)); points sorted by key; one output per occupied voxel in ascending key
 // order = float sums of x,y,z,intensity divided by the float count; if the index space overflows int32 the
 // input is returned unchanged.  PCL sorts with std::sort on the key alone, so the summation order inside a
-// voxel is an accident of introsort; here points of a voxel are summed in ascending input order (a STABLE sort by
-// key of the position-ordered list), which is deterministic and equals the oracle's "stable" variant bit for bit.
+// voxel is whatever libstdc++'s introsort leaves.  With a VoxExact scratch the record list first goes through the
+// partition phase of that very algorithm (introsort_block.cuh) and then through the stable radix sort below, which
+// together give std::sort's exact record order — centroids equal PCL's bit for bit.  Without it (and for inputs that
+// contain non-finite points, which never occur on the hot path) the points of a voxel are summed in ascending input
+// order: deterministic, equal to the oracle's "stable" variant, within 2e-5 m of PCL's order.
 //
 // One CTA of NW warps handles one cloud (NW = 4 for one ring of the less-flat cloud, 32 for LaserMapping's clouds).
 // The sort is an LSD radix sort with 8-bit digits over only the significant bits of the key (a 21-bit voxel index:
@@ -19,6 +22,7 @@
 // buffers (L2 resident).
 #pragma once
 #include "common.cuh"
+#include "introsort_block.cuh"
 
 typedef unsigned long long u64;
 #define VOX_BITS 8
@@ -32,6 +36,18 @@ struct VoxFrame {
   int overflow;
   int key_bits;  // bits that hold every voxel index AND the index one past the last (the key of non-finite points)
   int n_cells;
+};
+
+// Scratch of the exact (PCL == std::sort) record order.  e_smem: optional shared-memory home of the record list while it is
+// partitioned (e_cap records; longer lists stay in global memory).  pos / lists: n ints and 4 x list_cap range records; when
+// pos is null both are carved out of the second ping-pong key buffer, which is idle during the partition phase.
+struct VoxExact {
+  u64 *e_smem;
+  int e_cap;
+  int *pos;
+  uint2 *lists;
+  int list_cap;
+  IsbShared *isb;
 };
 
 template <int NW>
@@ -257,7 +273,7 @@ __device__ __forceinline__ int warp_vox_centroids(const u64 *keys, int lo, int h
 // of output points (same value in every thread).  All threads of the block (NW warps) must call.
 template <int NW, bool MASKED, class Member>
 __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Member member, float leaf, u64 *ka, u64 *kb, float4 *out,
-                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base) {
+                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base, const VoxExact *ex = nullptr) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nch = (n_src + 31) >> 5;
@@ -265,12 +281,14 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
   for (int ch = w; ch < nch; ch += NW) {
     const int i = ch * 32 + lane;
-    const bool m = i < n_src && (!MASKED || member(i));
+    bool m = i < n_src && (!MASKED || member(i));
     if (m) {
       const float4 p = pts[i];
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
         mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
         mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      } else if (MASKED) {
+        m = false;  // PCL skips non-finite points of a non-dense cloud before it sorts: they are not members
       }
     }
     if (MASKED) {
@@ -330,6 +348,8 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
   }
   // ---- (voxel key, input position) words; non-finite points get the key one past the last voxel and sort to the end
   const unsigned pad_key = (unsigned)frame.n_cells;
+  const bool in_smem = ex && ex->e_smem && n <= ex->e_cap;
+  if (in_smem) ka = ex->e_smem;  // the list lives in shared memory while it is partitioned (and for the first radix pass)
   int nfin = 0;
   for (int ch = w; ch < nch; ch += NW) {
     const int i = ch * 32 + lane;
@@ -360,6 +380,19 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
   }
   __syncthreads();
   const int nv = sh->nv;
+  // ---- std::sort's record order = its partition phase, then a stable sort by key (see introsort_block.cuh)
+  if (ex && nv == n) {
+    int *pos = ex->pos;
+    uint2 *lists = ex->lists;
+    int list_cap = ex->list_cap;
+    if (!pos) {  // carve the scratch out of the idle second key buffer: n ints, then 4 lists of n / 17 + 1 ranges
+      pos = reinterpret_cast<int *>(kb);
+      lists = reinterpret_cast<uint2 *>(kb + (n + 1) / 2);
+      list_cap = n / 17 + 1;
+    }
+    block_introsort_partitions<NW>(ka, pos, n, lists, list_cap, ex->isb);
+    __syncthreads();
+  }
   // ---- stable sort by voxel key
   const u64 *keys = block_radix_sort8<NW>(ka, kb, n, frame.key_bits, sh);
   // ---- centroids: every warp counts the runs that start in its slice, then writes them behind those of the warps before

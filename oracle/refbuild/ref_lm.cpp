@@ -110,16 +110,18 @@ int ref_lm_constants(double *out9) {
 
 void *ref_lm_create() {
   RefLm *h = new RefLm;
-  alego_ref::Bus &bus = alego_ref::bus();
-  const bool ok0 = bus.ok;
-  bus.ok = false;            // the worker threads onInit spawns fall out of their `while (ros::ok())` loops immediately
-  bus.park_sleepers = true;  // ... and the one that tests the function pointer parks in ros::Rate::sleep()
-  bus.subscribers = 0;       // nothing on this node's topics is consumed by the driver (and the parked thread must not publish)
+  alego_ref::Globals &gl = alego_ref::globals();
+  // library-wide and for good (nodes may be created from several threads at once): on a thread without ok_fn — i.e. on the worker
+  // threads onInit spawns — ros::ok() is false, so mainLoop / loopClosureThread return immediately; the visualisation thread,
+  // which tests the function pointer, parks in ros::Rate::sleep(); nothing is "subscribed" (the parked thread never publishes).
+  // The driver's own calls into mainLoop set ok_fn on their thread.
+  gl.ok = false;
+  gl.park_sleepers = true;
+  gl.subscribers = 0;
   h->node = new loam::LaserMapping;  // leaked on purpose, see header
   h->node->onInit();
   h->node->main_thread_.join();
   h->node->loop_thread_.join();
-  bus.ok = ok0;
   // the reference leaves these uninitialised until the first message (laserMapping.h:93-100; onInit sets new_laser_corner_ twice
   // and never new_laser_odom_, :36)
   h->node->new_laser_odom_ = false;

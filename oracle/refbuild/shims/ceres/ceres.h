@@ -117,8 +117,8 @@ struct Solver {
   };
 };
 
-// every Solve() appends its Summary here so that a driver can read iteration traces without touching the caller's code
-inline std::vector<Solver::Summary> &solve_log() { static std::vector<Solver::Summary> log; return log; }
+// every Solve() appends its Summary here (per thread) so that a driver can read iteration traces without touching the caller's code
+inline std::vector<Solver::Summary> &solve_log() { static thread_local std::vector<Solver::Summary> log; return log; }
 
 namespace shim_detail {
 

@@ -4,6 +4,7 @@
 // the publishing callback is still on the stack (that is how the driver reads ImageProjection's private images before pcCB clears them).
 #ifndef ALEGO_REF_SHIM_ROS_H
 #define ALEGO_REF_SHIM_ROS_H
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -27,18 +28,24 @@ using std::placeholders::_1;  // boost/bind.hpp puts its placeholders in the glo
 using std::placeholders::_2;
 
 namespace alego_ref {
+// Per-THREAD state of the stand-in middleware: a driver call and everything the reference code does underneath it run on the
+// caller's thread, so independent nodes can be driven from independent threads (bench.py's parity check does).
 struct Bus {
   std::map<std::string, std::shared_ptr<const void>> last;  // most recent message per topic
   std::map<std::string, int> count;
   std::function<void(const std::string &)> hook;            // called inside publish()
-  bool ok = true;                                           // what ros::ok() returns
-  bool park_sleepers = false;                               // ros::Rate::sleep() never returns (parks stray worker threads)
-  int subscribers = 1;                                      // what Publisher::getNumSubscribers() returns
-  std::function<bool()> ok_fn;                              // if set, overrides `ok`
+  std::function<bool()> ok_fn;                              // if set, decides ros::ok() on this thread
   bool capture_log = false;                                 // keep the reference's own timing log lines (see log_printf)
   std::vector<std::string> log;
 };
-inline Bus &bus() { static Bus b; return b; }
+inline Bus &bus() { static thread_local Bus b; return b; }
+// Per-LIBRARY state, seen by every thread — including the worker threads LaserMapping::onInit spawns.
+struct Globals {
+  std::atomic<bool> ok{true};             // what ros::ok() returns on a thread without ok_fn
+  std::atomic<bool> park_sleepers{false}; // ros::Rate::sleep() never returns (parks stray worker threads)
+  std::atomic<int> subscribers{1};        // what Publisher::getNumSubscribers() returns
+};
+inline Globals &globals() { static Globals g; return g; }
 // The reference reports its stage timings (TicToc, utility.h:99-120) through NODELET_INFO.  Only the lines whose format string
 // starts with one of these prefixes are formatted and kept (several other log calls in the reference pass fewer arguments than
 // their format string names, so nothing else is ever handed to vsnprintf).
@@ -74,12 +81,12 @@ struct Duration {
   explicit Duration(double d = 0) : d_(d) {}
   bool sleep() const { return true; }
 };
-inline bool ok() { alego_ref::Bus &b = alego_ref::bus(); return b.ok_fn ? b.ok_fn() : b.ok; }
+inline bool ok() { alego_ref::Bus &b = alego_ref::bus(); return b.ok_fn ? b.ok_fn() : alego_ref::globals().ok.load(); }
 inline void spinOnce() {}
 struct Rate {
   explicit Rate(double) {}
   bool sleep() {
-    while (alego_ref::bus().park_sleepers) std::this_thread::sleep_for(std::chrono::hours(1));
+    while (alego_ref::globals().park_sleepers.load()) std::this_thread::sleep_for(std::chrono::hours(1));
     return true;
   }
 };
@@ -88,7 +95,7 @@ class Publisher {
  public:
   Publisher() {}
   explicit Publisher(const std::string &topic) : topic_(topic) {}
-  int getNumSubscribers() const { return alego_ref::bus().subscribers; }
+  int getNumSubscribers() const { return alego_ref::globals().subscribers.load(); }
   template <typename M>
   void publish(const std::shared_ptr<M> &msg) const {
     alego_ref::Bus &b = alego_ref::bus();

@@ -29,7 +29,7 @@ def main():
         s[:, 2] = rng.normal(-1.7, 0.05, ns).astype(np.float32)  # mostly a ground sheet: many points per 0.8 m voxel
         ck.append(c); sk.append(s); okf.append(o)
         out["corner%d" % k], out["surf%d" % k], out["outlier%d" % k] = c, s, o
-    cm, sm, M = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=True)
+    cm, sm, M = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=False)
     out["corner_from_map_ds"], out["surf_from_map_ds"], out["matrices"] = cm, sm, M
     np.savez_compressed(os.path.join(HERE, "n1_local_map.npz"), **out)
     print("n1_local_map.npz: %d corner, %d surf map points" % (len(cm), len(sm)))

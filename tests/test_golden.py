@@ -1,4 +1,6 @@
-"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle on seeded inputs).
+"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py on seeded inputs: outputs of the REFERENCE BUILD
+oracle/_ref wherever the reference materialises them — cross-asserted against the port oracle when the files are written — and the
+port's index lists where it does not; PCL's literal VoxelGrid record order throughout).
 
 CPU (`-m "not gpu"`): the oracle still reproduces its committed golden outputs — integer/index/byte arrays bit-exact,
 float32 pass-through bit-exact, double solver state to 1e-12.
@@ -29,11 +31,11 @@ def vlp16(alego):
 # ------------------------------------------------------------------------------------------------ CPU: oracle
 def test_oracle_reproduces_cfg1(alego, ob):
     g = load("cfg1_vlp16_ip_features.npz")
-    o = ob.Oracle(vlp16(alego), stable_voxel=True)
+    o = ob.Oracle(vlp16(alego), stable_voxel=False)
     assert o.ip(g["scan"]) == 0
     o.lo_features()
     M = len(g["segmentedCloudColInd"])
-    for k in IP_KEYS + ["sharp_idx", "less_sharp_idx", "flat_idx", "less_flat_stable"]:
+    for k in IP_KEYS + ["sharp_idx", "less_sharp_idx", "flat_idx", "less_flat"]:
         assert np.array_equal(np.asarray(o.get(k)), g[k]), k + ": " + first_diff(o.get(k), g[k])
     for k in ("cloud_curvature", "cloud_neighbor_picked", "cloud_label", "cloud_sort_idx"):
         assert np.array_equal(o.get(k)[5:M - 5], g[k]), k
@@ -48,7 +50,7 @@ def test_oracle_reproduces_cfg2(alego, ob, tag, corner_iters):
     g1, g = load("cfg1_vlp16_ip_features.npz"), load("cfg2_vlp16_scan2scan.npz")
     P = vlp16(alego)
     P.lo_corner_iters = corner_iters
-    o = ob.Oracle(P, lm_every=0, stable_voxel=True)
+    o = ob.Oracle(P, lm_every=0, stable_voxel=False)
     for t, s in enumerate([g1["scan"], g["scan1"], g["scan2"]]):
         o.ip(s)
         o.lo_features()
@@ -70,7 +72,7 @@ def test_oracle_reproduces_cfg3_small(alego, ob, tag, iters):
     g = load("cfg3_small_scan2map.npz")
     P = vlp16(alego)
     P.lm_outer_iters, P.lm_max_iters = iters
-    o = ob.Oracle(P, stable_voxel=True)
+    o = ob.Oracle(P, stable_voxel=False)
     o.lm_set_map(g["corner_map"], g["surf_map"])
     o.lm_set_scan(g["corner"], g["surf"], g["outlier"])
     o.lm_set_odom(g["t_odom"], g["r_odom"])
@@ -106,7 +108,7 @@ def test_cuda_reproduces_cfg1(alego):
     assert np.array_equal(a.debug("cloud_sort_idx")[5:M - 5], g["cloud_sort_idx"]), "std::sort permutation"
     for k in ("sharp_idx", "less_sharp_idx", "flat_idx"):
         assert np.array_equal(a.debug(k), g[k]), k
-    assert np.array_equal(a.debug("less_flat"), g["less_flat_stable"])
+    assert np.array_equal(a.debug("less_flat"), g["less_flat"]), "per-ring VoxelGrid in PCL's record order"
     a.close()
 
 
@@ -174,13 +176,13 @@ def _n1_inputs(g):
 def test_oracle_reproduces_n1_local_map(ob):
     g = load("n1_local_map.npz")
     ck, sk, okf, poses = _n1_inputs(g)
-    cm, sm, M = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=True)
+    cm, sm, M = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=False)
     assert np.array_equal(M, g["matrices"]) and np.array_equal(cm, g["corner_from_map_ds"]) and np.array_equal(sm, g["surf_from_map_ds"])
     # known-answer sanity of the fixture: rotations are orthonormal, fewer map points than inputs, PCL order agrees to 2e-5
     for Mk in M.reshape(-1, 3, 4):
         assert np.abs(Mk[:, :3] @ Mk[:, :3].T - np.eye(3)).max() < 1e-6
     assert 0 < len(sm) < sum(len(x) for x in sk) + sum(len(x) for x in okf)
-    cm2, sm2, _ = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=False)
+    cm2, sm2, _ = ob.lm_assemble_map(ck, sk, okf, poses, 0.4, 0.8, stable=True)
     assert cm2.shape == cm.shape and np.allclose(cm2, cm, rtol=0, atol=2e-5) and np.allclose(sm2, sm, rtol=0, atol=2e-5)
 
 

@@ -509,7 +509,7 @@ def test_gpu_bootstrap_from_empty_local_map(alego, ob):
     seed = 6
     w = alego.SynthWorld(seed=seed)
     g = alego.Alego(P, n_seq=1)
-    o = ob.Oracle(P, lm_every=1, stable_voxel=True)
+    o = ob.Oracle(P, lm_every=1, stable_voxel=False)
     empty = np.zeros((0, 4), np.float32)
     g.lm_set_map(0, empty, empty)
     o.lm_set_map(empty, empty)
@@ -535,7 +535,7 @@ def test_gpu_bootstrap_from_empty_local_map(alego, ob):
         poses6.append(np.asarray(o.get("lm_params"), np.float32))  # the same keyframe poses on both sides
         ck, sk, ok_ = [k[0] for k in kfs], [k[1] for k in kfs], [k[2] for k in kfs]
         g.lm_assemble_map(0, ck, sk, ok_, np.stack(poses6))
-        cm, sm, _ = ob.lm_assemble_map(ck, sk, ok_, np.stack(poses6), P.lm_corner_leaf, P.lm_surf_leaf, stable=True)
+        cm, sm, _ = ob.lm_assemble_map(ck, sk, ok_, np.stack(poses6), P.lm_corner_leaf, P.lm_surf_leaf, stable=False)
         o.lm_set_map(cm, sm)
         gc, gs = g.lm_get_map(0)
         assert np.array_equal(gc, cm) and np.array_equal(gs, sm), t

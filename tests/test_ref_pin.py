@@ -308,6 +308,36 @@ def test_adjust_distortion_matches_reference(alego, ob, rb):
     assert np.abs(ref_out[:, :3] - cloud[:, :3]).max() > 1e-3  # the correction is not a no-op
 
 
+def test_reference_nodes_are_independent_across_threads(alego, rb):
+    """bench.py's parity check drives several reference chains from a thread pool: the stand-in middleware keeps its state per
+    thread, so concurrent chains give exactly what they give one after the other."""
+    from concurrent.futures import ThreadPoolExecutor
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    seeds = [1, 2, 3, 4]
+    worlds = {s: alego.SynthWorld(seed=s) for s in seeds}
+    maps = {s: worlds[s].make_map(3000, 15000, seed=s, radius=60.0) for s in seeds}
+    sweeps = {s: [worlds[s].render(P, alego.trajectory_pose(t, seed=s), noise_seed=10 * s + t) for t in range(3)] for s in seeds}
+
+    def chain(s):
+        rip, rlo, rlm = rb.RefImageProjection("vlp16_1800"), rb.RefLaserOdometry("vlp16_1800"), rb.RefLaserMapping("vlp16_1800")
+        out = []
+        for t, scan in enumerate(sweeps[s]):
+            assert rip.process(scan) == 0 and rlo.process(rip) == 0
+            odom = rlo.get("odom_lidar") if t > 0 else np.array([0, 0, 0, 1.0, 0, 0, 0])
+            assert rlm.scan2map(maps[s][0], maps[s][1], rlo.get("corner_last"), rlo.get("surf_last"), rip.get("outlier_cloud"), odom[:3], odom[3:]) == 0
+            out.append((rip.get("label_mat").copy(), rlo.get("less_flat").copy(), rlo.get("lo_params").copy(), rlm.get("lm_params").copy(),
+                        rlm.get("lm_trace").copy()))
+        return out
+
+    serial = [chain(s) for s in seeds]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        threaded = list(ex.map(chain, seeds))
+    for a, b in zip(serial, threaded):
+        for ra, rb_ in zip(a, b):
+            for x, y in zip(ra, rb_):
+                assert np.array_equal(x, y)
+
+
 # ------------------------------------------------------------------------------------------------ GPU: CUDA vs the reference build
 def _gpu_vs_ref_ip_features(alego, ob, rb, preset, seeds):
     P = alego.default_params(preset)
