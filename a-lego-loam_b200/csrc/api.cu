@@ -6,6 +6,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sort_voxel.cuh"
+#include "vox_order.cuh"
 #include "grid.cuh"
 #include "ip_kernels.cuh"
 #include "lm_kernels.cuh"
@@ -203,6 +205,8 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   DMALLOC(h, h->sort_idx, B * RC);
   DMALLOC(h, h->sort_scratch, B * RC);
   DMALLOC(h, h->lfv_keys, B * RC);
+  CUDA_TRY(h, cudaMalloc(&h->lfv_state, (size_t)B * R * sizeof(VoxState)));
+  CUDA_TRY(h, cudaMalloc(&h->lmv_state, (size_t)B * 4 * sizeof(VoxState)));
   DMALLOC(h, h->ring_feat_cnt, B * R * 4);
   DMALLOC(h, h->ring_sharp, B * R * 12);
   DMALLOC(h, h->ring_less_sharp, B * R * 120);
@@ -312,7 +316,7 @@ void alego_destroy(AlegoHandle *h) {
   for (auto p : h->stage_n) cudaFree(p);
   void *ptrs[] = {h->raw_own, h->n_pts_own, h->winner, h->cloud, h->range, h->ground, h->cell_flags, h->parent, h->comp_stat,
                   h->comp_id, h->label, h->rowcnt, h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring, h->end_ring,
-                  h->M, h->outlier_buf[0], h->outlier_buf[1], h->n_outlier_buf[0], h->n_outlier_buf[1], h->o2l_lo[0], h->o2l_lo[1], h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys,
+                  h->M, h->outlier_buf[0], h->outlier_buf[1], h->n_outlier_buf[0], h->n_outlier_buf[1], h->o2l_lo[0], h->o2l_lo[1], h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys, h->lfv_state, h->lmv_state,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,
                   h->n_feat, h->sharp, h->flat, h->lf_stage, h->vox_sort, h->less_sharp[0], h->less_sharp[1], h->less_flat[0],
                   h->less_flat[1], h->ls_ring_off[0], h->ls_ring_off[1], h->lf_ring_off[0], h->lf_ring_off[1], h->lo_pose, h->az_stage, h->az_pts[0], h->az_pts[1], h->az_off[0], h->az_off[1], h->lo_params, h->t_w,

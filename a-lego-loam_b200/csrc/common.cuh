@@ -132,6 +132,8 @@ struct AlegoHandle {
   int *sort_idx = nullptr;     // [B][RC]  cloud_sort_idx_
   unsigned long long *sort_scratch = nullptr;  // [B][RC]  sort words (segment sort slow path; less-flat voxel keys, buffer A)
   unsigned long long *lfv_keys = nullptr;      // [B][RC]  less-flat voxel keys, buffer B
+  struct VoxState *lfv_state = nullptr;        // [B][R]   per ring: what the key stage of the VoxelGrid leaves for the next two
+  struct VoxState *lmv_state = nullptr;        // [B][4]   the same for LaserMapping's four VoxelGrid filters
   int *ring_feat_cnt = nullptr;  // [B][R][4]  sharp, less_sharp, flat, less_flat_ds per ring
   int *ring_sharp = nullptr;     // [B][R][12]
   int *ring_less_sharp = nullptr;// [B][R][120]

@@ -21,7 +21,7 @@
 #include "common.cuh"
 #include "stdsort_clone.cuh"
 
-#define ISB_BIG 1536  // ranges at least this long are partitioned by the whole CTA, shorter ones by one warp each
+#define ISB_BIG 1024  // ranges at least this long are partitioned by the whole CTA, shorter ones by one warp each
 
 struct IsbShared {
   int cnt_big[2], cnt_small[2];  // list lengths of the current / next level
@@ -40,32 +40,63 @@ __device__ __forceinline__ void isb_push(IsbShared *sh, uint2 *big, uint2 *small
   else small_[atomicAdd(&sh->cnt_small[nxt], 1)] = make_uint2((unsigned)f, (unsigned)l);
 }
 
-// one warp partitions [f, l): returns the cut (same value in every lane).  pos: scratch of l - f ints owned by the range.
-__device__ __forceinline__ int isb_warp_partition(unsigned long long *e, int *pos, int f, int l) {
+__device__ __forceinline__ unsigned isb_key_at(const unsigned long long *e, int t) {
+  return reinterpret_cast<const unsigned *>(e)[2 * t + 1];  // high word of a little-endian 64-bit record
+}
+
+// swaps recorded in posL / posR (k-th left stopper <-> k-th right stopper); wpos: optional per-warp shared-memory home of the
+// positions (16-bit offsets from f, for ranges up to ISB_REG elements), else the global scratch owned by the range
+__device__ __forceinline__ void isb_warp_swaps(unsigned long long *e, const int *posL, const int *posR, const unsigned short *wpos, int f,
+                                               int half, int K) {
+  const int lane = threadIdx.x & 31;
+  for (int k = lane; k < K; k += 32) {
+    const int a = wpos ? f + wpos[k] : posL[k], c2 = wpos ? f + wpos[half + k] : posR[k];
+    const unsigned long long ea = e[a], ec = e[c2];
+    e[a] = ec;
+    e[c2] = ea;
+  }
+}
+
+#define ISB_REG 256  // ranges up to this many elements keep their keys in registers (16 per lane): one load round trip
+
+// register path of the warp partition: the scan range (f, l) has at most 32 * NR elements
+template <int NR>
+__device__ __forceinline__ int isb_warp_partition_regs(unsigned long long *e, int *posL, int *posR, unsigned short *wpos, int f, int l,
+                                                       unsigned p, int half) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
-  if (lane == 0) ssc::median_to_first(e + f, e + f + 1, e + f + (l - f) / 2, e + l - 1);
-  __syncwarp();
-  const unsigned p = isb_key(e[f]);
-  const int lo = f + 1, m = l - lo;
-  int *posL = pos + f + 1, *posR = pos + f + 1 + (m - m / 2);  // at most m / 2 swaps
+  const int lo = f + 1;
+  unsigned kq[NR];
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    const int t = lo + q * 32 + lane;
+    kq[q] = t < l ? isb_key_at(e, t) : 0u;
+  }
   int totR = 0;
-  for (int c = lo; c < l; c += 32) {
-    const int t = c + lane;
-    totR += __popc(__ballot_sync(full, t < l && isb_key(e[t]) <= p));
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    const int t = lo + q * 32 + lane;
+    totR += __popc(__ballot_sync(full, t < l && kq[q] <= p));
   }
   int runL = 0, runR = 0, K = 0, first_keep_L = 0x7fffffff, min_swap_R = l;
-  for (int c = lo; c < l; c += 32) {
-    const int t = c + lane;
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    if (NR > 2 && lo + q * 32 >= l) break;  // warp-uniform
+    const int t = lo + q * 32 + lane;
     const bool v = t < l;
-    const unsigned kt = v ? isb_key(e[t]) : 0u;
+    const unsigned kt = kq[q];
     const bool isL = v && kt >= p, isR = v && kt <= p;
     const unsigned mL = __ballot_sync(full, isL), mR = __ballot_sync(full, isR);
     const int cL = runL + __popc(mL & lt_mask);           // left stoppers before t
     const int cR = totR - (runR + __popc(mR & le_mask));  // right stoppers after t
     const bool sL = isL && cR > cL, sR = isR && cL > cR;
-    if (sL) posL[cL] = t;
-    if (sR) posR[cR] = t;
+    if (wpos) {
+      if (sL) wpos[cL] = (unsigned short)(t - f);
+      if (sR) wpos[half + cR] = (unsigned short)(t - f);
+    } else {
+      if (sL) posL[cL] = t;
+      if (sR) posR[cR] = t;
+    }
     if (isL && !sL) first_keep_L = min(first_keep_L, t);
     if (sR) min_swap_R = min(min_swap_R, t);
     K += __popc(__ballot_sync(full, sL));
@@ -75,14 +106,99 @@ __device__ __forceinline__ int isb_warp_partition(unsigned long long *e, int *po
   first_keep_L = __reduce_min_sync(full, first_keep_L);
   min_swap_R = __reduce_min_sync(full, min_swap_R);
   __syncwarp();
-  for (int k = lane; k < K; k += 32) {
-    const int a = posL[k], c2 = posR[k];
-    const unsigned long long ea = e[a];
-    e[a] = e[c2];
-    e[c2] = ea;
-  }
+  isb_warp_swaps(e, posL, posR, wpos, f, half, K);
   __syncwarp();
   return min(first_keep_L, min_swap_R);
+}
+
+// one warp partitions [f, l): returns the cut (same value in every lane).  pos: scratch of l - f ints owned by the range.
+// wpos: per-warp shared scratch of ISB_REG 16-bit positions, or nullptr.
+__device__ __forceinline__ int isb_warp_partition(unsigned long long *e, int *pos, int f, int l, unsigned short *wpos) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+  if (lane == 0) ssc::median_to_first(e + f, e + f + 1, e + f + (l - f) / 2, e + l - 1);
+  __syncwarp();
+  const unsigned p = isb_key_at(e, f);
+  const int lo = f + 1, m = l - lo;
+  const int half = m - m / 2;
+  int *posL = pos + f + 1, *posR = pos + f + 1 + half;  // at most m / 2 swaps
+  if (m <= 32) return isb_warp_partition_regs<1>(e, posL, posR, wpos, f, l, p, half);
+  if (m <= 64) return isb_warp_partition_regs<2>(e, posL, posR, wpos, f, l, p, half);
+  if (m <= 128) return isb_warp_partition_regs<4>(e, posL, posR, wpos, f, l, p, half);
+  if (m <= ISB_REG) return isb_warp_partition_regs<ISB_REG / 32>(e, posL, posR, wpos, f, l, p, half);
+  int runL = 0, runR = 0, K = 0, first_keep_L = 0x7fffffff, min_swap_R = l, totR = 0;
+  // longer ranges: two sweeps, several chunks of loads in flight at a time
+  for (int c = lo; c < l; c += 128) {
+    unsigned k4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = c + q * 32 + lane;
+      k4[q] = t < l ? isb_key_at(e, t) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = c + q * 32 + lane;
+      totR += __popc(__ballot_sync(full, t < l && k4[q] <= p));
+    }
+  }
+  for (int c = lo; c < l; c += 128) {
+    unsigned k4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = c + q * 32 + lane;
+      k4[q] = t < l ? isb_key_at(e, t) : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = c + q * 32 + lane;
+      const bool v = t < l;
+      const unsigned kt = k4[q];
+      const bool isL = v && kt >= p, isR = v && kt <= p;
+      const unsigned mL = __ballot_sync(full, isL), mR = __ballot_sync(full, isR);
+      const int cL = runL + __popc(mL & lt_mask);
+      const int cR = totR - (runR + __popc(mR & le_mask));
+      const bool sL = isL && cR > cL, sR = isR && cL > cR;
+      if (sL) posL[cL] = t;
+      if (sR) posR[cR] = t;
+      if (isL && !sL) first_keep_L = min(first_keep_L, t);
+      if (sR) min_swap_R = min(min_swap_R, t);
+      K += __popc(__ballot_sync(full, sL));
+      runL += __popc(mL);
+      runR += __popc(mR);
+    }
+  }
+  first_keep_L = __reduce_min_sync(full, first_keep_L);
+  min_swap_R = __reduce_min_sync(full, min_swap_R);
+  __syncwarp();
+  isb_warp_swaps(e, posL, posR, nullptr, f, half, K);
+  __syncwarp();
+  return min(first_keep_L, min_swap_R);
+}
+
+// one warp finishes the introsort loop of [f, l) on its own (explicit stack: the right part is deferred, the left part continued —
+// the parts are disjoint, so the order in which they are processed does not matter)
+__device__ __forceinline__ void isw_heap(unsigned long long *e, int f, int l, unsigned long long *wheap);
+__device__ __forceinline__ void isb_warp_finish(unsigned long long *e, int *pos, int f, int l, int depth, unsigned short *wpos,
+                                                unsigned long long *wheap = nullptr) {
+  uint2 st[40];  // y = l | depth << 24
+  int sp = 0;
+  st[sp++] = make_uint2((unsigned)f, (unsigned)l | ((unsigned)depth << 24));
+  while (sp > 0) {
+    const uint2 fr = st[--sp];
+    f = (int)fr.x;
+    l = (int)(fr.y & 0xffffffu);
+    depth = (int)(fr.y >> 24);
+    while (l - f > 16) {
+      if (depth == 0) {
+        isw_heap(e, f, l, wheap);
+        break;
+      }
+      --depth;
+      const int cut = isb_warp_partition(e, pos, f, l, wpos);
+      if (l - cut > 16 && sp < 40) st[sp++] = make_uint2((unsigned)cut, (unsigned)l | ((unsigned)depth << 24));
+      l = cut;
+    }
+  }
 }
 
 // the whole CTA (NW warps) partitions [f, l): every warp owns a contiguous, 32-aligned slice of (f, l)
@@ -157,9 +273,12 @@ __device__ __forceinline__ int isb_block_partition(unsigned long long *e, int *p
 
 // e[0..n): the list (shared or global memory).  pos: n ints of scratch.  lists: 4 x list_cap range records (two levels x big /
 // small), list_cap >= n / 17 + 2.  Afterwards e holds exactly what std::__introsort_loop(e, e + n, 2 * lg(n)) leaves.
+// wpos_all: optional shared memory, NW x ISB_REG 16-bit entries (per-warp swap positions of short ranges), or nullptr.
 template <int NW>
-__device__ void block_introsort_partitions(unsigned long long *e, int *pos, int n, uint2 *lists, int list_cap, IsbShared *sh) {
+__device__ void block_introsort_partitions(unsigned long long *e, int *pos, int n, uint2 *lists, int list_cap, IsbShared *sh,
+                                           unsigned short *wpos_all = nullptr) {
   const int lane = threadIdx.x & 31;
+  unsigned short *wpos = wpos_all ? wpos_all + (threadIdx.x >> 5) * ISB_REG : nullptr;
   if (n <= 16) return;
   int depth = 2 * (31 - __clz(n));
   uint2 *big[2] = {lists, lists + list_cap}, *small_[2] = {lists + 2 * list_cap, lists + 3 * list_cap};
@@ -171,6 +290,7 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
   }
   __syncthreads();
   int cur = 0;
+  const int w = threadIdx.x >> 5;
   while (true) {
     const int nb = sh->cnt_big[cur], ns = sh->cnt_small[cur];
     if (nb + ns == 0) break;
@@ -180,6 +300,15 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
       for (int r = threadIdx.x; r < nb + ns; r += NW * 32) {
         const uint2 fl = r < nb ? big[cur][r] : small_[cur][r - nb];
         ssc::heap_sort(e + fl.x, (long)(fl.y - fl.x));
+      }
+      __syncthreads();
+      break;
+    }
+    if (nb == 0 && (ns >= NW || n < 64 * NW)) {
+      // enough independent ranges (or a short list): every warp finishes its share without further block-wide steps
+      for (int r = w; r < ns; r += NW) {
+        const uint2 fl = small_[cur][r];
+        isb_warp_finish(e, pos, (int)fl.x, (int)fl.y, depth, wpos);
       }
       __syncthreads();
       break;
@@ -198,7 +327,7 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
       r = __shfl_sync(0xffffffffu, r, 0);
       if (r >= ns) break;
       const uint2 fl = small_[cur][r];
-      const int cut = isb_warp_partition(e, pos, (int)fl.x, (int)fl.y);
+      const int cut = isb_warp_partition(e, pos, (int)fl.x, (int)fl.y, wpos);
       if (lane == 0) {
         isb_push(sh, big[nxt], small_[nxt], nxt, (int)fl.x, cut);
         isb_push(sh, big[nxt], small_[nxt], nxt, cut, (int)fl.y);
@@ -210,4 +339,160 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
     cur = nxt;
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Work-sharing variant for one list per CTA without any block-wide step: a task is a range (f, l, depth) that one warp
+// partitions; the warp keeps the left part, hands the right part to a shared-memory queue when it is long enough to be worth
+// another warp (ISW_SPLIT) and otherwise to its private stack.  The 10-20 dependent levels of a list thus overlap between the
+// warps, and the top levels fan out over 1, 2, 4 ... warps.  The list stays with one SM, so its records are served from L1.
+// Queue discipline: indices only grow.  push: outstanding += 1, slot = tail++, write the item, fence, ready[slot] = 1.
+// pop: slot = head++ (every warp claims its own slot), wait until ready[slot] — or until outstanding == 0, which can only happen
+// when every pushed task has completed, i.e. the claimed slot will never be filled: the warp leaves.  A task is completed
+// (outstanding -= 1) after everything it kept privately is finished.  A watchdog turns an impossible wait into an error flag.
+// ---------------------------------------------------------------------------------------------------------------------------
+#define ISW_SPLIT 96
+#define ISW_CAP 1024
+#define ISW_HEAP 128  // depth-limit ranges up to this long are heap-sorted in shared memory
+
+struct IswShared {
+  int head, tail, outstanding, err;
+  int4 items[ISW_CAP];  // x = f, y = l, z = depth limit left
+  int ready[ISW_CAP];
+};
+
+__device__ __forceinline__ bool isw_push(IswShared *q, int f, int l, int depth) {
+  const int slot = atomicAdd(&q->tail, 1);
+  if (slot >= ISW_CAP) return false;  // queue exhausted: the caller keeps the range
+  atomicAdd(&q->outstanding, 1);
+  q->items[slot] = make_int4(f, l, depth, 0);
+  __threadfence_block();
+  atomicExch(&q->ready[slot], 1);
+  return true;
+}
+
+// depth limit reached: std::__partial_sort(first, last, last) == heapsort, sequential by nature; short ranges in shared memory
+__device__ __forceinline__ void isw_heap(unsigned long long *e, int f, int l, unsigned long long *wheap) {
+  const int lane = threadIdx.x & 31, len = l - f;
+  if (wheap && len <= ISW_HEAP) {
+    for (int t = lane; t < len; t += 32) wheap[t] = e[f + t];
+    __syncwarp();
+    if (lane == 0) ssc::heap_sort(wheap, (long)len);
+    __syncwarp();
+    for (int t = lane; t < len; t += 32) e[f + t] = wheap[t];
+  } else if (lane == 0) {
+    ssc::heap_sort(e + f, (long)len);
+  }
+  __syncwarp();
+}
+
+// every warp of the CTA calls; q must have been reset and the root task pushed (block_introsort_ws does both)
+__device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, int *pos, unsigned short *wpos, unsigned long long *wheap) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&q->head, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= ISW_CAP) return;
+    int got = 0;
+    if (lane == 0) {
+      unsigned spins = 0;
+      while (true) {
+        if (*reinterpret_cast<volatile int *>(&q->ready[slot])) { got = 1; break; }
+        if (*reinterpret_cast<volatile int *>(&q->outstanding) <= 0) break;  // nothing left that could fill this slot
+        __nanosleep(100);
+        if (++spins > (1u << 23)) { q->err = 1; break; }  // watchdog (~1 s): give up instead of hanging
+      }
+    }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (!got) return;
+    const int4 it = q->items[slot];
+    uint2 st[40];  // private stack: y = l | depth << 24
+    int sp = 0;
+    st[sp++] = make_uint2((unsigned)it.x, (unsigned)it.y | ((unsigned)it.z << 24));
+    while (sp > 0) {
+      const uint2 fr = st[--sp];
+      int f = (int)fr.x, l = (int)(fr.y & 0xffffffu), depth = (int)(fr.y >> 24);
+      while (l - f > 16) {
+        if (depth == 0) {
+          isw_heap(e, f, l, wheap);
+          break;
+        }
+        --depth;
+        const int cut = isb_warp_partition(e, pos, f, l, wpos);
+        const int rlen = l - cut;
+        if (rlen > 16) {
+          int pushed = 0;
+          if (rlen > ISW_SPLIT) {
+            if (lane == 0) pushed = isw_push(q, cut, l, depth) ? 1 : 0;
+            pushed = __shfl_sync(0xffffffffu, pushed, 0);
+          }
+          if (!pushed && sp < 40) st[sp++] = make_uint2((unsigned)cut, (unsigned)l | ((unsigned)depth << 24));
+        }
+        l = cut;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicSub(&q->outstanding, 1); }
+  }
+}
+
+// The partition phase of std::sort on e[0..n) by the NW warps of the CTA.  Long ranges (>= ISW_BIG) first, level by level, each
+// partitioned by the whole CTA (isb_block_partition: the top levels of a long list would otherwise be one warp's serial,
+// latency-bound chain); what they leave below ISW_BIG becomes the initial tasks of the work-sharing phase (isw_worker).
+// pos: n ints of scratch.  wpos_all / wheap_all: per-warp shared scratch (NW x ISB_REG 16-bit positions; NW x ISW_HEAP records,
+// or nullptr).  Every thread of the CTA must call; ends with a barrier.
+#define ISW_BIG 2048
+#define ISW_MAX_BIG 64  // lists of up to ISW_BIG * ISW_MAX_BIG = 131072 records
+struct IswBig {
+  IsbShared coop;
+  int2 range[2][ISW_MAX_BIG];
+  int cnt[2];
+};
+
+template <int NW>
+__device__ void block_introsort_ws(unsigned long long *e, int *pos, int n, IswShared *q, IswBig *big, unsigned short *wpos_all,
+                                   unsigned long long *wheap_all) {
+  if (n <= 16) return;  // uniform
+  for (int t = threadIdx.x; t < ISW_CAP; t += NW * 32) q->ready[t] = 0;
+  int depth = 2 * (31 - __clz(n));
+  if (threadIdx.x == 0) {
+    q->head = 0; q->tail = 0; q->outstanding = 0; q->err = 0;
+    big->cnt[0] = big->cnt[1] = 0;
+    if (n >= ISW_BIG && n <= ISW_BIG * ISW_MAX_BIG) { big->range[0][0] = make_int2(0, n); big->cnt[0] = 1; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && big->cnt[0] == 0) isw_push(q, 0, n, depth);
+  int cur = 0;
+  while (true) {
+    __syncthreads();
+    const int nb = big->cnt[cur];
+    if (nb == 0) break;
+    const int nxt = cur ^ 1;
+    if (depth == 0) {  // depth limit on a long range: hand it to the workers, which heap-sort it
+      if (threadIdx.x == 0)
+        for (int r = 0; r < nb; ++r) isw_push(q, big->range[cur][r].x, big->range[cur][r].y, 0);
+      break;
+    }
+    --depth;
+    for (int r = 0; r < nb; ++r) {
+      const int2 fl = big->range[cur][r];
+      const int cut = isb_block_partition<NW>(e, pos, fl.x, fl.y, &big->coop);
+      if (threadIdx.x == 0) {
+        const int part[2][2] = {{fl.x, cut}, {cut, fl.y}};
+        for (int c = 0; c < 2; ++c) {
+          const int len = part[c][1] - part[c][0];
+          if (len >= ISW_BIG) big->range[nxt][big->cnt[nxt]++] = make_int2(part[c][0], part[c][1]);
+          else if (len > 16) isw_push(q, part[c][0], part[c][1], depth);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) big->cnt[cur] = 0;
+    cur = nxt;
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5;
+  isw_worker(q, e, pos, wpos_all + w * ISB_REG, wheap_all ? wheap_all + (size_t)w * ISW_HEAP : nullptr);
+  __syncthreads();
 }

@@ -17,6 +17,7 @@
 #include "lm_kernels.cuh"
 #include "solver.cuh"
 #include "sort_voxel.cuh"
+#include "vox_order.cuh"
 
 namespace {
 
@@ -70,7 +71,8 @@ __global__ void lm_prepare_kernel(const int *use_ext, const Pose *lo_pose, Pose 
 // memory); sized so that two CTAs still share an SM
 #define LMV_EXACT_RECORDS 4608
 #define LMV_VOX_BYTES ((sizeof(VoxShared<LMV_WARPS>) + 15) & ~(size_t)15)
-#define LMV_SMEM (LMV_VOX_BYTES + (size_t)LMV_EXACT_RECORDS * sizeof(u64))
+#define LMV_SMEM_EXACT (LMV_VOX_BYTES + (size_t)LMV_EXACT_RECORDS * sizeof(u64))  // voxel_single: the one-CTA, all-in-one variant
+#define LMV_SMEM LMV_VOX_BYTES
 __device__ __forceinline__ VoxExact lmv_exact(uint8_t *smem, IsbShared *isb) {
   VoxExact ex;
   ex.e_smem = reinterpret_cast<u64 *>(smem + LMV_VOX_BYTES);
@@ -79,18 +81,25 @@ __device__ __forceinline__ VoxExact lmv_exact(uint8_t *smem, IsbShared *isb) {
   ex.lists = nullptr;
   ex.list_cap = 0;
   ex.isb = isb;
+  ex.wpos = nullptr;
   return ex;
 }
-// kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launch)
+// kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launches).
+// stage 0: record lists (sort_voxel.cuh block_voxel_keys).  A cloud none of whose voxels holds three or more points (typically
+//          surf_total: its inputs are already one point per voxel) is finished on the spot — the order of the records inside a
+//          voxel cannot change a sum of at most two terms; every other cloud is left to the ordering kernel (vox_order.cu:
+//          pcl::VoxelGrid's std::sort order) and finished by stage 1.
+// stage 1: stable radix sort + centroids of the clouds stage 0 left pending.
 __global__ void __launch_bounds__(LMV_THREADS)
-lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s, float4 *ds_o,
-                float4 *total, float4 *ds_total, int cap_c, int cap_s, int cap_o, int *lm_n, u64 *sort_c, u64 *sort_s, u64 *sort_o,
-                int sort_cap_c, int sort_cap_s, int sort_cap_o) {
+lm_voxel_kernel(LmInputs in, int first_kind, int stage, float leaf_c, float leaf_s, float leaf_o, float4 *ds_c, float4 *ds_s,
+                float4 *ds_o, float4 *total, float4 *ds_total, int cap_c, int cap_s, int cap_o, int *lm_n, u64 *sort_base, u64 *sort_c,
+                u64 *sort_s, u64 *sort_o, int sort_cap_c, int sort_cap_s, int sort_cap_o, VoxState *states) {
   extern __shared__ __align__(16) uint8_t lmv_smem[];
   VoxShared<LMV_WARPS> *sh = reinterpret_cast<VoxShared<LMV_WARPS> *>(lmv_smem);
-  __shared__ IsbShared s_isb;
-  const VoxExact ex = lmv_exact(lmv_smem, &s_isb);
+  __shared__ int s_flag;
   const int b = blockIdx.x, kind = first_kind + blockIdx.y;
+  VoxState *state = states + b * 4 + kind;
+  if (stage == 1 && state->done) return;
   const float4 *src;
   int n;
   float leaf;
@@ -101,13 +110,15 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
     // laser_surf_total_ = laser_surf_ds_ + laser_outlier_ds_ (:337-340)
     const int ns = lm_n[b * 8 + 1], no = lm_n[b * 8 + 2];
     float4 *tot = total + (size_t)b * (cap_s + cap_o);
-    for (int t = threadIdx.x; t < ns; t += blockDim.x) tot[t] = ds_s[(size_t)b * cap_s + t];
-    for (int t = threadIdx.x; t < no; t += blockDim.x) tot[ns + t] = ds_o[(size_t)b * cap_o + t];
-    __syncthreads();
+    if (stage == 0) {
+      for (int t = threadIdx.x; t < ns; t += blockDim.x) tot[t] = ds_s[(size_t)b * cap_s + t];
+      for (int t = threadIdx.x; t < no; t += blockDim.x) tot[ns + t] = ds_o[(size_t)b * cap_o + t];
+      __syncthreads();
+      if (threadIdx.x == 0) lm_n[b * 8 + 3] = ns + no;
+    }
     src = tot; n = ns + no; leaf = leaf_s;
     dst = ds_total + (size_t)b * (cap_s + cap_o);
     keys = sort_s + (size_t)b * 2 * sort_cap_s; sort_cap = sort_cap_s;
-    if (threadIdx.x == 0) lm_n[b * 8 + 3] = n;
   } else {
     src = lm_input(in, b, kind, &n);
     if (kind == 0) { leaf = leaf_c; dst = ds_c + (size_t)b * cap_c; keys = sort_c + (size_t)b * 2 * sort_cap_c; sort_cap = sort_cap_c; n = min(n, cap_c); }
@@ -115,9 +126,33 @@ lm_voxel_kernel(LmInputs in, int first_kind, float leaf_c, float leaf_s, float l
     else { leaf = leaf_o; dst = ds_o + (size_t)b * cap_o; keys = sort_o + (size_t)b * 2 * sort_cap_o; sort_cap = sort_cap_o; n = min(n, cap_o); }
   }
   n = min(n, sort_cap);
+  int *n_out_ptr = lm_n + b * 8 + (kind == 3 ? 4 : kind);
   // ping-pong key buffers [2][sort_cap] in global memory (L2 resident), digit counters in shared memory
-  const int n_out = block_voxel_grid8<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, keys + sort_cap, dst, sh, nullptr, nullptr, &ex);
-  if (threadIdx.x == 0) lm_n[b * 8 + (kind == 3 ? 4 : kind)] = n_out;
+  if (stage == 1) {
+    const VoxState st = *state;
+    const int n_out = block_voxel_finish<LMV_WARPS>(src, keys, keys + sort_cap, dst, sh, st.n, st.nv, st.frame.key_bits);
+    if (threadIdx.x == 0) { *n_out_ptr = n_out; state->done = 1; }  // nothing pending any more (the ordering kernel skips it)
+    return;
+  }
+  const bool done = block_voxel_keys<LMV_WARPS, false>(src, n, [](int) { return true; }, leaf, keys, dst, sh, nullptr, nullptr);
+  const int nl = max(sh->n, 0), nv = sh->nv;
+  // lists with non-finite points (never on the hot path) keep the input order inside a voxel, as do lists that cannot care
+  const bool need_order = !done && nv == nl && nl > 16 && block_any_voxel_ge3<LMV_WARPS>(keys, nl, reinterpret_cast<u64 *>(dst), &s_flag);
+  if (!need_order) {
+    const int n_out = done ? nl : block_voxel_finish<LMV_WARPS>(src, keys, keys + sort_cap, dst, sh, nl, nv, sh->frame.key_bits);
+    if (threadIdx.x == 0) { *n_out_ptr = n_out; state->done = 1; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    VoxState st;
+    st.frame = sh->frame;
+    st.n = nl;
+    st.nv = nv;
+    st.done = 0;
+    st.off = (long long)(keys - sort_base);
+    st.off_b = st.off + sort_cap;
+    *state = st;
+  }
 }
 
 // stand-alone VoxelGrid of one device cloud (alego_voxel_grid)
@@ -570,14 +605,22 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   }
   const int cs = h->ds_cap_s, cc = h->ds_cap_c, co = h->ds_cap_o;
   u64 *sort_c = h->vox_sort, *sort_s = sort_c + (size_t)B * 2 * cc, *sort_o = sort_s + (size_t)B * 2 * (cs + co);
-  { LAUNCH(h, "lm_voxel_3");
-    lm_voxel_kernel<<<dim3(B, 3), LMV_THREADS, LMV_SMEM, s>>>(in, 0, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
-        (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
-        h->lm_n, sort_c, sort_s, sort_o, cc, cs + co, co); }
-  { LAUNCH(h, "lm_voxel_total");
-    lm_voxel_kernel<<<dim3(B, 1), LMV_THREADS, LMV_SMEM, s>>>(in, 3, (float)h->P.lm_corner_leaf, (float)h->P.lm_surf_leaf,
-        (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total, h->lm_surf_total_ds, cc, cs, co,
-        h->lm_n, sort_c, sort_s, sort_o, cc, cs + co, co); }
+  // downsampleCurrentScan (:325-346): three filters, then the filter of their union; each = record lists -> std::sort's partition
+  // phase (vox_order.cu) -> stable radix + centroids
+  auto voxel_stage = [&](const char *tag, int first_kind, int n_kinds, int stage) {
+    LAUNCH(h, tag);
+    lm_voxel_kernel<<<dim3(B, n_kinds), LMV_THREADS, LMV_SMEM, s>>>(in, first_kind, stage, (float)h->P.lm_corner_leaf,
+        (float)h->P.lm_surf_leaf, (float)h->P.lm_outlier_leaf, h->lm_corner_ds, h->lm_surf_ds, h->lm_outlier_ds, h->lm_surf_total,
+        h->lm_surf_total_ds, cc, cs, co, h->lm_n, h->vox_sort, sort_c, sort_s, sort_o, cc, cs + co, co, h->lmv_state);
+  };
+  voxel_stage("lm_voxel_keys_3", 0, 3, 0);
+  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_3");
+  if (rc != ALEGO_OK) return rc;
+  voxel_stage("lm_voxel_finish_3", 0, 3, 1);
+  voxel_stage("lm_voxel_keys_total", 3, 1, 0);
+  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_total");
+  if (rc != ALEGO_OK) return rc;
+  voxel_stage("lm_voxel_finish_total", 3, 1, 1);
   if (!index_ready && (h->rebuild_map_every_step || !h->map_index_valid)) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)
     rc = lm_build_map_index(h);
     if (rc != ALEGO_OK) return rc;
@@ -646,8 +689,8 @@ int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float 
   CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)2 * n * sizeof(u64)));
   CUDA_TRY(h, cudaMalloc(&d_n, sizeof(int)));
   CUDA_TRY(h, cudaMemcpyAsync(d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
-  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM, s>>>(d_in, n, leaf, d_out, d_keys, d_n); }
+  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM_EXACT));
+  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM_EXACT, s>>>(d_in, n, leaf, d_out, d_keys, d_n); }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(n_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -714,8 +757,8 @@ int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *se
   CUDA_TRY(h, cudaMemcpyAsync(d_M, M_host, (size_t)n_mat * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
   { LAUNCH(h, "lm_kf_transform");
     lm_kf_transform_kernel<<<std::min(div_up(n, 256), 2048), 256, 0, s>>>(d_in, n, d_off, n_seg, d_M, mat_shift); }
-  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM));
-  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM, s>>>(d_in, n, leaf, dst, d_keys, n_dst); }
+  CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM_EXACT));
+  { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM_EXACT, s>>>(d_in, n, leaf, dst, d_keys, n_dst); }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(s));  // the host clouds and the scratch are released on return
   cudaFree(d_in); cudaFree(d_keys); cudaFree(d_off); cudaFree(d_M);

@@ -11,6 +11,7 @@
 #include "lo_kernels.cuh"
 #include "sort_voxel.cuh"
 #include "stdsort_clone.cuh"
+#include "vox_order.cuh"
 
 namespace {
 
@@ -401,26 +402,19 @@ lo_select_kernel(const int *__restrict__ seg_col, const uint8_t *__restrict__ se
 // into AZ_BINS azimuth bins.  lo_assoc<SURF> walks "every point of rings cs-2..cs+2" (laserOdometry.cpp:348-395) only
 // inside the azimuth window that can hold a point closer than its current best — same result, ~10x fewer candidates.
 // az_stage[j] = (x, y, z, position of the point inside the ring); az_off[0..AZ_BINS] = bin starts.
+//
+// Three launches (one stream): lo_lfv_keys (membership, bounding box, (voxel, point) records), lo_lfv_order (vox_order.cu: the
+// partition phase of std::sort on every ring's list, one warp per ring — no block-wide step, where a CTA-per-ring,
+// barrier-per-level version left three of four warps idle), lo_lfv_finish (stable radix sort, centroids, azimuth bins).
 #define LFV_WARPS 4
 #define LFV_MAX_CHUNKS 256  // 8192 columns / 32
 __global__ void __launch_bounds__(LFV_WARPS * 32)
-lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ flabel, const int *__restrict__ start_ring,
-                          const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, int *__restrict__ ring_feat_cnt,
-                          u64 *__restrict__ keys_a, u64 *__restrict__ keys_b, float4 *__restrict__ az_stage,
-                          int *__restrict__ az_off, int R, int RC, float leaf, int ex_cap) {
+lo_lfv_keys_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ flabel, const int *__restrict__ start_ring,
+                   const int *__restrict__ end_ring, float4 *__restrict__ lf_stage, u64 *__restrict__ keys_a, VoxState *__restrict__ state,
+                   int R, int RC, float leaf) {
   __shared__ VoxShared<LFV_WARPS> sh;
   __shared__ unsigned s_member[LFV_MAX_CHUNKS];
   __shared__ int s_chunk_base[LFV_MAX_CHUNKS];
-  __shared__ IsbShared s_isb;
-  // record list, swap positions and range lists of the exact (PCL == std::sort) record order: a ring holds at most C points
-  extern __shared__ __align__(16) unsigned char lfv_dyn[];
-  VoxExact ex;
-  ex.e_smem = reinterpret_cast<u64 *>(lfv_dyn);
-  ex.e_cap = ex_cap;
-  ex.pos = reinterpret_cast<int *>(ex.e_smem + ex_cap);
-  ex.list_cap = ex_cap / 17 + 1;
-  ex.lists = reinterpret_cast<uint2 *>(ex.pos + ex_cap);
-  ex.isb = &s_isb;
   const int ring = blockIdx.x, b = blockIdx.y;
   const int br = b * R + ring;
   const size_t base = (size_t)b * RC;
@@ -447,8 +441,34 @@ lo_less_flat_voxel_kernel(const float4 *__restrict__ seg_cloud, const int *__res
     }
     return m && lab[i] <= 0;
   };
-  const int n_out = block_voxel_grid8<LFV_WARPS, true>(pts, max(end - start, 0), member, leaf, keys_a + base + lo, keys_b + base + lo, out,
-                                                       &sh, s_member, s_chunk_base, &ex);
+  const bool done = block_voxel_keys<LFV_WARPS, true>(pts, max(end - start, 0), member, leaf, keys_a + base + lo, out, &sh, s_member,
+                                                      s_chunk_base);
+  if (threadIdx.x == 0) {
+    VoxState st;
+    st.frame = sh.frame;
+    st.n = max(sh.n, 0);
+    st.nv = sh.nv;
+    st.done = done ? 1 : 0;
+    st.off = st.off_b = (long long)(base + lo);
+    state[br] = st;
+  }
+}
+
+__global__ void __launch_bounds__(LFV_WARPS * 32)
+lo_lfv_finish_kernel(const float4 *__restrict__ seg_cloud, const int *__restrict__ start_ring, float4 *__restrict__ lf_stage,
+                     int *__restrict__ ring_feat_cnt, u64 *__restrict__ keys_a, u64 *__restrict__ keys_b,
+                     const VoxState *__restrict__ state, float4 *__restrict__ az_stage, int *__restrict__ az_off, int R, int RC) {
+  __shared__ VoxShared<LFV_WARPS> sh;
+  const int ring = blockIdx.x, b = blockIdx.y;
+  const int br = b * R + ring;
+  const size_t base = (size_t)b * RC;
+  const int start = start_ring[br];
+  const int lo = max(start - 5, 0);
+  const float4 *pts = seg_cloud + base + start;
+  float4 *out = lf_stage + base + lo;
+  const VoxState st = state[br];
+  const int n_out = st.done ? st.n : block_voxel_finish<LFV_WARPS>(pts, keys_a + base + lo, keys_b + base + lo, out, &sh, st.n, st.nv,
+                                                                    st.frame.key_bits);
   if (threadIdx.x == 0) ring_feat_cnt[br * 4 + 3] = n_out;
   // ---- azimuth bins of the ring's output
   int *azo = az_off + (size_t)br * (AZ_BINS + 1);
@@ -551,20 +571,14 @@ int lo_extract_device(AlegoHandle *h) {
     lo_select_kernel<<<dim3(div_up(R, SEL_WARPS), B), SEL_WARPS * 32, (size_t)SEL_WARPS * pkcap, s>>>(
         h->seg_col, h->seg_ground, h->curv, h->sort_idx, h->start_ring, h->end_ring, h->picked0, h->picked, h->flabel,
         h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, R, RC, pkcap); }
-  // dynamic shared memory of the exact record order: C records (8 B) + C positions (4 B) + 4 range lists
-  const int ex_cap = (C + 3) & ~3;
-  const size_t lfv_smem = (size_t)ex_cap * 12 + (size_t)4 * (ex_cap / 17 + 1) * sizeof(uint2);
-  if (lfv_smem > 40 * 1024) {
-    static bool lfv_attr[ALEGO_MAX_DEVICES] = {};
-    if (!lfv_attr[h->dev]) {
-      CUDA_TRY(h, cudaFuncSetAttribute(lo_less_flat_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      lfv_attr[h->dev] = true;
-    }
-  }
-  { LAUNCH(h, "lo_less_flat_voxel");
-    lo_less_flat_voxel_kernel<<<dim3(R, B), LFV_WARPS * 32, lfv_smem, s>>>(
-        h->seg_cloud, h->flabel, h->start_ring, h->end_ring, h->lf_stage, h->ring_feat_cnt, h->sort_scratch, h->lfv_keys, h->az_stage,
-        h->az_off[h->cur], R, RC, (float)h->P.less_flat_leaf, ex_cap); }
+  { LAUNCH(h, "lo_lfv_keys");
+    lo_lfv_keys_kernel<<<dim3(R, B), LFV_WARPS * 32, 0, s>>>(h->seg_cloud, h->flabel, h->start_ring, h->end_ring, h->lf_stage,
+                                                             h->sort_scratch, h->lfv_state, R, RC, (float)h->P.less_flat_leaf); }
+  const int rc_q = vox_order_lists_by_warp(h, h->lfv_state, B * R, h->sort_scratch, h->lfv_keys, s, "lo_lfv_order");
+  if (rc_q != ALEGO_OK) return rc_q;
+  { LAUNCH(h, "lo_lfv_finish");
+    lo_lfv_finish_kernel<<<dim3(R, B), LFV_WARPS * 32, 0, s>>>(h->seg_cloud, h->start_ring, h->lf_stage, h->ring_feat_cnt, h->sort_scratch,
+                                                               h->lfv_keys, h->lfv_state, h->az_stage, h->az_off[h->cur], R, RC); }
   const int cur = h->cur;
   { LAUNCH(h, "lo_finalize");
     lo_finalize_kernel<<<dim3(R, B), 128, 0, s>>>(h->seg_cloud, h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat,

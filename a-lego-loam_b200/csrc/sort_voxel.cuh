@@ -48,6 +48,7 @@ struct VoxExact {
   uint2 *lists;
   int list_cap;
   IsbShared *isb;
+  unsigned short *wpos;  // optional shared memory: (warps of the CTA) x ISB_REG swap positions of short ranges
 };
 
 template <int NW>
@@ -267,13 +268,23 @@ __device__ __forceinline__ int warp_vox_centroids(const u64 *keys, int lo, int h
   return runs;
 }
 
-// Block-wide VoxelGrid of the points {pts[i] : i < n_src, member(i)} in ascending i.  MASKED = false: every i < n_src
-// takes part (member is not called).  MASKED = true: member_bits / chunk_base are ceil(n_src/32) words of shared memory.
-// ka / kb: two buffers of (number of members) words in global memory.  out: room for as many points.  Returns the number
-// of output points (same value in every thread).  All threads of the block (NW warps) must call.
+// What the key stage of a VoxelGrid leaves for the later stages when they run in separate kernels (per cloud)
+struct VoxState {
+  VoxFrame frame;
+  int n;      // records in the list
+  int nv;     // records with a finite point (nv == n: the list holds no pad keys)
+  int done;   // 1: the output is already final (empty input, or PCL's "leaf size too small" pass-through), n_out = n
+  long long off;    // where the cloud's record list starts in the batch-wide key buffer A ...
+  long long off_b;  // ... and its scratch (the second ping-pong buffer) in buffer B
+};
+
+// Stage 1 of the block-wide VoxelGrid of the points {pts[i] : i < n_src, member(i)} in ascending i: membership, bounding box,
+// (voxel key, input position) records into ka.  MASKED = false: every i < n_src takes part (member is not called).  MASKED = true:
+// member_bits / chunk_base are ceil(n_src/32) words of shared memory.  Returns through sh: frame, n, nv; the function result is
+// true when the output is already final (see VoxState::done; out then holds sh->n points).  All threads of the block must call.
 template <int NW, bool MASKED, class Member>
-__device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Member member, float leaf, u64 *ka, u64 *kb, float4 *out,
-                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base, const VoxExact *ex = nullptr) {
+__device__ bool block_voxel_keys(const float4 *__restrict__ pts, int n_src, Member member, float leaf, u64 *ka, float4 *out,
+                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nch = (n_src + 31) >> 5;
@@ -327,11 +338,12 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
         for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], sh->red[ww][a]); mx[a] = fmaxf(mx[a], sh->red[ww][3 + a]); }
       sh->frame = vox_frame(mn, mx, leaf);
       sh->n = n;
+      sh->nv = n;
     }
   }
   __syncthreads();
   const int n = sh->n;
-  if (n <= 0) return 0;
+  if (n <= 0) return true;
   const VoxFrame frame = sh->frame;
   if (frame.overflow) {  // "leaf size is too small": output = input
     for (int ch = w; ch < nch; ch += NW) {
@@ -344,12 +356,10 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
       }
     }
     __syncthreads();
-    return n;
+    return true;
   }
   // ---- (voxel key, input position) words; non-finite points get the key one past the last voxel and sort to the end
   const unsigned pad_key = (unsigned)frame.n_cells;
-  const bool in_smem = ex && ex->e_smem && n <= ex->e_cap;
-  if (in_smem) ka = ex->e_smem;  // the list lives in shared memory while it is partitioned (and for the first radix pass)
   int nfin = 0;
   for (int ch = w; ch < nch; ch += NW) {
     const int i = ch * 32 + lane;
@@ -379,22 +389,16 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
     sh->nv = s;
   }
   __syncthreads();
-  const int nv = sh->nv;
-  // ---- std::sort's record order = its partition phase, then a stable sort by key (see introsort_block.cuh)
-  if (ex && nv == n) {
-    int *pos = ex->pos;
-    uint2 *lists = ex->lists;
-    int list_cap = ex->list_cap;
-    if (!pos) {  // carve the scratch out of the idle second key buffer: n ints, then 4 lists of n / 17 + 1 ranges
-      pos = reinterpret_cast<int *>(kb);
-      lists = reinterpret_cast<uint2 *>(kb + (n + 1) / 2);
-      list_cap = n / 17 + 1;
-    }
-    block_introsort_partitions<NW>(ka, pos, n, lists, list_cap, ex->isb);
-    __syncthreads();
-  }
-  // ---- stable sort by voxel key
-  const u64 *keys = block_radix_sort8<NW>(ka, kb, n, frame.key_bits, sh);
+  return false;
+}
+
+// Stage 3: stable sort of the records by voxel key, then one centroid per run, in key order.  n / nv / frame as left by the key
+// stage.  Returns the number of output points (same value in every thread).  All threads of the block must call.
+template <int NW>
+__device__ int block_voxel_finish(const float4 *__restrict__ pts, u64 *ka, u64 *kb, float4 *out, VoxShared<NW> *sh, int n, int nv,
+                                  int key_bits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u64 *keys = block_radix_sort8<NW>(ka, kb, n, key_bits, sh);
   // ---- centroids: every warp counts the runs that start in its slice, then writes them behind those of the warps before
   int lo, hi;
   vox_slice<NW>(nv, w, lo, hi);
@@ -410,4 +414,64 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
   warp_vox_centroids(keys, lo, hi, nv, pts, out, before, sh->win_key[w], sh->win_pt[w], false);
   __syncthreads();
   return total;
+}
+
+// Does any voxel of the record list hold three or more points?  Only then does the order of the records inside a voxel matter:
+// a float sum of one or two terms (starting from 0.f) is the same in either order.  Open-addressing table of 2n (key + 1, count)
+// slots in `table` (16n bytes of scratch: the output buffer, idle until the centroid stage).  All threads of the block must call.
+template <int NW>
+__device__ bool block_any_voxel_ge3(const u64 *keys, int n, u64 *table, int *flag_smem) {
+  const unsigned T = 2u * (unsigned)n;
+  if (threadIdx.x == 0) *flag_smem = 0;
+  for (unsigned t = threadIdx.x; t < T; t += NW * 32) table[t] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += NW * 32) {
+    const unsigned key1 = (unsigned)(keys[i] >> 32) + 1u;
+    unsigned s = (unsigned)(((u64)(key1 * 2654435761u) * T) >> 32);
+    for (unsigned probe = 0; probe < T; ++probe) {
+      u64 cur = *reinterpret_cast<volatile u64 *>(table + s);
+      if ((unsigned)(cur >> 32) == 0u) {
+        const u64 old = atomicCAS(table + s, 0ull, ((u64)key1 << 32) | 1ull);
+        if (old == 0ull) break;
+        cur = old;
+      }
+      if ((unsigned)(cur >> 32) == key1) {
+        const u64 before = atomicAdd(table + s, 1ull);
+        if ((unsigned)(before & 0xffffffffu) + 1u >= 3u) *flag_smem = 1;
+        break;
+      }
+      s = s + 1u == T ? 0u : s + 1u;
+    }
+  }
+  __syncthreads();
+  return *flag_smem != 0;
+}
+
+// The whole VoxelGrid in one call (one CTA per cloud).  ka / kb: two buffers of (number of members) words in global memory.
+// out: room for as many points.  ex: scratch of the exact record order (stage 2 = introsort partition phase), or nullptr.
+template <int NW, bool MASKED, class Member>
+__device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Member member, float leaf, u64 *ka, u64 *kb, float4 *out,
+                                 VoxShared<NW> *sh, unsigned *member_bits, int *chunk_base, const VoxExact *ex = nullptr) {
+  if (block_voxel_keys<NW, MASKED>(pts, n_src, member, leaf, ka, out, sh, member_bits, chunk_base)) return max(sh->n, 0);
+  const int n = sh->n, nv = sh->nv;
+  u64 *list = ka;
+  // ---- std::sort's record order = its partition phase, then a stable sort by key (see introsort_block.cuh)
+  if (ex && nv == n && n > 16) {
+    if (ex->e_smem && n <= ex->e_cap) {  // partition in shared memory (the first radix pass then reads it from there)
+      for (int t = threadIdx.x; t < n; t += NW * 32) ex->e_smem[t] = ka[t];
+      __syncthreads();
+      list = ex->e_smem;
+    }
+    int *pos = ex->pos;
+    uint2 *lists = ex->lists;
+    int list_cap = ex->list_cap;
+    if (!pos) {  // carve the scratch out of the idle second key buffer: n ints, then 4 lists of n / 17 + 1 ranges
+      pos = reinterpret_cast<int *>(kb);
+      lists = reinterpret_cast<uint2 *>(kb + (n + 1) / 2);
+      list_cap = n / 17 + 1;
+    }
+    block_introsort_partitions<NW>(list, pos, n, lists, list_cap, ex->isb, ex->wpos);
+    __syncthreads();
+  }
+  return block_voxel_finish<NW>(pts, list, kb, out, sh, n, nv, sh->frame.key_bits);
 }

@@ -1,0 +1,9 @@
+// vox_order.cuh — host entry points of the batch record-ordering kernels (vox_order.cu)
+#pragma once
+#include "common.cuh"
+#include "sort_voxel.cuh"
+
+// partition every list that needs it (state[i].done == 0, no pad keys, more than 16 records): records of list i start at
+// buf_a + state[i].off, its scratch (as many ints) at buf_b + state[i].off_b
+int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag);
+int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag);

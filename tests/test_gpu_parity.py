@@ -243,7 +243,7 @@ def test_idempotent_and_batch_independent(alego):
     g.close()
 
 
-@pytest.mark.parametrize("n,leaf", [(1, 0.4), (17, 0.4), (5000, 0.4), (5000, 0.8), (40000, 0.8), (70000, 1.0)])
+@pytest.mark.parametrize("n,leaf", [(1, 0.4), (17, 0.4), (33, 2.0), (600, 1.5), (5000, 0.4), (5000, 0.8), (5000, 3.0), (40000, 0.8), (70000, 1.0), (70000, 4.0)])
 def test_voxel_grid(alego, ob, n, leaf):
     rng = np.random.default_rng(n)
     pts = np.zeros((n, 4), np.float32)
@@ -255,8 +255,11 @@ def test_voxel_grid(alego, ob, n, leaf):
     out = g.voxel_grid(pts, leaf)
     ref_stable, _ = ob.voxel_grid(pts, leaf, stable=True)
     ref_pcl, _ = ob.voxel_grid(pts, leaf, stable=False)
-    assert np.array_equal(out, ref_stable), first_diff(out, ref_stable)
-    assert out.shape == ref_pcl.shape and np.allclose(out, ref_pcl, rtol=0, atol=2e-5)
+    # PCL's record order (std::sort on the voxel index alone): the float sums inside a voxel follow introsort's permutation
+    assert np.array_equal(out, ref_pcl), first_diff(out, ref_pcl)
+    assert out.shape == ref_stable.shape and np.allclose(out, ref_stable, rtol=0, atol=2e-5 if leaf < 2.0 else 5e-4)
+    if n >= 40000:
+        assert not np.array_equal(ref_pcl, ref_stable)  # the case does distinguish the two orders
     # tiny leaf on a wide cloud: PCL's overflow guard returns the input unchanged
     if n == 5000 and leaf == 0.4:
         wide = pts.copy()
