@@ -205,7 +205,7 @@ _DEBUG_DTYPES = {
     "lm_params": np.float64, "lm_corner_ds": np.float32, "lm_surf_ds": np.float32, "lm_outlier_ds": np.float32,
     "lm_surf_total_ds": np.float32, "lm_edge": np.float64, "lm_plane": np.float64, "t_map2laser": np.float64,
     "r_map2laser": np.float64, "t_map2odom": np.float64, "r_map2odom": np.float64,
-    "lm_report": np.uint8, "lo_report": np.uint8,
+    "lm_report": np.uint8, "lo_report": np.uint8, "map_index_kind": np.int32,
 }
 _DEBUG_COLS = {"full_cloud": 4, "segmented_cloud": 4, "outlier_cloud": 4, "sharp": 4, "flat": 4, "less_sharp": 4, "less_flat": 4,
                "corner_last": 4, "surf_last": 4, "lo_surf_corr": 4, "lo_corner_corr": 3, "lo_trace": 7, "lm_trace": 7,

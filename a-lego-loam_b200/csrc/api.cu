@@ -11,6 +11,7 @@
 #include "grid.cuh"
 #include "ip_kernels.cuh"
 #include "lm_kernels.cuh"
+#include "map_rows.cuh"
 #include "lo_kernels.cuh"
 
 namespace {
@@ -62,6 +63,18 @@ int join_side(AlegoHandle *h) {
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side_tail, 0));
   h->side_busy = false;
   return ALEGO_OK;
+}
+
+// LaserMapping's lazily sized buffers, and — once per map change, with the side stream joined — the decision whether the surf map
+// can use the voxel-row index (map_rows.cuh); both outside any stream capture
+static int lm_ready(AlegoHandle *h) {
+  int rc = lm_ensure_buffers(h, 0, 0, 0);
+  if (rc != ALEGO_OK) return rc;
+  if (!h->map_rows_checked && h->map_surf) {
+    if ((rc = join_side(h)) != ALEGO_OK) return rc;
+    rc = lm_validate_map_rows(h);
+  }
+  return rc;
 }
 
 int d2h(AlegoHandle *h, void *dst, const void *src, size_t bytes) {
@@ -332,6 +345,7 @@ void alego_destroy(AlegoHandle *h) {
   grid_free(&h->g_corner_last);
   grid_free(&h->g_map_corner);
   grid_free(&h->g_map_surf);
+  map_rows_free(&h->rows_map_surf);
   grid_free(&h->g_icp);
   if (h->h_pose) cudaFreeHost(h->h_pose);
   for (auto &k : h->prof)
@@ -643,6 +657,7 @@ int alego_lm_set_map(AlegoHandle *h, int seq, const float *corner_xyzi, int32_t 
   CUDA_TRY(h, cudaMemcpyAsync(h->n_map_surf + seq, &n_surf, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->map_index_valid = false;
+  h->map_rows_checked = false;
   return ALEGO_OK;
 }
 
@@ -712,6 +727,7 @@ int alego_lm_assemble_map(AlegoHandle *h, int seq, int n_keyframes, const float 
   if ((rc = lm_assemble_cloud(h, sp.data(), sn.data(), 2 * K, M.data(), std::max(K, 1), 1, (float)h->P.lm_surf_leaf,
                               h->map_surf + (size_t)seq * h->map_cap_s, h->n_map_surf + seq)) != ALEGO_OK) return rc;
   h->map_index_valid = false;
+  h->map_rows_checked = false;
   return ALEGO_OK;
 }
 
@@ -789,7 +805,7 @@ int alego_lm_scan2map(AlegoHandle *h, AlegoSolveReport *reports) {
   if (!h) return ALEGO_BAD_ARG;
   CUDA_TRY(h, cudaSetDevice(h->dev));
   if (join_side(h) != ALEGO_OK) return ALEGO_CUDA_ERROR;
-  int rc = lm_ensure_buffers(h, 0, 0, 0);
+  int rc = lm_ready(h);
   if (rc != ALEGO_OK) return rc;
   rc = lm_scan2map_device(h, h->lm_guard, true, false);
   if (rc != ALEGO_OK) return rc;
@@ -880,7 +896,7 @@ static int pipeline_enqueue(AlegoHandle *h, cudaEvent_t consumed_ev = nullptr) {
   const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
   const bool overlap = h->overlap_lm && !h->profiling;
   const int par = h->cur;  // buffer parity of this sweep's clouds
-  if (!cap && run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
+  if (!cap && run_lm && (rc = lm_ready(h)) != ALEGO_OK) return rc;
   // ---- front end (main stream)
   if (cap) {
     if (overlap) {
@@ -953,7 +969,7 @@ static int pipeline_enqueue_graph(AlegoHandle *h) {
   for (auto v : h->lm_scan_is_external) any_ext |= v != 0;
   const bool run_lm = h->lm_every > 0 && h->map_corner && h->map_surf && (h->scan_count % h->lm_every == 0);
   if (any_ext || h->profiling || h->scan_count < 2) return pipeline_enqueue(h);  // first sweeps (lazy set-up) run eagerly
-  if (run_lm && (rc = lm_ensure_buffers(h, 0, 0, 0)) != ALEGO_OK) return rc;
+  if (run_lm && (rc = lm_ready(h)) != ALEGO_OK) return rc;
   if ((rc = join_side(h)) != ALEGO_OK) return rc;
   if (h->graphs_epoch != h->graph_epoch || h->graphs.size() > 64) drop_graphs(h);
   const int par = h->cur;
@@ -1187,6 +1203,11 @@ int64_t alego_debug_get(AlegoHandle *h, const char *name, int seq, void *dst, si
     from_pose = true;
     if (s[0] == 't') { std::memcpy(pose_buf, pose.t, 24); bytes = 24; }
     else { std::memcpy(pose_buf, pose.R, 72); bytes = 72; }
+  } else if (s == "map_index_kind") {  // 1: the surf map is searched through the voxel-row index, 0: through the hashed grid
+    const int kind = h->map_rows_checked && h->rows_map_surf.usable ? 1 : 0;
+    std::memcpy(pose_buf, &kind, sizeof kind);
+    from_pose = true;
+    bytes = sizeof kind;
   } else {
     h->err = "unknown debug array: " + s;
     return ALEGO_BAD_ARG;

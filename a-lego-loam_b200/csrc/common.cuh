@@ -31,6 +31,25 @@ struct GridIndex {
   float4 *sorted = nullptr;   // [B][cap]  xyz + original index (int bits in .w)
 };
 
+// Voxel-row index over a local-map cloud that is pcl::VoxelGrid output (see map_rows.cuh)
+struct MapFrame {
+  float inv;      // 1 / leaf
+  int min_b[3];   // floor(min * inv) per axis
+  int dim[3];     // voxels per axis
+  int W;          // 32-voxel words per row
+  int valid;      // 1: the table describes the cloud (voxel order, one point per voxel, fits the table)
+  int n;
+};
+
+struct MapRows {
+  uint2 *tab = nullptr;      // [B][cap] x = occupancy mask of the word, y = index of its first point
+  MapFrame *frame = nullptr; // [B]
+  int *bbox = nullptr;       // [B][6] min xyz / max xyz as order-preserving ints
+  int cap = 0;               // entries per sequence
+  float leaf = 0.f;
+  bool usable = false;       // host: every sequence's cloud is in voxel order and fits (decided by map_rows_validate)
+};
+
 struct KernelProfile {
   std::string name;
   int64_t launches = 0;
@@ -181,6 +200,8 @@ struct AlegoHandle {
   float4 *map_corner = nullptr, *map_surf = nullptr;  // [B][cap]
   int *n_map_corner = nullptr, *n_map_surf = nullptr; // [B]
   GridIndex g_map_corner, g_map_surf;
+  MapRows rows_map_surf;          // voxel-row index of the surf map when it is pcl::VoxelGrid output (map_rows.cuh)
+  bool map_rows_checked = false;  // rows_map_surf.usable is up to date with the current map clouds
   bool map_index_valid = false;
   int lm_cap_c = 0, lm_cap_s = 0, lm_cap_o = 0;       // capacities of stand-alone inputs
   float4 *lm_in_corner = nullptr, *lm_in_surf = nullptr, *lm_in_outlier = nullptr;  // [B][cap]

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include "lm_kernels.cuh"
+#include "map_rows.cuh"
 #include "solver.cuh"
 #include "sort_voxel.cuh"
 #include "vox_order.cuh"
@@ -360,6 +361,64 @@ lm_knn_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict_
   }
 }
 
+// K14a/K15a over the voxel-row index (map_rows.cuh) of a map that is pcl::VoxelGrid output: same exact gated 5-NN, same
+// (distance, index) ranking — the index of a point is its position in the map cloud either way — but the candidates are read
+// in place: the rows (y, z voxel pairs) and x voxels that a point within the gate can occupy, found by voxel arithmetic with a
+// margin that covers float rounding of the coordinates (1.001 m for a 1 m gate).
+__global__ void __launch_bounds__(256, 4)
+lm_knn_rows_kernel(const float4 *__restrict__ query, int qcap, const int *__restrict__ lm_n, int n_slot, const float4 *__restrict__ map,
+                   int map_cap, const MapFrame *__restrict__ frame, const uint2 *__restrict__ tab, int tab_cap,
+                   const Pose *__restrict__ m2l, const int *__restrict__ guard, int *__restrict__ nn) {
+  const int b = blockIdx.y;
+  const int nq = min(lm_n[b * 8 + n_slot], qcap);
+  const MapFrame F = frame[b];
+  const bool ok = guard[b] != 0 && F.valid;
+  const Pose &P = m2l[b];
+  const float4 *mp = map + (size_t)b * map_cap;
+  const uint2 *t = tab + (size_t)b * tab_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+    int *o = nn + ((size_t)b * qcap + i) * 5;
+    if (!ok) { o[0] = -1; continue; }
+    const float4 cp = query[(size_t)b * qcap + i];
+    // pointAssociateToMap (laserMapping.h:187-194): double transform, float result
+    const float sx = (float)(P.R[0] * cp.x + P.R[1] * cp.y + P.R[2] * cp.z + P.t[0]);
+    const float sy = (float)(P.R[3] * cp.x + P.R[4] * cp.y + P.R[5] * cp.z + P.t[1]);
+    const float sz = (float)(P.R[6] * cp.x + P.R[7] * cp.y + P.R[8] * cp.z + P.t[2]);
+    float bd[5];
+    int bi[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { bd[k] = 3.402823466e+38f; bi[k] = 0x7fffffff; }
+    int found = 0;
+    const float G = 1.001f;
+    const int x0 = max(mr_voxel(sx - G, F.inv, F.min_b[0]), 0), x1 = min(mr_voxel(sx + G, F.inv, F.min_b[0]), F.dim[0] - 1);
+    const int y0 = max(mr_voxel(sy - G, F.inv, F.min_b[1]), 0), y1 = min(mr_voxel(sy + G, F.inv, F.min_b[1]), F.dim[1] - 1);
+    const int z0 = max(mr_voxel(sz - G, F.inv, F.min_b[2]), 0), z1 = min(mr_voxel(sz + G, F.inv, F.min_b[2]), F.dim[2] - 1);
+    if (x0 <= x1) {
+      const int w0 = x0 >> 5, w1 = x1 >> 5;
+      for (int iz = z0; iz <= z1; ++iz)
+        for (int iy = y0; iy <= y1; ++iy) {
+          const uint2 *row = t + (size_t)(iy + F.dim[1] * iz) * F.W;
+          for (int w = w0; w <= w1; ++w) {
+            const uint2 ent = row[w];
+            const int lo = w == w0 ? (x0 & 31) : 0, hi = w == w1 ? (x1 & 31) : 31;
+            unsigned m = ent.x & (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
+            while (m) {
+              const int bit = __ffs(m) - 1;
+              m &= m - 1;
+              const int idx = (int)ent.y + __popc(ent.x & ((1u << bit) - 1u));
+              const float4 p = mp[idx];
+              const float d = l2_simple(sx, sy, sz, p);
+              if (d < 1.0f) knn5_offer(d, idx, bd, bi, found);
+            }
+          }
+        }
+    }
+    if (found < 5) { o[0] = -1; continue; }  // point_dist_[4] < 1.0 (:376, :426)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) o[k] = bi[k];
+  }
+}
+
 // K14b/K15b: per query with 5 neighbours — line test (PCA) or plane fit in double; writes the residual block
 template <bool EDGE>
 __device__ __forceinline__ void lm_fit_one(const float4 *__restrict__ query, int qcap, const float4 *__restrict__ map, int map_cap,
@@ -581,10 +640,23 @@ static LmInputs make_inputs(AlegoHandle *h) {
   return in;
 }
 
+// Decide (once per map change, synchronising) whether the surf map can use the voxel-row index: it can when every sequence's
+// cloud is pcl::VoxelGrid output (one point per voxel, ascending voxel index) — what surf_from_map_ds_ is (laserMapping.cpp:316-319).
+int lm_validate_map_rows(AlegoHandle *h) {
+  if (h->map_rows_checked || !h->map_surf) return ALEGO_OK;
+  const int rc = map_rows_validate(h, &h->rows_map_surf, h->map_surf, (size_t)h->map_cap_s, h->n_map_surf, (float)h->P.lm_surf_leaf, "map_surf");
+  if (rc != ALEGO_OK) return rc;
+  h->map_rows_checked = true;
+  return ALEGO_OK;
+}
+
 int lm_build_map_index(AlegoHandle *h) {
   int rc = grid_build(h, &h->g_map_corner, h->map_corner, (size_t)h->map_cap_c, h->n_map_corner, 1, "map_corner");
   if (rc != ALEGO_OK) return rc;
-  rc = grid_build(h, &h->g_map_surf, h->map_surf, (size_t)h->map_cap_s, h->n_map_surf, 1, "map_surf");
+  if (h->map_rows_checked && h->rows_map_surf.usable)
+    rc = map_rows_build(h, &h->rows_map_surf, h->map_surf, (size_t)h->map_cap_s, h->n_map_surf, "map_surf");
+  else
+    rc = grid_build(h, &h->g_map_surf, h->map_surf, (size_t)h->map_cap_s, h->n_map_surf, 1, "map_surf");
   if (rc != ALEGO_OK) return rc;
   h->map_index_valid = true;
   return ALEGO_OK;
@@ -632,9 +704,15 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
   { LAUNCH(h, "lm_fit_corner");
     lm_fit_kernel<true><<<dim3(min(div_up(cc, 128), 64), B), 128, 0, s>>>(h->lm_corner_ds, cc, h->lm_n, 0, h->map_corner, h->map_cap_c,
                                                                   h->lm_nn_c, h->lm_edge, 10); }
-  { LAUNCH(h, "lm_knn_surf");
+  if (h->map_rows_checked && h->rows_map_surf.usable) {
+    LAUNCH(h, "lm_knn_surf");
+    lm_knn_rows_kernel<<<dim3(min(div_up(cs + co, 256), 32), B), 256, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf,
+        h->map_cap_s, h->rows_map_surf.frame, h->rows_map_surf.tab, h->rows_map_surf.cap, h->m2l, guard_dev, h->lm_nn_s);
+  } else {
+    LAUNCH(h, "lm_knn_surf");
     lm_knn_kernel<<<dim3(min(div_up(cs + co, 256), 32), B), 256, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->g_map_surf, h->m2l, guard_dev,
-                                                                h->lm_nn_s); }
+                                                                h->lm_nn_s);
+  }
   { LAUNCH(h, "lm_fit_surf");
     lm_fit_kernel<false><<<dim3(min(div_up(cs + co, 128), 64), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
                                                                        h->lm_nn_s, h->lm_plane, 8); }

@@ -4,6 +4,8 @@
 
 int lm_ensure_buffers(AlegoHandle *h, int need_c, int need_s, int need_o);
 int lm_build_map_index(AlegoHandle *h);                                     // laserMapping.cpp:356-357
+// once per map change (synchronises): can the surf map use the voxel-row index instead of the hashed grid?
+int lm_validate_map_rows(AlegoHandle *h);
 // index_ready: the caller has (re)built the local-map index already; launches go to h->launch_stream when it is set
 int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool index_ready);  // laserMapping.cpp:325-489
 int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float *out_xyzi, int *n_out);

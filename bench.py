@@ -58,9 +58,9 @@ def parse():
     ap.add_argument("--point-stride", type=int, default=3, choices=[3, 4],
                     help="floats per input point: 3 = packed x,y,z (the path never reads the sensor intensity), 4 = x,y,z,intensity")
     ap.add_argument("--map-order", default="voxel", choices=["voxel", "generator"],
-                    help="order of the local-map clouds: 'voxel' = ascending PCL VoxelGrid index (x fastest), the order of the "
-                         "reference's corner_from_map_ds_ / surf_from_map_ds_ (VoxelGrid outputs, laserMapping.cpp:316-319); "
-                         "'generator' = the synthetic generator's structure-by-structure order")
+                    help="structure of the local-map clouds: 'voxel' = pcl::VoxelGrid output (one point per occupied voxel, ascending "
+                         "voxel index, x fastest) like the reference's corner_from_map_ds_ / surf_from_map_ds_ (laserMapping.cpp:316-319); "
+                         "'generator' = the synthetic generator's structure-by-structure order, several points per voxel")
     ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the pass (launch-latency regime: few sequences per GPU)")
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -88,8 +88,10 @@ def config_block(args, P):
             "lo_iters": "%d surf + %d corner" % (P.lo_surf_iters, P.lo_corner_iters)}
 
 
-def voxel_order(cloud, leaf):
-    """Reorder a cloud the way pcl::VoxelGrid emits its output: ascending voxel index ijk0 + ijk1*dx + ijk2*dx*dy (stable)."""
+def voxel_grid_output(cloud, leaf, n_keep, seed):
+    """Give a cloud the structure of pcl::VoxelGrid OUTPUT — what the reference's corner_from_map_ds_ / surf_from_map_ds_ are
+    (laserMapping.cpp:316-319): exactly one point per occupied voxel, in ascending voxel index ijk0 + ijk1*dx + ijk2*dx*dy (x fastest).
+    The first point of every voxel is kept, then voxels are dropped at random (seeded) down to n_keep points."""
     if len(cloud) == 0:
         return cloud
     inv = np.float32(1.0) / np.float32(leaf)
@@ -97,7 +99,11 @@ def voxel_order(cloud, leaf):
     ijk -= ijk.min(axis=0)
     d = ijk.max(axis=0) + 1
     key = ijk[:, 0] + ijk[:, 1] * d[0] + ijk[:, 2] * d[0] * d[1]
-    return np.ascontiguousarray(cloud[np.argsort(key, kind="stable")])
+    _, first = np.unique(key, return_index=True)  # ascending key, first occurrence
+    if len(first) > n_keep:
+        first = np.sort(np.random.default_rng(seed).choice(first, n_keep, replace=False))
+        first = first[np.argsort(key[first], kind="stable")]
+    return np.ascontiguousarray(cloud[first])
 
 
 def make_sequences(alego, P, n_sweeps, n_corner, n_surf, ids=None, map_order="voxel"):
@@ -110,9 +116,12 @@ def make_sequences(alego, P, n_sweeps, n_corner, n_surf, ids=None, map_order="vo
         seed = sharding.sequence_seed(gid)
         w = alego.SynthWorld(seed=seed)
         sweeps = [w.render(P, alego.trajectory_pose(t, seed=seed), noise_seed=1000 * seed + t) for t in range(n_sweeps)]
-        corner, surf = w.make_map(n_corner, n_surf, seed=seed, radius=100.0)
-        if map_order == "voxel":
-            corner, surf = voxel_order(corner, P.lm_corner_leaf), voxel_order(surf, P.lm_surf_leaf)
+        if map_order == "voxel":  # over-generate, then one point per voxel (VoxelGrid output), exactly the requested sizes
+            corner, surf = w.make_map(int(n_corner * 1.5), int(n_surf * 1.6), seed=seed, radius=100.0)
+            corner = voxel_grid_output(corner, P.lm_corner_leaf, n_corner, seed)
+            surf = voxel_grid_output(surf, P.lm_surf_leaf, n_surf, seed + 1)
+        else:
+            corner, surf = w.make_map(n_corner, n_surf, seed=seed, radius=100.0)
         return {"id": gid, "sweeps": sweeps, "map_corner": corner, "map_surf": surf}
 
     with ThreadPoolExecutor(max_workers=min(len(ids), os.cpu_count() or 1)) as ex:  # the generator is C++ behind ctypes (no GIL)

@@ -326,13 +326,19 @@ def lm_standalone_case(alego, P, seed, n_corner, n_surf, offset):
     return w, corner_map, surf_map, scan
 
 
-@pytest.mark.parametrize("n_corner,n_surf,outer,iters", [(6000, 30000, 2, 20), (50000, 200000, 2, 20), (50000, 200000, 1, 10)])
-def test_scan_to_map_parity(alego, ob, n_corner, n_surf, outer, iters):
+@pytest.mark.parametrize("n_corner,n_surf,outer,iters,voxel_map", [(6000, 30000, 2, 20, False), (50000, 200000, 2, 20, False),
+                                                                   (50000, 200000, 1, 10, False), (6000, 30000, 2, 20, True),
+                                                                   (50000, 200000, 2, 20, True)])
+def test_scan_to_map_parity(alego, ob, n_corner, n_surf, outer, iters, voxel_map):
     """BASELINE config 3: LaserMapping scan-to-map against a 50k corner + 200k surf local map (and a small one); 2 x 20 LM
-    iterations as in the code (laserMapping.cpp:360,470) and the 10 iterations BASELINE.json quotes."""
+    iterations as in the code (laserMapping.cpp:360,470) and the 10 iterations BASELINE.json quotes.  voxel_map: the map clouds
+    are pcl::VoxelGrid outputs (one point per voxel, voxel order) like the reference's corner_from_map_ds_ / surf_from_map_ds_
+    (laserMapping.cpp:316-319) — the device then searches the surf map through its voxel-row index instead of the hashed grid."""
     P = alego.default_params(alego.PRESET_HDL64_1800)
     P.lm_outer_iters, P.lm_max_iters = outer, iters
     w, cm, sm, scan = lm_standalone_case(alego, P, 5, n_corner, n_surf, None)
+    if voxel_map:
+        cm, sm = ob.voxel_grid(cm, P.lm_corner_leaf)[0], ob.voxel_grid(sm, P.lm_surf_leaf)[0]
     # features of the sweep from the oracle front end, fed to both LaserMapping implementations
     o = ob.Oracle(P, stable_voxel=False)
     o.ip(scan)
@@ -356,6 +362,7 @@ def test_scan_to_map_parity(alego, ob, n_corner, n_surf, outer, iters):
         g.lm_set_params(b, x0)
     rc, rep = g.lm_scan2map()
     orep = o.report("lm")
+    assert int(g.debug("map_index_kind")[0]) == (1 if voxel_map else 0)
     for b in range(2):
         for k in ("lm_corner_ds", "lm_surf_ds", "lm_outlier_ds", "lm_surf_total_ds"):
             assert np.array_equal(g.debug(k, b), o.get(k)), k + ": " + first_diff(g.debug(k, b), o.get(k))
