@@ -185,6 +185,7 @@ int alego_create(const AlegoParams *p, int device, int n_seq, int max_points_per
   DMALLOC(h, h->range, B * RC);
   DMALLOC(h, h->ground, B * RC);
   DMALLOC(h, h->cell_flags, B * RC);
+  DMALLOC(h, h->cell_class, B * RC);
   DMALLOC(h, h->parent, B * RC);
   DMALLOC(h, h->comp_stat, B * RC);
   DMALLOC(h, h->comp_id, B * RC);
@@ -327,7 +328,7 @@ void alego_destroy(AlegoHandle *h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto p : h->stage_raw) cudaFree(p);
   for (auto p : h->stage_n) cudaFree(p);
-  void *ptrs[] = {h->raw_own, h->n_pts_own, h->winner, h->cloud, h->range, h->ground, h->cell_flags, h->parent, h->comp_stat,
+  void *ptrs[] = {h->raw_own, h->n_pts_own, h->winner, h->cloud, h->range, h->ground, h->cell_flags, h->cell_class, h->parent, h->comp_stat,
                   h->comp_id, h->label, h->rowcnt, h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring, h->end_ring,
                   h->M, h->outlier_buf[0], h->outlier_buf[1], h->n_outlier_buf[0], h->n_outlier_buf[1], h->o2l_lo[0], h->o2l_lo[1], h->orient, h->curv, h->picked0, h->picked, h->flabel, h->sort_idx, h->sort_scratch, h->lfv_keys, h->lfv_state, h->lmv_state,
                   h->ring_feat_cnt, h->ring_sharp, h->ring_less_sharp, h->ring_flat, h->sharp_idx, h->less_sharp_idx, h->flat_idx,

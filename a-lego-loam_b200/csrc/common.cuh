@@ -124,6 +124,7 @@ struct AlegoHandle {
   float *range = nullptr;      // [B][RC]  range_mat_ (f32 is lossless: the reference stores a float sqrt)
   uint8_t *ground = nullptr;   // [B][RC]  ground_mat_
   uint8_t *cell_flags = nullptr;  // [B][RC]  validity + join flags of every cell (ip_image -> ccl_*)
+  uint8_t *cell_class = nullptr;  // [B][RC] keep / outlier / feasible-root verdict of every cell (ip_rowcount -> ip_compact)
   int *parent = nullptr;       // [B][RC]  union-find forest; -1 = not a segmentation candidate
   int2 *comp_stat = nullptr;   // [B][RC]  at roots: (size, max row)
   int *comp_id = nullptr;      // [B][RC]  at roots: final label 1..K

@@ -136,6 +136,7 @@ __device__ __forceinline__ bool seg_join(float ra, float rb, bool horizontal, co
 #define CELL_GROUND 2
 #define CELL_JOIN_LEFT 4  // joined with the cell one column to the left (column 0: with column C-1, :241-248)
 #define CELL_JOIN_DOWN 8  // joined with the cell one row up in the image (row + 1)
+#define CELL_STRIP_ROOT 16  // set by ccl_strip: the cell is the root of its component inside its column strip
 
 // K1b + K2 + the join tests of K3 in one pass over the image.  A CTA owns a strip of IMG_W columns x all rows, staged in
 // shared memory together with the column to its left:
@@ -273,104 +274,159 @@ __device__ __forceinline__ void uf_unite(int *L, int a, int b) {
   } while (!done);
 }
 
-// inclusive block-wide max scan of one int per thread (smem: >= 33 ints); all threads must call
-__device__ __forceinline__ int block_incl_max_scan(int v, int *smem) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v = max(v, t);
-  }
-  __syncthreads();
-  if (lane == 31) smem[wid] = v;
-  __syncthreads();
-  if (wid == 0) {
-    int w = lane < nw ? smem[lane] : -0x7fffffff;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w = max(w, t);
-    }
-    smem[lane] = w;
-  }
-  __syncthreads();
-  return wid > 0 ? max(v, smem[wid - 1]) : v;
+// ---------------------------------------------------------------------------------------------------
+// labelComponents (:210-316) as connected components in SHARED MEMORY, strip by strip: one CTA owns all R rows of CCL_W
+// columns (R * CCL_W <= 4096 cells).  Inside the strip: per-row runs by a warp max-scan (no atomics), vertical joins by
+// union-find on 32-bit labels in shared memory, flatten, per-component size / highest row by shared-memory atomics.  What
+// leaves the CTA: parent[cell] = the strip-local root (global raster index: the smallest one of the component's cells in the
+// strip) and (size, highest row) at the roots.  ccl_seam then unites strip roots across the strip seams and the column wrap
+// (:241-248) — a few hundred joins per image — and hands every absorbed root's statistics to the root that survives, so a
+// final root is at most ONE hop from any cell's parent (ccl_root).  Nothing is resolved through global-memory pointer chasing.
+// ---------------------------------------------------------------------------------------------------
+#define CCL_CELLS 4096
+#define CCL_SMEM (CCL_CELLS * 13)
+// strip width: the largest power of two with R * W <= CCL_CELLS (>= 32), so that cell <-> (row, column) is shift and mask
+__host__ __device__ __forceinline__ int ccl_strip_shift(int R) {
+  int sh = 5;
+  while (sh < 12 && (R << (sh + 1)) <= CCL_CELLS) ++sh;
+  return sh;
 }
+__device__ __forceinline__ int ccl_strip_width(int R) { return 1 << ccl_strip_shift(R); }
 
-// Horizontal pass, one CTA per (ring, sequence): candidate mask (:134-143) and the horizontal joins of the ring.  A
-// ring decomposes into runs of cells each joined to its left neighbour; every cell is pointed at the first cell of its
-// run by a max-scan of the run-start columns — no atomics.  The column wrap (:241-248) links the last run to the first.
-__global__ void __launch_bounds__(256) ccl_rows_kernel(const uint8_t *__restrict__ flags, int *__restrict__ parent,
-                                                       int2 *__restrict__ comp_stat, IpDev P) {
-  const int b = blockIdx.y, row = blockIdx.x;
-  const size_t base = (size_t)b * P.RC + (size_t)row * P.C;
-  const uint8_t *fl = flags + base;
-  __shared__ int s_scan[34];
-  int carry = -1;  // run-start column inherited from the columns left of this chunk
-  for (int c0 = 0; c0 < P.C; c0 += blockDim.x) {
-    const int col = c0 + threadIdx.x;
-    bool valid = false, join_left = false;
-    if (col < P.C) {
-      const int f = fl[col];
-      valid = (f & CELL_VALID) != 0;
-      join_left = col > 0 && (f & CELL_JOIN_LEFT) != 0;
-      comp_stat[base + col] = make_int2(0, 0);
-    }
-    const int start = (valid && !join_left) ? col : -1;
-    const int run = max(block_incl_max_scan(start, s_scan), carry);
-    if (col < P.C) parent[base + col] = valid ? row * P.C + run : -1;
-    // the last thread of the chunk holds the max over the whole chunk
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_scan[33] = run;
-    __syncthreads();
-    carry = s_scan[33];
-  }
-  if (threadIdx.x == 0 && P.C > 1 && (fl[0] & CELL_JOIN_LEFT)) {  // column wrap: the last run of the ring joins the first
-    const int last_root = parent[base + P.C - 1];  // written by this CTA (same thread block: visible after the barrier)
-    if (last_root != row * P.C) parent[(size_t)b * P.RC + last_root] = row * P.C;
-  }
-}
-
-// Vertical pass: joins between a cell and the cell below it (rows do not wrap, :237) on the union-find forest
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t *__restrict__ flags, int *parent, IpDev P) {
-  const int b = blockIdx.y;
+__global__ void __launch_bounds__(256) ccl_strip_kernel(uint8_t *flags, int *__restrict__ parent, int2 *__restrict__ comp_stat, IpDev P) {
+  extern __shared__ __align__(16) unsigned char ccl_smem[];  // CCL_SMEM bytes
+  int *s_lab = reinterpret_cast<int *>(ccl_smem);
+  int *s_cnt = s_lab + CCL_CELLS;
+  int *s_mxr = s_cnt + CCL_CELLS;
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_mxr + CCL_CELLS);
+  const int b = blockIdx.y, WS = ccl_strip_shift(P.R), W = 1 << WS, c0 = blockIdx.x * W, w = min(W, P.C - c0), n = P.R * W;
   const size_t base = (size_t)b * P.RC;
-  int *L = parent + base;
-  const uint8_t *fl = flags + base;
-  const int n = P.RC - P.C;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < n; cell += gridDim.x * blockDim.x) {
-    const int f = fl[cell];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int r = idx >> WS, c = idx & (W - 1);
+    s_fl[idx] = c < w ? flags[base + (size_t)r * P.C + c0 + c] : 0;
+    s_cnt[idx] = 0;
+    s_mxr[idx] = 0;
+  }
+  __syncthreads();
+  // runs of every row: a cell joined to its left neighbour continues the run (the strip's first column starts one: the join
+  // across the seam is ccl_seam's)
+  for (int r = warp; r < P.R; r += (int)(blockDim.x >> 5)) {
+    int carry = -1;
+    for (int cc = 0; cc < W; cc += 32) {
+      const int c = cc + lane, f = s_fl[r * W + c];
+      const bool valid = (f & CELL_VALID) != 0, join_left = c > 0 && (f & CELL_JOIN_LEFT) != 0;
+      int run = (valid && !join_left) ? c : -1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run = max(run, t);
+      }
+      run = max(run, carry);
+      s_lab[r * W + c] = valid ? r * W + run : -1;
+      carry = __shfl_sync(0xffffffffu, run, 31);
+    }
+  }
+  __syncthreads();
+  // joins between a cell and the cell one row up in the image (rows do not wrap, :237)
+  for (int idx = threadIdx.x; idx < n - W; idx += blockDim.x) {
+    const int f = s_fl[idx];
     if (!(f & CELL_JOIN_DOWN)) continue;
-    // the two runs were already united by the cell to the left when that cell joins down too and both rows continue their
-    // runs into this column: only the first column of every (run, run) contact touches the forest
-    const int col = cell % P.C;
-    if (col > 0 && (f & CELL_JOIN_LEFT) && (fl[cell + P.C] & CELL_JOIN_LEFT) && (fl[cell - 1] & CELL_JOIN_DOWN)) continue;
-    uf_unite(L, cell, cell + P.C);
+    // two runs in contact along several columns: only the first column of the contact touches the forest
+    const int c = idx & (W - 1);
+    if (c > 0 && (f & CELL_JOIN_LEFT) && (s_fl[idx + W] & CELL_JOIN_LEFT) && (s_fl[idx - 1] & CELL_JOIN_DOWN)) continue;
+    uf_unite(s_lab, idx, idx + W);
   }
-}
-
-// flatten + per-component size and highest row (rows of a 4-connected component are contiguous, so the
-// number of distinct rows (:289-296) is max_row - row(root) + 1)
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int *parent, int2 *comp_stat, IpDev P) {
-  const int b = blockIdx.y;
-  const size_t base = (size_t)b * P.RC;
-  int *L = parent + base;
-  const int start = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int cell0 = start - threadIdx.x; cell0 < P.RC; cell0 += gridDim.x * blockDim.x) {
-    const int cell = cell0 + threadIdx.x;
-    int root = -1;
-    if (cell < P.RC && L[cell] >= 0) root = uf_find_compress(L, cell);
-    const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
-    if (root >= 0) {
-      const unsigned peers = __match_any_sync(active, root);
-      const int row = cell / P.C;
-      const int mx = __reduce_max_sync(peers, row);
-      if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
-        atomicAdd(&comp_stat[base + root].x, __popc(peers));
-        atomicMax(&comp_stat[base + root].y, mx);
+  __syncthreads();
+  // flatten by pointer jumping: the vertical joins chain the runs of a column row by row (up to R hops), so every cell chasing
+  // its own root would walk those chains serially; halving all paths together needs about log2(R) sweeps
+  {
+    bool changed;
+    do {
+      changed = false;
+      for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int l = s_lab[idx];
+        if (l < 0) continue;
+        const int ll = s_lab[l];
+        if (ll != l) { s_lab[idx] = ll; changed = true; }
+      }
+      changed = __syncthreads_or(changed) != 0;
+    } while (changed);
+  }
+  for (int idx0 = 0; idx0 < n; idx0 += blockDim.x) {  // whole warps take part in the match
+    const int idx = idx0 + threadIdx.x;
+    const int root = idx < n ? s_lab[idx] : -1;
+    // the cells a warp holds mostly share a component: one shared-memory atomic per (warp, component)
+    const unsigned peers = __match_any_sync(0xffffffffu, root);
+    if (root >= 0 && (peers & ((1u << lane) - 1u)) == 0u) {
+      atomicAdd(&s_cnt[root], __popc(peers));
+      atomicMax(&s_mxr[root], (idx | 31) >> WS);  // a warp's 32 cells share a row when W >= 32: its highest row
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int r = idx >> WS, c = idx & (W - 1);
+    if (c >= w) continue;
+    const size_t cell = base + (size_t)r * P.C + c0 + c;
+    const int lab = s_lab[idx];
+    int g = -1;
+    if (lab >= 0) {
+      const int root = lab;  // flattened above
+      g = (root >> WS) * P.C + c0 + (root & (W - 1));
+      if (root == idx) {
+        comp_stat[cell] = make_int2(s_cnt[idx], s_mxr[idx]);
+        flags[cell] = (uint8_t)(s_fl[idx] | CELL_STRIP_ROOT);
       }
     }
+    parent[cell] = g;
   }
+}
+
+// joins across the strip seams and the column wrap: one CTA per image.  Only strip roots are linked (their entries of parent[]).
+__global__ void __launch_bounds__(256) ccl_seam_kernel(const uint8_t *__restrict__ flags, int *parent, int2 *comp_stat, IpDev P) {
+  const int b = blockIdx.x, W = ccl_strip_width(P.R);
+  const size_t base = (size_t)b * P.RC;
+  int *L = parent + base;
+  int2 *S = comp_stat + base;
+  const uint8_t *fl = flags + base;
+  const int n_seams = (P.C + W - 1) / W;  // seam 0 = the wrap between column C-1 and column 0
+  const int n_edges = P.C > 1 ? n_seams * P.R : 0;
+  for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+    const int s = e / P.R, r = e - s * P.R;
+    const int col = s * W, left = col == 0 ? P.C - 1 : col - 1;
+    if (fl[r * P.C + col] & CELL_JOIN_LEFT) uf_unite(L, L[r * P.C + col], L[r * P.C + left]);
+  }
+  __syncthreads();
+  // every strip root that was absorbed: point it straight at the surviving root and hand over its statistics (once)
+  for (int e = threadIdx.x; e < 2 * n_edges; e += blockDim.x) {
+    const int ee = e >> 1, s = ee / P.R, r = ee - s * P.R;
+    const int col = s * W, left = col == 0 ? P.C - 1 : col - 1;
+    if (!(fl[r * P.C + col] & CELL_JOIN_LEFT)) continue;
+    const int cell = r * P.C + ((e & 1) ? left : col);
+    const int x = (fl[cell] & CELL_STRIP_ROOT) ? cell : L[cell];  // a non-root cell still points at its strip root
+    const int f = uf_find(L, x);
+    if (f == x) continue;
+    L[x] = f;
+    const int old = atomicExch(&S[x].x, 0);
+    if (old > 0) {
+      atomicAdd(&S[f].x, old);
+      atomicMax(&S[f].y, S[x].y);
+    }
+  }
+}
+
+// final root of a cell's component: its strip root, or what ccl_seam pointed that root at
+__device__ __forceinline__ int ccl_root(const int *L, int cell) {
+  int root = L[cell];
+  if (root >= 0) {
+    const int up = L[root];
+    if (up != root) {
+      root = up;
+      int up2 = L[root];
+      while (up2 != root) { root = up2; up2 = L[root]; }  // only when a hand-over has not been flattened (never after ccl_seam)
+    }
+  }
+  return root;
 }
 
 struct CellClass {
@@ -379,7 +435,7 @@ struct CellClass {
 __device__ __forceinline__ CellClass classify(int cell, int row, int col, const int *L, const int2 *stat, const uint8_t *gr,
                                               const IpDev &P) {
   CellClass c;
-  const int root = L[cell];
+  const int root = ccl_root(L, cell);
   c.valid = root >= 0;
   c.feasible = false;
   if (c.valid) {
@@ -396,7 +452,8 @@ __device__ __forceinline__ CellClass classify(int cell, int row, int col, const 
 }
 
 __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat,
-                                                          const uint8_t *__restrict__ ground, int4 *__restrict__ rowcnt,
+                                                          const uint8_t *__restrict__ ground, uint8_t *__restrict__ cell_class,
+                                                          int4 *__restrict__ rowcnt,
                                                           const float *__restrict__ raw, int stride, const int *__restrict__ n_pts,
                                                           float *orient, int Nmax, IpDev P) {
   const int b = blockIdx.y, row = blockIdx.x;
@@ -404,6 +461,8 @@ __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict_
   int nk = 0, no = 0, nr = 0;
   for (int col = threadIdx.x; col < P.C; col += blockDim.x) {
     const CellClass c = classify(row * P.C + col, row, col, parent + base, comp_stat + base, ground + base, P);
+    // the compaction kernel reads the verdict back instead of classifying every cell two more times
+    cell_class[base + row * P.C + col] = (uint8_t)((c.keep ? 1 : 0) | (c.outl ? 2 : 0) | (c.rootflag ? 4 : 0));
     nk += c.keep;
     no += c.outl;
     nr += c.rootflag;
@@ -453,8 +512,7 @@ __global__ void __launch_bounds__(256) ip_rowcount_kernel(const int *__restrict_
 }
 
 __global__ void __launch_bounds__(256)
-ip_compact_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_stat, const uint8_t *__restrict__ ground,
-                  const int4 *__restrict__ rowcnt, const float4 *__restrict__ cloud, const float *__restrict__ range,
+ip_compact_kernel(const uint8_t *__restrict__ cell_class, const uint8_t *__restrict__ ground, const int4 *__restrict__ rowcnt, const float4 *__restrict__ cloud, const float *__restrict__ range,
                   int *__restrict__ comp_id, float4 *__restrict__ seg_cloud, uint8_t *__restrict__ seg_ground,
                   int *__restrict__ seg_col, float *__restrict__ seg_range, int *__restrict__ start_ring,
                   int *__restrict__ end_ring, int *__restrict__ Mout, float4 *__restrict__ outlier, int *__restrict__ n_outlier,
@@ -482,16 +540,17 @@ ip_compact_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_
     }
   }
   __syncthreads();
-  // every thread owns `per` consecutive columns: count, ONE block scan for the whole ring, then the ordered writes (the
-  // classification is evaluated twice — cached loads — instead of scanning the ring in eight 256-column chunks)
+  // every thread owns `per` consecutive columns: count, ONE block scan for the whole ring, then the ordered writes (the class
+  // bytes ip_rowcount left are read twice — cached loads — instead of scanning the ring in eight 256-column chunks)
   const int per = (P.C + (int)blockDim.x - 1) / (int)blockDim.x;
   const int c_lo = min((int)threadIdx.x * per, P.C), c_hi = min(c_lo + per, P.C);
   int nk = 0, no = 0, nr = 0;
+  const uint8_t *cls = cell_class + base + (size_t)row * P.C;
   for (int col = c_lo; col < c_hi; ++col) {
-    const CellClass c = classify(row * P.C + col, row, col, parent + base, comp_stat + base, ground + base, P);
-    nk += c.keep;
-    no += c.outl;
-    nr += c.rootflag;
+    const int c = cls[col];
+    nk += c & 1;
+    no += (c >> 1) & 1;
+    nr += (c >> 2) & 1;
   }
   int total;
   const int ex_ko = block_excl_scan(nk | (no << 16), s_scan, &total);  // a ring holds < 65536 cells
@@ -499,19 +558,19 @@ ip_compact_kernel(const int *__restrict__ parent, const int2 *__restrict__ comp_
   int dk = s_base[0] + (ex_ko & 0xffff), dout = s_base[1] + (ex_ko >> 16), dr = s_base[2] + ex_r;
   for (int col = c_lo; col < c_hi; ++col) {
     const int cell = row * P.C + col;
-    const CellClass c = classify(cell, row, col, parent + base, comp_stat + base, ground + base, P);
-    if (c.keep) {
+    const int c = cls[col];
+    if (c & 1) {
       seg_cloud[base + dk] = cloud[base + cell];
       seg_ground[base + dk] = ground[base + cell] == 1;  // (:183)
       seg_col[base + dk] = col;                          // (:184)
       seg_range[base + dk] = range[base + cell];         // (:185)
       ++dk;
     }
-    if (c.outl) {
+    if (c & 2) {
       if (dout < out_cap) outlier[(size_t)b * out_cap + dout] = cloud[base + cell];
       ++dout;
     }
-    if (c.rootflag) comp_id[base + cell] = ++dr;  // label_cnt_ in raster-seed order (:303-306)
+    if (c & 4) comp_id[base + cell] = ++dr;  // label_cnt_ in raster-seed order (:303-306)
   }
 }
 
@@ -520,7 +579,7 @@ __global__ void __launch_bounds__(256) ip_label_kernel(const int *__restrict__ p
   const int b = blockIdx.y;
   const size_t base = (size_t)b * P.RC;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P.RC; cell += gridDim.x * blockDim.x) {
-    const int root = parent[base + cell];
+    const int root = ccl_root(parent + base, cell);
     int lab = -1;
     if (root >= 0) {
       const int2 s = comp_stat[base + root];
@@ -577,14 +636,19 @@ int ip_run_device(AlegoHandle *h, bool want_labels) {
   // the winner image is consumed: empty it for the next sweep (a cell is reset by memset rather than by its reader because the
   // neighbouring strip reads it too)
   CUDA_TRY(h, cudaMemsetAsync(h->winner, 0xFF, (size_t)B * h->RC * sizeof(int), s));
-  { LAUNCH(h, "ccl_rows"); ccl_rows_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->cell_flags, h->parent, h->comp_stat, P); }
-  { LAUNCH(h, "ccl_merge"); ccl_merge_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->cell_flags, h->parent, P); }
-  { LAUNCH(h, "ccl_flatten"); ccl_flatten_kernel<<<dim3(cell_blocks, B), 256, 0, s>>>(h->parent, h->comp_stat, P); }
+  const int ccl_w = 1 << ccl_strip_shift(P.R);
+  static bool ccl_attr_set[ALEGO_MAX_DEVICES] = {};
+  if (!ccl_attr_set[h->dev]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CCL_SMEM));
+    ccl_attr_set[h->dev] = true;
+  }
+  { LAUNCH(h, "ccl_strip"); ccl_strip_kernel<<<dim3(div_up(P.C, ccl_w), B), 256, CCL_SMEM, s>>>(h->cell_flags, h->parent, h->comp_stat, P); }
+  { LAUNCH(h, "ccl_seam"); ccl_seam_kernel<<<B, 256, 0, s>>>(h->cell_flags, h->parent, h->comp_stat, P); }
   { LAUNCH(h, "ip_rowcount");
-    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, reinterpret_cast<const float *>(h->raw), h->in_stride, h->n_pts, h->orient,
+    ip_rowcount_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->cell_class, h->rowcnt, reinterpret_cast<const float *>(h->raw), h->in_stride, h->n_pts, h->orient,
                                                    h->Nmax, P); }
   { LAUNCH(h, "ip_compact");
-    ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->parent, h->comp_stat, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,
+    ip_compact_kernel<<<dim3(P.R, B), 256, 0, s>>>(h->cell_class, h->ground, h->rowcnt, h->cloud, h->range, h->comp_id,
                                                   h->seg_cloud, h->seg_ground, h->seg_col, h->seg_range, h->start_ring,
                                                   h->end_ring, h->M, h->outlier, h->n_outlier, h->out_cap, P); }
   h->label_valid = false;

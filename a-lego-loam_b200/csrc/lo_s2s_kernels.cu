@@ -334,7 +334,11 @@ struct LoStagedSet {
   }
 };
 
-__global__ void __launch_bounds__(256)
+// 128 threads with the full register budget: two sequences per SM solve side by side, so a batch of 256 is one wave (a
+// scan-to-scan problem has a few hundred residual blocks; what costs is the latency of the serial trust-region logic, not the
+// sweep over the blocks — capping the registers at 128 for four CTAs per SM spilled and was slower)
+#define LO_SOLVE_THREADS 128
+__global__ void __launch_bounds__(LO_SOLVE_THREADS, 2)
 lo_solve_kernel(int phase, const float *__restrict__ surf_res, const int *__restrict__ surf_corr, const float *__restrict__ corner_res,
                 const int *__restrict__ corner_corr, const int *__restrict__ n_feat, double *lo_params, double *t_w, double *r_w,
                 int *lo_init, AlegoSolveReport *report, double *trace, int *trace_n, int trace_cap, int R, int surf_iters,
@@ -444,8 +448,9 @@ int lo_scan2scan_device(AlegoHandle *h) {
   cudaStream_t s = h->stream;
   const int cur = h->cur, prev = 1 - cur;
   const double gate = h->P.nearest_feature_dist, hub = h->P.huber_delta;
-  // shared-memory staging of the residual blocks: every surf (12 floats) and corner (9 floats) slot, capped at 200 KB
-  const size_t lo_stage_bytes = std::min<size_t>((size_t)R * (24 * 12 + 12 * 9) * sizeof(float), 200 * 1024);
+  // shared-memory staging of the valid residual blocks (surf 12 floats, corner 9 floats), capped at 48 KB so that four CTAs share
+  // an SM (a sweep with more correspondences than that is solved from global memory)
+  const size_t lo_stage_bytes = std::min<size_t>((size_t)R * (24 * 12 + 12 * 9) * sizeof(float), 48 * 1024);
   static bool lo_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
   if (!lo_attr_set[h->dev]) {
     CUDA_TRY(h, cudaFuncSetAttribute(lo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -457,7 +462,7 @@ int lo_scan2scan_device(AlegoHandle *h) {
         h->flat, R * 24, h->n_feat, h->less_flat[prev], (size_t)RC, h->lf_ring_off[prev], h->g_surf_last, h->lo_pose, h->lo_init,
         h->lo_surf_res, h->lo_surf_corr, R, gate, h->az_pts[prev], h->az_off[prev]); }
   { LAUNCH(h, "lo_solve_surf");
-    lo_solve_kernel<<<B, 256, lo_stage_bytes, s>>>(1, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
+    lo_solve_kernel<<<B, LO_SOLVE_THREADS, lo_stage_bytes, s>>>(1, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
                                       h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub, (int)(lo_stage_bytes / sizeof(float))); }
   { LAUNCH(h, "lo_pose"); lo_pose_kernel<<<div_up(B, 128), 128, 0, s>>>(h->lo_params, h->lo_pose, B); }
@@ -466,7 +471,7 @@ int lo_scan2scan_device(AlegoHandle *h) {
         h->sharp, R * 12, h->n_feat, h->less_sharp[prev], (size_t)R * 120, h->ls_ring_off[prev], h->g_corner_last, h->lo_pose,
         h->lo_init, h->lo_corner_res, h->lo_corner_corr, R, gate, nullptr, nullptr); }
   { LAUNCH(h, "lo_solve_corner");
-    lo_solve_kernel<<<B, 256, lo_stage_bytes, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
+    lo_solve_kernel<<<B, LO_SOLVE_THREADS, lo_stage_bytes, s>>>(2, h->lo_surf_res, h->lo_surf_corr, h->lo_corner_res, h->lo_corner_corr, h->n_feat,
                                       h->lo_params, h->t_w, h->r_w, h->lo_init, h->lo_report, h->lo_trace, h->lo_trace_n,
                                       h->lo_trace_cap, R, h->P.lo_surf_iters, h->P.lo_corner_iters, hub, (int)(lo_stage_bytes / sizeof(float))); }
   { LAUNCH(h, "lo_snapshot"); lo_snapshot_kernel<<<div_up(B, 128), 128, 0, s>>>(h->t_w, h->r_w, h->o2l_lo[cur], B); }

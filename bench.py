@@ -476,7 +476,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     n_visible = torch.cuda.device_count()
-    device = sharding.device_for_local_rank(local_rank, n_visible, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    if os.environ.get("ALEGO_BENCH_DEVICE_ORDER", "") == "identity":  # for the rank -> GPU comparison in profiles/ (default: interleaved)
+        device = local_rank % n_visible
+    else:
+        device = sharding.device_for_local_rank(local_rank, n_visible, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     torch.cuda.set_device(device)
     numa = None
     try:  # keep the rank (and the pinned sweep buffers it first-touches) on the CPUs next to its GPU
