@@ -175,11 +175,63 @@ __device__ __forceinline__ int isb_warp_partition(unsigned long long *e, int *po
   return min(first_keep_L, min_swap_R);
 }
 
-// one warp finishes the introsort loop of [f, l) on its own (explicit stack: the right part is deferred, the left part continued —
-// the parts are disjoint, so the order in which they are processed does not matter)
 __device__ __forceinline__ void isw_heap(unsigned long long *e, int f, int l, unsigned long long *wheap);
-__device__ __forceinline__ void isb_warp_finish(unsigned long long *e, int *pos, int f, int l, int depth, unsigned short *wpos,
-                                                unsigned long long *wheap = nullptr) {
+
+// A whole range of at most 32 records, finished in registers: one record per lane, median-of-3 and the partition exchanges by
+// shuffles (the partner of the k-th exchanging left stopper is the k-th right stopper from the top: __fns on the stopper mask),
+// no memory traffic and no per-range bookkeeping until the final store.  Of the two parts of such a range at most one is longer
+// than 16, so the introsort loop needs no stack here.  About half of all partitions of a list happen on ranges this short.
+__device__ __forceinline__ void isb_warp_small(unsigned long long *e, int f, int l, int depth, unsigned long long *wheap) {
+  const int lane = threadIdx.x & 31, len = l - f;
+  const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u, gt_mask = ~(lt_mask | (1u << lane));
+  unsigned long long rec = lane < len ? e[f + lane] : ~0ull;
+  int a = 0, b = len;
+  while (b - a > 16) {
+    if (depth == 0) {  // depth limit: heapsort of what is left of the range
+      if (lane < len) e[f + lane] = rec;
+      __syncwarp();
+      isw_heap(e, f + a, f + b, wheap);
+      return;
+    }
+    --depth;
+    // std::__move_median_to_first(a, a + 1, mid, b - 1)
+    const int ia = a + 1, ib = a + (b - a) / 2, ic = b - 1;
+    const unsigned key = (unsigned)(rec >> 32);
+    const unsigned ka = __shfl_sync(full, key, ia), kb = __shfl_sync(full, key, ib), kc = __shfl_sync(full, key, ic);
+    int sidx;
+    if (ka < kb) sidx = kb < kc ? ib : (ka < kc ? ic : ia);
+    else sidx = ka < kc ? ia : (kb < kc ? ic : ib);
+    const unsigned long long ra = __shfl_sync(full, rec, a), rs = __shfl_sync(full, rec, sidx);
+    if (lane == a) rec = rs;
+    else if (lane == sidx) rec = ra;
+    const unsigned p = (unsigned)(rs >> 32), k = (unsigned)(rec >> 32);
+    // std::__unguarded_partition(a + 1, b, pivot at a)
+    const bool in = lane > a && lane < b;
+    const bool isL = in && k >= p, isR = in && k <= p;
+    const unsigned mL = __ballot_sync(full, isL), mR = __ballot_sync(full, isR);
+    const int cL = __popc(mL & lt_mask), cR = __popc(mR & gt_mask);
+    const bool sL = isL && cR > cL, sR = isR && cL > cR;
+    int src = lane;
+    if (sL) src = (int)__fns(mR, 31, -(cL + 1));
+    if (sR) src = (int)__fns(mL, 0, cR + 1);
+    rec = __shfl_sync(full, rec, src);
+    const unsigned keepL = __ballot_sync(full, isL && !sL), swapR = __ballot_sync(full, sR);
+    const int cut = min(keepL ? __ffs(keepL) - 1 : 0x7fffffff, swapR ? __ffs(swapR) - 1 : b);
+    if (cut - a > 16) b = cut;
+    else if (b - cut > 16) a = cut;
+    else break;
+  }
+  if (lane < len) e[f + lane] = rec;
+  __syncwarp();
+}
+
+// one warp finishes the introsort loop of [f, l) on its own (explicit stack: the right part is deferred, the left part continued —
+// the parts are disjoint, so the order in which they are processed does not matter).  LOCAL = true: e is the warp's shared-memory
+// copy of a range of at most ISB_REG records (pos unused: the exchange positions live in wpos).
+template <bool LOCAL>
+__device__ __forceinline__ void isb_warp_finish_t(unsigned long long *e, int *pos, int f, int l, int depth, unsigned short *wpos,
+                                                  unsigned long long *wheap, unsigned long long *wbuf) {
+  const int lane = threadIdx.x & 31;
   uint2 st[40];  // y = l | depth << 24
   int sp = 0;
   st[sp++] = make_uint2((unsigned)f, (unsigned)l | ((unsigned)depth << 24));
@@ -189,8 +241,23 @@ __device__ __forceinline__ void isb_warp_finish(unsigned long long *e, int *pos,
     l = (int)(fr.y & 0xffffffu);
     depth = (int)(fr.y >> 24);
     while (l - f > 16) {
+      if (l - f <= 32) {
+        isb_warp_small(e, f, l, depth, LOCAL ? nullptr : wheap);
+        break;
+      }
+      if (!LOCAL && wbuf && l - f <= ISB_REG) {
+        // everything below this size happens in the warp's shared-memory copy of the range: one read and one write of global
+        // memory for all the levels that are left
+        for (int t = lane; t < l - f; t += 32) wbuf[t] = e[f + t];
+        __syncwarp();
+        isb_warp_finish_t<true>(wbuf - f, nullptr, f, l, depth, wpos, nullptr, nullptr);
+        __syncwarp();
+        for (int t = lane; t < l - f; t += 32) e[f + t] = wbuf[t];
+        __syncwarp();
+        break;
+      }
       if (depth == 0) {
-        isw_heap(e, f, l, wheap);
+        isw_heap(e, f, l, LOCAL ? nullptr : wheap);
         break;
       }
       --depth;
@@ -199,6 +266,10 @@ __device__ __forceinline__ void isb_warp_finish(unsigned long long *e, int *pos,
       l = cut;
     }
   }
+}
+__device__ __forceinline__ void isb_warp_finish(unsigned long long *e, int *pos, int f, int l, int depth, unsigned short *wpos,
+                                                unsigned long long *wheap = nullptr, unsigned long long *wbuf = nullptr) {
+  isb_warp_finish_t<false>(e, pos, f, l, depth, wpos, wheap, wbuf);
 }
 
 // the whole CTA (NW warps) partitions [f, l): every warp owns a contiguous, 32-aligned slice of (f, l)
@@ -351,8 +422,8 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
 // when every pushed task has completed, i.e. the claimed slot will never be filled: the warp leaves.  A task is completed
 // (outstanding -= 1) after everything it kept privately is finished.  A watchdog turns an impossible wait into an error flag.
 // ---------------------------------------------------------------------------------------------------------------------------
-#define ISW_SPLIT 96
-#define ISW_CAP 1024
+#define ISW_SPLIT 256  // = ISB_REG: what a warp finishes in its shared-memory copy is not worth handing over
+#define ISW_CAP 512
 #define ISW_HEAP 128  // depth-limit ranges up to this long are heap-sorted in shared memory
 
 struct IswShared {
@@ -387,7 +458,8 @@ __device__ __forceinline__ void isw_heap(unsigned long long *e, int f, int l, un
 }
 
 // every warp of the CTA calls; q must have been reset and the root task pushed (block_introsort_ws does both)
-__device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, int *pos, unsigned short *wpos, unsigned long long *wheap) {
+__device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, int *pos, unsigned short *wpos, unsigned long long *wheap,
+                                           unsigned long long *wbuf) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     int slot = 0;
@@ -414,6 +486,10 @@ __device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, 
       const uint2 fr = st[--sp];
       int f = (int)fr.x, l = (int)(fr.y & 0xffffffu), depth = (int)(fr.y >> 24);
       while (l - f > 16) {
+        if (l - f <= ISB_REG) {  // short enough for the warp's shared-memory copy: finish it there
+          isb_warp_finish(e, pos, f, l, depth, wpos, wheap, wbuf);
+          break;
+        }
         if (depth == 0) {
           isw_heap(e, f, l, wheap);
           break;
@@ -440,8 +516,8 @@ __device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, 
 // The partition phase of std::sort on e[0..n) by the NW warps of the CTA.  Long ranges (>= ISW_BIG) first, level by level, each
 // partitioned by the whole CTA (isb_block_partition: the top levels of a long list would otherwise be one warp's serial,
 // latency-bound chain); what they leave below ISW_BIG becomes the initial tasks of the work-sharing phase (isw_worker).
-// pos: n ints of scratch.  wpos_all / wheap_all: per-warp shared scratch (NW x ISB_REG 16-bit positions; NW x ISW_HEAP records,
-// or nullptr).  Every thread of the CTA must call; ends with a barrier.
+// pos: n ints of scratch.  wpos_all / wbuf_all: per-warp shared scratch (NW x ISB_REG 16-bit positions; NW x ISB_REG records: the
+// warp's copy of a short range, also the heapsort buffer).  Every thread of the CTA must call; ends with a barrier.
 #define ISW_BIG 2048
 #define ISW_MAX_BIG 64  // lists of up to ISW_BIG * ISW_MAX_BIG = 131072 records
 struct IswBig {
@@ -452,7 +528,7 @@ struct IswBig {
 
 template <int NW>
 __device__ void block_introsort_ws(unsigned long long *e, int *pos, int n, IswShared *q, IswBig *big, unsigned short *wpos_all,
-                                   unsigned long long *wheap_all) {
+                                   unsigned long long *wbuf_all) {
   if (n <= 16) return;  // uniform
   for (int t = threadIdx.x; t < ISW_CAP; t += NW * 32) q->ready[t] = 0;
   int depth = 2 * (31 - __clz(n));
@@ -493,6 +569,6 @@ __device__ void block_introsort_ws(unsigned long long *e, int *pos, int n, IswSh
   }
   __syncthreads();
   const int w = threadIdx.x >> 5;
-  isw_worker(q, e, pos, wpos_all + w * ISB_REG, wheap_all ? wheap_all + (size_t)w * ISW_HEAP : nullptr);
+  isw_worker(q, e, pos, wpos_all + w * ISB_REG, wbuf_all + (size_t)w * ISB_REG, wbuf_all + (size_t)w * ISB_REG);
   __syncthreads();
 }

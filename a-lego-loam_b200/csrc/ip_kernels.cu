@@ -244,17 +244,6 @@ __device__ __forceinline__ int uf_find(const int *L, int x) {
   }
   return x;
 }
-__device__ __forceinline__ int uf_find_compress(int *L, int x) {
-  int root = uf_find(L, x);
-  // point the whole path at the root (plain stores: every value written is an ancestor)
-  int p = L[x];
-  while (p != root) {
-    L[x] = root;
-    x = p;
-    p = L[x];
-  }
-  return root;
-}
 __device__ __forceinline__ void uf_unite(int *L, int a, int b) {
   bool done;
   do {

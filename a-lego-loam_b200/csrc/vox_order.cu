@@ -12,41 +12,49 @@
 
 namespace {
 #define VOW_WARPS 8
+#define VO_WARP_MAX 2048
 __global__ void __launch_bounds__(VOW_WARPS * 32)
-vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b) {
+vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int max_n) {
   __shared__ unsigned short s_wpos[VOW_WARPS * ISB_REG];
-  __shared__ u64 s_heap[VOW_WARPS * ISW_HEAP];
+  __shared__ u64 s_buf[VOW_WARPS * ISB_REG];  // per warp: its copy of a short range / heapsort buffer
   const int warp = threadIdx.x >> 5;
   const int c = blockIdx.x * VOW_WARPS + warp;
   if (c >= n_lists) return;
   const int n = state[c].n;
-  if (state[c].done || state[c].nv != n || n <= 16) return;
+  if (state[c].done || state[c].nv != n || n <= 16 || n > max_n) return;
   isb_warp_finish(buf_a + state[c].off, reinterpret_cast<int *>(buf_b + state[c].off_b), 0, n, 2 * (31 - __clz(n)), s_wpos + warp * ISB_REG,
-                  s_heap + (size_t)warp * ISW_HEAP);
+                  s_buf + (size_t)warp * ISB_REG, s_buf + (size_t)warp * ISB_REG);
 }
 
 #define VOC_WARPS 8
 __global__ void __launch_bounds__(VOC_WARPS * 32)
-vox_order_cta_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b) {
+vox_order_cta_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int min_n) {
   __shared__ IswShared s_q;
   __shared__ IswBig s_big;
   __shared__ unsigned short s_wpos[VOC_WARPS * ISB_REG];
-  __shared__ u64 s_heap[VOC_WARPS * ISW_HEAP];
+  __shared__ u64 s_buf[VOC_WARPS * ISB_REG];
   const VoxState &st = state[blockIdx.x];
   const int n = st.n;
-  if (st.done || st.nv != n || n <= 16) return;  // uniform
-  block_introsort_ws<VOC_WARPS>(buf_a + st.off, reinterpret_cast<int *>(buf_b + st.off_b), n, &s_q, &s_big, s_wpos, s_heap);
+  if (st.done || st.nv != n || n <= 16 || n < min_n) return;  // uniform
+  block_introsort_ws<VOC_WARPS>(buf_a + st.off, reinterpret_cast<int *>(buf_b + st.off_b), n, &s_q, &s_big, s_wpos, s_buf);
 }
 }  // namespace
 
 int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag) {
-  { LAUNCH(h, tag); vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b); }
+  // a list is one warp's serial work: the longest ones would be the tail of the launch, so lists above VO_WARP_MAX records go
+  // to work-sharing CTAs instead (same launch window: the two kernels touch disjoint lists)
+  { LAUNCH(h, tag); vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_WARP_MAX); }
+  { std::string t2 = std::string(tag) + "_long"; LAUNCH(h, t2.c_str());
+    vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }
 
 int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag) {
-  { LAUNCH(h, tag); vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b); }
+  // same routing by length (a batch whose lists range from a few hundred to ten thousand records: LaserMapping's clouds)
+  { LAUNCH(h, tag); vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1); }
+  { std::string t2 = std::string(tag) + "_short"; LAUNCH(h, t2.c_str());
+    vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_WARP_MAX); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }
