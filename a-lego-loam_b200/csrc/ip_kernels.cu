@@ -291,11 +291,21 @@ __global__ void __launch_bounds__(256) ccl_strip_kernel(uint8_t *flags, int *__r
   const int b = blockIdx.y, WS = ccl_strip_shift(P.R), W = 1 << WS, c0 = blockIdx.x * W, w = min(W, P.C - c0), n = P.R * W;
   const size_t base = (size_t)b * P.RC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int r = idx >> WS, c = idx & (W - 1);
-    s_fl[idx] = c < w ? flags[base + (size_t)r * P.C + c0 + c] : 0;
-    s_cnt[idx] = 0;
-    s_mxr[idx] = 0;
+  if ((P.C & 3) == 0 && (w & 3) == 0) {  // four flag bytes per load (rows start 4-byte aligned when C is a multiple of 4)
+    const uint32_t *f4 = reinterpret_cast<const uint32_t *>(flags + base + c0);
+    uint32_t *s4 = reinterpret_cast<uint32_t *>(s_fl);
+    for (int q = threadIdx.x; q < (n >> 2); q += blockDim.x) {
+      const int idx = q << 2, r = idx >> WS, c = idx & (W - 1);
+      s4[q] = c < w ? f4[((size_t)r * P.C + c) >> 2] : 0u;
+    }
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) { s_cnt[idx] = 0; s_mxr[idx] = 0; }
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const int r = idx >> WS, c = idx & (W - 1);
+      s_fl[idx] = c < w ? flags[base + (size_t)r * P.C + c0 + c] : 0;
+      s_cnt[idx] = 0;
+      s_mxr[idx] = 0;
+    }
   }
   __syncthreads();
   // runs of every row: a cell joined to its left neighbour continues the run (the strip's first column starts one: the join

@@ -32,12 +32,18 @@ __global__ void __launch_bounds__(256) mr_bbox_kernel(const float4 *__restrict__
       mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
-  if ((threadIdx.x & 31) == 0 && blockIdx.x * blockDim.x < n) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(bbox + b * 6 + a, f2ord(mn[a]));
-      atomicMax(bbox + b * 6 + 3 + a, f2ord(mx[a]));
-    }
+  // one set of atomics per CTA (the six words of a sequence are a serialisation point in L2: per-warp atomics dominated the kernel)
+  __shared__ float s_red[8][6];
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int a = 0; a < 3; ++a) { s_red[wid][a] = mn[a]; s_red[wid][3 + a] = mx[a]; }
+  __syncthreads();
+  if (threadIdx.x < 6 && blockIdx.x * blockDim.x < n) {
+    const int a = threadIdx.x;
+    float v = s_red[0][a];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = a < 3 ? fminf(v, s_red[w][a]) : fmaxf(v, s_red[w][a]);
+    if (a < 3) atomicMin(bbox + b * 6 + a, f2ord(v));
+    else atomicMax(bbox + b * 6 + a, f2ord(v));
   }
 }
 
@@ -147,7 +153,7 @@ static int mr_frames(AlegoHandle *h, MapRows *m, const float4 *pts, size_t pts_s
   const int B = h->B;
   std::string t0 = std::string("maprows_bbox_") + tag;
   mr_bbox_init_kernel<<<div_up(B, 128), 128, 0, s>>>(m->bbox, B);
-  { LAUNCH(h, t0.c_str()); mr_bbox_kernel<<<dim3(std::min(div_up(points_cap, 256 * 4), 64), B), 256, 0, s>>>(pts, pts_stride, n_ptr, m->bbox); }
+  { LAUNCH(h, t0.c_str()); mr_bbox_kernel<<<dim3(std::min(div_up(points_cap, 256 * 8), 48), B), 256, 0, s>>>(pts, pts_stride, n_ptr, m->bbox); }
   mr_frame_kernel<<<div_up(B, 128), 128, 0, s>>>(m->bbox, n_ptr, m->frame, m->leaf, cap, B);
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;

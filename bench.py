@@ -398,6 +398,15 @@ def algorithmic_bytes(name, st):
         "grid_fill_map_surf": 36.0 * st["map_surf_pts"],     # 16 B point + 4 B cursor + 16 B sorted copy
         "grid_count_map_corner": 20.0 * st["map_corner_pts"],
         "grid_fill_map_corner": 36.0 * st["map_corner_pts"],
+        # voxel-row index of the surf map (VoxelGrid-output maps): bounding box = read the points; fill = read the points + one
+        # 8 B entry per touched word (<= one per point); clear = the table
+        "maprows_bbox_map_surf": 16.0 * st["map_surf_pts"],
+        "maprows_fill_map_surf": 24.0 * st["map_surf_pts"],
+        # std::sort's partition phase over the (voxel, point) records of the per-ring less-flat lists: read + write each 8 B
+        # record once (the ~8 partition levels in between are on-chip work when the list fits in L1 / shared memory)
+        "lo_lfv_order": 16.0 * kept,
+        "lo_lfv_keys": (16.0 + 4.0 + 8.0) * kept,      # point + label in, record out
+        "lo_lfv_finish": (8.0 + 16.0) * kept + 16.0 * st.get("less_flat_pts", 0.0),
         # §8 d4 K14/K15: 16 B query + 5 x 16 B neighbours + 40 B result per query (candidate buckets come on top: see "traffic")
         "lm_knn_corner": 136.0 * qc, "lm_knn_surf": 136.0 * qs,
         # §8 d4 K16: 56 B per residual block per pass, 2 passes per LM iteration

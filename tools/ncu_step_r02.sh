@@ -7,7 +7,7 @@
 TAG=$1; NSEQ=${2:-64}; SRC=${3:-"ccl_strip|mr_fill|mr_bbox|ip_image|ip_project|lo_curv_occl|vox_order_warp|vox_order_cta"}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-check"
-timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip 700 -c 260 --csv \
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip 330 -c 270 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $BENCH --n-seq 256 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 echo "launch list rc=$?"
 python tools/ncu_launch_table.py gpurun_out/${TAG}_launches.csv 256 hdl64_1800 3 gpurun_out/${TAG}_ncu_traffic.json > gpurun_out/${TAG}_launch_table.md
