@@ -424,7 +424,8 @@ def lm_block(kernels, lm_reports, lo_reports, B):
     it = float(np.mean([r["iterations"] for r in lm_reports])) if lm_reports else 0.0
     solve_ms = kernels.get("lm_solve", {}).get("ms_per_launch")
     assoc_ms = sum(kernels[k]["ms_per_launch"] for k in ("lm_knn_corner", "lm_fit_corner", "lm_knn_surf", "lm_fit_surf") if k in kernels)
-    index_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for k, v in kernels.items() if k.startswith("grid_") and "_map_" in k)
+    index_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for k, v in kernels.items()
+                   if (k.startswith("grid_") and "_map_" in k) or k.startswith("maprows_"))
     out = {"iters_per_scan2map": it, "edge_correspondences": float(np.mean([r["n_corner"] for r in lm_reports])) if lm_reports else 0.0,
            "plane_correspondences": float(np.mean([r["n_surf"] for r in lm_reports])) if lm_reports else 0.0,
            "lo_iters_per_scan": float(np.mean([r["iterations"] for r in lo_reports])) if lo_reports else 0.0}
