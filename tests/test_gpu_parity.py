@@ -269,6 +269,49 @@ def test_voxel_grid(alego, ob, n, leaf):
     g.close()
 
 
+@pytest.mark.parametrize("n,shape", [(3000, "organ_pipe"), (20000, "organ_pipe"), (6000, "sorted_runs"), (2500, "few_voxels")])
+def test_voxel_grid_adversarial_record_order(alego, ob, n, shape):
+    """Inputs on which std::sort's median-of-3 quicksort degenerates (organ-pipe / concatenated sorted runs of voxel indices — what a
+    concatenation of per-ring VoxelGrid outputs looks like) so that introsort reaches its depth limit and falls back to heapsort,
+    and a cloud with hundreds of points per voxel: the device must still leave PCL's exact record order (bit-exact centroids)."""
+    rng = np.random.default_rng(n)
+    pts = np.zeros((n, 4), np.float32)
+    if shape == "organ_pipe":
+        x = np.concatenate([np.linspace(-50, 50, n // 2), np.linspace(50, -50, n - n // 2)])
+        pts[:, 0] = x + rng.uniform(-0.05, 0.05, n)
+        pts[:, 1] = rng.uniform(-0.3, 0.3, n)
+    elif shape == "sorted_runs":
+        runs = [np.sort(rng.uniform(-60, 60, n // 12)) for _ in range(12)]
+        x = np.concatenate(runs)
+        pts[:len(x), 0] = x
+        pts[len(x):, 0] = rng.uniform(-60, 60, n - len(x))
+        pts[:, 1] = rng.uniform(-0.3, 0.3, n)
+    else:
+        pts[:, :2] = rng.uniform(-1.5, 1.5, (n, 2))
+    pts[:, 2] = rng.uniform(-0.2, 0.2, n)
+    pts[:, 3] = rng.uniform(0, 64, n)
+    g = alego.Alego(alego.default_params(0), n_seq=1)
+    out = g.voxel_grid(pts, 0.8)
+    ref_pcl, _ = ob.voxel_grid(pts, 0.8, stable=False)
+    ref_stable, _ = ob.voxel_grid(pts, 0.8, stable=True)
+    assert np.array_equal(out, ref_pcl), first_diff(out, ref_pcl)
+    assert not np.array_equal(ref_pcl, ref_stable)
+    # the same clouds through LaserMapping's downsampleCurrentScan: the batch ordering kernels (one warp per list up to 2048
+    # records, a work-sharing CTA above) instead of the all-in-one kernel of alego_voxel_grid
+    P = alego.default_params(0)
+    w = alego.SynthWorld(seed=1)
+    cm, sm = w.make_map(2000, 8000, seed=1, radius=40.0)
+    g.lm_set_map(0, cm, sm)
+    g.lm_set_scan(0, pts, pts[::-1].copy(), pts[: n // 3])
+    g.lm_set_odom(0, np.zeros(3), np.eye(3))
+    g.lm_scan2map()
+    for name, cloud, leaf in (("lm_corner_ds", pts, P.lm_corner_leaf), ("lm_surf_ds", pts[::-1], P.lm_surf_leaf),
+                              ("lm_outlier_ds", pts[: n // 3], P.lm_outlier_leaf)):
+        want, _ = ob.voxel_grid(np.ascontiguousarray(cloud), leaf, stable=False)
+        assert np.array_equal(g.debug(name), want), name + ": " + first_diff(g.debug(name), want)
+    g.close()
+
+
 def run_sequence(alego, ob, P, seed, n_sweeps, with_lm, lm_every=1, map_sizes=(6000, 30000)):
     w = alego.SynthWorld(seed=seed)
     g = alego.Alego(P, n_seq=1)
