@@ -571,4 +571,5 @@ __device__ void block_introsort_ws(unsigned long long *e, int *pos, int n, IswSh
   const int w = threadIdx.x >> 5;
   isw_worker(q, e, pos, wpos_all + w * ISB_REG, wbuf_all + (size_t)w * ISB_REG, wbuf_all + (size_t)w * ISB_REG);
   __syncthreads();
+  if (q->err) __trap();  // the watchdog fired: fail the launch loudly rather than leave a half-ordered list behind
 }

@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(256) mr_clear_kernel(const MapFrame *__restric
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) t[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// one thread per point: mask bit of its voxel, start of its word when it opens one; voxel keys must increase strictly
+// One thread per point.  pcl::VoxelGrid output lists the voxels in increasing key order, so the points of one 32-voxel word are
+// consecutive in the cloud: the lane that opens a word gathers the bits of its followers — the rest of this warp's 32 points plus,
+// for the word still open at the warp's end, the next 32 (a word holds at most 32 points) — and writes {mask, start} with one
+// plain 8-byte store.  No atomics, no read-modify-write; words nobody opens keep the zeros mr_clear_kernel wrote.
 __global__ void __launch_bounds__(256) mr_fill_kernel(const float4 *__restrict__ pts, size_t pts_stride, MapFrame *__restrict__ frame,
                                                       uint2 *__restrict__ tab, int cap) {
   const int b = blockIdx.y;
@@ -105,33 +108,55 @@ __global__ void __launch_bounds__(256) mr_fill_kernel(const float4 *__restrict__
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < f.n; i0 += gridDim.x * blockDim.x) {  // whole warps
     const int i = i0 + lane;
     const bool live = i < f.n;
-    int entry = -1 - lane, prev_entry = -1;  // dead lanes: distinct keys, no peers
+    long long key = -1;
+    int entry = -1;
     unsigned bit = 0u;
-    bool bad = false;
+    bool finite = true;
     if (live) {
       const float4 p = ldg_f4(src + i);
       const int ix = mr_voxel(p.x, f.inv, f.min_b[0]), iy = mr_voxel(p.y, f.inv, f.min_b[1]), iz = mr_voxel(p.z, f.inv, f.min_b[2]);
       const int row = iy + f.dim[1] * iz;
-      const long long key = (long long)row * f.dim[0] + ix;
+      key = (long long)row * f.dim[0] + ix;
       entry = row * f.W + (ix >> 5);
       bit = 1u << (ix & 31);
-      if (i > 0) {
-        const float4 q = ldg_f4(src + i - 1);
+      finite = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    }
+    // the point before mine: lane - 1, or (lane 0) the last point of the previous 32
+    long long prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+    int prev_entry = __shfl_up_sync(0xffffffffu, entry, 1);
+    if (lane == 0) {
+      prev_key = -1;
+      prev_entry = -1;
+      if (i0 > 0) {
+        const float4 q = ldg_f4(src + i0 - 1);
         const int jx = mr_voxel(q.x, f.inv, f.min_b[0]), jy = mr_voxel(q.y, f.inv, f.min_b[1]), jz = mr_voxel(q.z, f.inv, f.min_b[2]);
         const int prow = jy + f.dim[1] * jz;
-        bad = (long long)prow * f.dim[0] + jx >= key;  // not pcl::VoxelGrid output order: the index does not apply
+        prev_key = (long long)prow * f.dim[0] + jx;
         prev_entry = prow * f.W + (jx >> 5);
       }
-      bad = bad || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
     }
-    // the points of one word are consecutive in the cloud: one atomic per word and warp instead of one per point
-    const unsigned peers = __match_any_sync(0xffffffffu, entry);
-    const unsigned word = __reduce_or_sync(peers, bit);
+    const bool bad = live && (prev_key >= key || !finite);  // not pcl::VoxelGrid output order: the index does not apply
     if (bad) frame[b].valid = 0;
-    if (live && !bad) {
-      if ((peers & ((1u << lane) - 1u)) == 0u) atomicOr(&t[entry].x, word);
-      if (entry != prev_entry) t[entry].y = (unsigned)i;
+    // followers of the warp's last word among the next 32 points
+    const int last_entry = __shfl_sync(0xffffffffu, entry, 31);
+    unsigned ahead = 0u;
+    if (last_entry >= 0 && i + 32 < f.n) {
+      const float4 q = ldg_f4(src + i + 32);
+      const int jx = mr_voxel(q.x, f.inv, f.min_b[0]), jy = mr_voxel(q.y, f.inv, f.min_b[1]), jz = mr_voxel(q.z, f.inv, f.min_b[2]);
+      if ((jy + f.dim[1] * jz) * f.W + (jx >> 5) == last_entry) ahead = 1u << (jx & 31);
     }
+    ahead = __reduce_or_sync(0xffffffffu, ahead);
+    // lanes of one word are a run that starts at an opener
+    const bool opens = live && entry != prev_entry;
+    const unsigned heads = __ballot_sync(0xffffffffu, opens || !live) | 1u;  // lane 0 starts a run even when it continues a word
+    const unsigned below = heads & (0xffffffffu >> (31 - lane));             // heads at or below my lane
+    const int first = 31 - __clz(below);
+    const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+    const int end = above ? __ffs(above) - 1 : 32;                           // one past the run
+    const unsigned peers = (end == 32 ? 0xffffffffu : ((1u << end) - 1u)) & (0xffffffffu << first);
+    unsigned word = __reduce_or_sync(peers, bit);
+    if (entry == last_entry) word |= ahead;
+    if (opens && !bad) t[entry] = make_uint2(word, (unsigned)i);
   }
 }
 

@@ -371,7 +371,7 @@ def run_reference(args, alego, P, rank):
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -467,8 +467,32 @@ def parity_check(alego, args, P, kind, seqs_by_slot, slots, snapshots, n_steps):
             "ok": bool(idx_equal and max(worst_lo, worst_lm) < 1e-4)}
 
 
+_JSON_FD = None
+
+
+def own_stdout():
+    """The contract is ONE JSON line on stdout.  Native code under this process (the compiled reference prints progress with
+    std::cout / printf) shares file descriptor 1, so move everything that is not the JSON line to stderr: fd 1 is re-pointed at
+    fd 2 for the whole run and the original stdout is kept for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    own_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -721,7 +745,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block(args, P, seqs[0], kind)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,10 +34,19 @@ struct Blobs {
 };
 
 // the reference prints progress with std::cout (e.g. laserMapping.cpp:477); keep the host process' stdout clean while it runs
+// Counted per library: calls may run on several threads at once (one chain per thread), and std::cout is process-wide.
 struct MuteCout {
-  std::streambuf *saved;
-  MuteCout() : saved(std::cout.rdbuf(nullptr)) {}
-  ~MuteCout() { std::cout.rdbuf(saved); std::cout.clear(); }
+  static std::mutex &mu() { static std::mutex m; return m; }
+  static int &depth() { static int d = 0; return d; }
+  static std::streambuf *&saved() { static std::streambuf *s = nullptr; return s; }
+  MuteCout() {
+    std::lock_guard<std::mutex> g(mu());
+    if (depth()++ == 0) saved() = std::cout.rdbuf(nullptr);
+  }
+  ~MuteCout() {
+    std::lock_guard<std::mutex> g(mu());
+    if (--depth() == 0) { std::cout.rdbuf(saved()); std::cout.clear(); }
+  }
 };
 
 template <typename Cloud>
