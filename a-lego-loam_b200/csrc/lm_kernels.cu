@@ -493,7 +493,11 @@ __global__ void lm_guard_kernel(const int *lm_n, const int *n_map_corner, int *g
   guard[b] = !(lm_n[b * 8 + 0] < 10 || lm_n[b * 8 + 3] < 100 || n_map_corner[b] < 10);
 }
 
-#define LM_STAGE_BYTES (200 * 1024)  // shared-memory staging of the residual blocks (one CTA per SM: the solver takes the register file)
+// Shared-memory staging of the residual blocks.  The solver wants the full register budget per thread, so an SM holds 256 solver
+// threads either way: one 256-thread CTA with 200 KB when the batch fits one wave of that shape (B <= SMs), otherwise two
+// 128-thread CTAs with 100 KB each — a batch of 256 sequences is then a single wave instead of 148 + 108.
+#define LM_STAGE_BYTES_WIDE (200 * 1024)
+#define LM_STAGE_BYTES_PAIR (100 * 1024)
 struct LmResidSet {
   const double *edge;
   int n_edge_slots;
@@ -541,7 +545,8 @@ struct LmStagedSet {
   }
 };
 
-__global__ void __launch_bounds__(256)
+template <int NT, int NB>
+__global__ void __launch_bounds__(NT, NB)
 lm_solve_kernel(const double *__restrict__ edge, int ecap, const double *__restrict__ plane, int pcap, const int *__restrict__ lm_n,
                 const int *__restrict__ guard, double *lm_params, Pose *m2o, const Pose *o2l, Pose *m2l, AlegoSolveReport *report,
                 double *trace, int *trace_n, int trace_cap, int outer_iters, int max_iters, double huber_a, double *pose_out,
@@ -717,14 +722,22 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
     lm_fit_kernel<false><<<dim3(min(div_up(cs + co, 128), 64), B), 128, 0, s>>>(h->lm_surf_total_ds, cs + co, h->lm_n, 4, h->map_surf, h->map_cap_s,
                                                                        h->lm_nn_s, h->lm_plane, 8); }
   static bool solve_attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  static int sm_count[ALEGO_MAX_DEVICES] = {};
   if (!solve_attr_set[h->dev]) {
-    CUDA_TRY(h, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_STAGE_BYTES));
+    CUDA_TRY(h, cudaFuncSetAttribute(lm_solve_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_STAGE_BYTES_WIDE));
+    CUDA_TRY(h, cudaFuncSetAttribute(lm_solve_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_STAGE_BYTES_PAIR));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sm_count[h->dev], cudaDevAttrMultiProcessorCount, h->dev));
     solve_attr_set[h->dev] = true;
   }
   { LAUNCH(h, "lm_solve");
-    lm_solve_kernel<<<B, 256, LM_STAGE_BYTES, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o, h->o2l, h->m2l,
-        h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
-        write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur], (int)(LM_STAGE_BYTES / sizeof(double))); }
+    if (B <= sm_count[h->dev])
+      lm_solve_kernel<256, 1><<<B, 256, LM_STAGE_BYTES_WIDE, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o,
+          h->o2l, h->m2l, h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
+          write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur], (int)(LM_STAGE_BYTES_WIDE / sizeof(double)));
+    else
+      lm_solve_kernel<128, 2><<<B, 128, LM_STAGE_BYTES_PAIR, s>>>(h->lm_edge, cc, h->lm_plane, cs + co, h->lm_n, guard_dev, h->lm_params, h->m2o,
+          h->o2l, h->m2l, h->lm_report, h->lm_trace, h->lm_trace_n, h->lm_trace_cap, h->P.lm_outer_iters, h->P.lm_max_iters, h->P.huber_delta,
+          write_pose ? h->d_pose : nullptr, h->o2l_lo[1 - h->cur], (int)(LM_STAGE_BYTES_PAIR / sizeof(double))); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }

@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(256) mr_clear_kernel(const MapFrame *__restric
 }
 
 // One thread per point.  pcl::VoxelGrid output lists the voxels in increasing key order, so the points of one 32-voxel word are
-// consecutive in the cloud: the lane that opens a word gathers the bits of its followers — the rest of this warp's 32 points plus,
-// for the word still open at the warp's end, the next 32 (a word holds at most 32 points) — and writes {mask, start} with one
-// plain 8-byte store.  No atomics, no read-modify-write; words nobody opens keep the zeros mr_clear_kernel wrote.
+// consecutive in the cloud — a run of lanes.  The lane that opens a run sums its lanes' bits (distinct bits: a segment sum of the
+// warp's modular prefix sum) and writes {mask, start} with one plain 8-byte store; only the runs cut by the warp's edges (the first
+// when it continues the previous warp's word, and the last) go through atomicOr on the cleared table.  Issue-bound: the loop body
+// is kept to ~80 instructions (32-bit keys, uniform look-behind load, no per-run masked reductions).
 __global__ void __launch_bounds__(256) mr_fill_kernel(const float4 *__restrict__ pts, size_t pts_stride, MapFrame *__restrict__ frame,
                                                       uint2 *__restrict__ tab, int cap) {
   const int b = blockIdx.y;
@@ -108,55 +109,45 @@ __global__ void __launch_bounds__(256) mr_fill_kernel(const float4 *__restrict__
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < f.n; i0 += gridDim.x * blockDim.x) {  // whole warps
     const int i = i0 + lane;
     const bool live = i < f.n;
-    long long key = -1;
-    int entry = -1;
-    unsigned bit = 0u;
-    bool finite = true;
-    if (live) {
-      const float4 p = ldg_f4(src + i);
-      const int ix = mr_voxel(p.x, f.inv, f.min_b[0]), iy = mr_voxel(p.y, f.inv, f.min_b[1]), iz = mr_voxel(p.z, f.inv, f.min_b[2]);
-      const int row = iy + f.dim[1] * iz;
-      key = (long long)row * f.dim[0] + ix;
-      entry = row * f.W + (ix >> 5);
-      bit = 1u << (ix & 31);
-      finite = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-    }
-    // the point before mine: lane - 1, or (lane 0) the last point of the previous 32
-    long long prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-    int prev_entry = __shfl_up_sync(0xffffffffu, entry, 1);
-    if (lane == 0) {
-      prev_key = -1;
-      prev_entry = -1;
-      if (i0 > 0) {
-        const float4 q = ldg_f4(src + i0 - 1);
-        const int jx = mr_voxel(q.x, f.inv, f.min_b[0]), jy = mr_voxel(q.y, f.inv, f.min_b[1]), jz = mr_voxel(q.z, f.inv, f.min_b[2]);
-        const int prow = jy + f.dim[1] * jz;
-        prev_key = (long long)prow * f.dim[0] + jx;
-        prev_entry = prow * f.W + (jx >> 5);
-      }
-    }
-    const bool bad = live && (prev_key >= key || !finite);  // not pcl::VoxelGrid output order: the index does not apply
+    // dead lanes re-read the last point: they extend the last run with bits it already has and are never openers
+    const float4 p = ldg_f4(src + min(i, f.n - 1));
+    const int ix = mr_voxel(p.x, f.inv, f.min_b[0]);
+    const int row = mr_voxel(p.y, f.inv, f.min_b[1]) + f.dim[1] * mr_voxel(p.z, f.inv, f.min_b[2]);
+    const int entry = row * f.W + (ix >> 5);
+    const unsigned bit = live ? 1u << (ix & 31) : 0u;
+    // the point before mine: lane - 1, or (lane 0) the last point of the previous 32 — one broadcast load for the warp
+    const float4 q = ldg_f4(src + max(i0 - 1, 0));
+    const int q_ix = mr_voxel(q.x, f.inv, f.min_b[0]);
+    const int q_row = i0 == 0 ? -1 : mr_voxel(q.y, f.inv, f.min_b[1]) + f.dim[1] * mr_voxel(q.z, f.inv, f.min_b[2]);
+    const int s_ix = __shfl_up_sync(0xffffffffu, ix, 1), s_row = __shfl_up_sync(0xffffffffu, row, 1);
+    const int prev_ix = lane == 0 ? q_ix : s_ix, prev_row = lane == 0 ? q_row : s_row;
+    const int prev_entry = prev_row * f.W + (prev_ix >> 5);  // negative for the cloud's first point
+    // not pcl::VoxelGrid output order (keys must rise strictly), or not finite: the index does not apply
+    const bool bad = live && (prev_row > row || (prev_row == row && prev_ix >= ix) || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)));
     if (bad) frame[b].valid = 0;
-    // followers of the warp's last word among the next 32 points
-    const int last_entry = __shfl_sync(0xffffffffu, entry, 31);
-    unsigned ahead = 0u;
-    if (last_entry >= 0 && i + 32 < f.n) {
-      const float4 q = ldg_f4(src + i + 32);
-      const int jx = mr_voxel(q.x, f.inv, f.min_b[0]), jy = mr_voxel(q.y, f.inv, f.min_b[1]), jz = mr_voxel(q.z, f.inv, f.min_b[2]);
-      if ((jy + f.dim[1] * jz) * f.W + (jx >> 5) == last_entry) ahead = 1u << (jx & 31);
-    }
-    ahead = __reduce_or_sync(0xffffffffu, ahead);
-    // lanes of one word are a run that starts at an opener
     const bool opens = live && entry != prev_entry;
-    const unsigned heads = __ballot_sync(0xffffffffu, opens || !live) | 1u;  // lane 0 starts a run even when it continues a word
-    const unsigned below = heads & (0xffffffffu >> (31 - lane));             // heads at or below my lane
-    const int first = 31 - __clz(below);
-    const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
-    const int end = above ? __ffs(above) - 1 : 32;                           // one past the run
-    const unsigned peers = (end == 32 ? 0xffffffffu : ((1u << end) - 1u)) & (0xffffffffu << first);
-    unsigned word = __reduce_or_sync(peers, bit);
-    if (entry == last_entry) word |= ahead;
-    if (opens && !bad) t[entry] = make_uint2(word, (unsigned)i);
+    // modular inclusive prefix sum of the bits: a run's mask is the difference of two prefixes (its bits are distinct)
+    unsigned pre = bit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const unsigned heads = __ballot_sync(0xffffffffu, opens);
+    const unsigned above = heads & (0xfffffffeu << lane);
+    const int last = above ? __ffs(above) - 2 : 31;  // last lane of my run
+    const unsigned run_sum = __shfl_sync(0xffffffffu, pre, last) - (pre - bit);
+    const bool inside = entry >= 0 && entry < cap;   // (a NaN coordinate lands anywhere; the frame is flagged invalid above)
+    if (opens && !bad && inside) {
+      if (above) t[entry] = make_uint2(run_sum, (unsigned)i);               // opened and closed in this warp: all mine
+      else { atomicOr(&t[entry].x, run_sum); t[entry].y = (unsigned)i; }    // the warp's last run may go on in the next 32 points
+    }
+    // lanes before the first opener continue a word an earlier warp opened
+    const int n_cont = heads ? __ffs(heads) - 1 : 32;
+    if (n_cont > 0) {
+      const unsigned cont = __shfl_sync(0xffffffffu, pre, n_cont - 1);
+      if (lane == 0 && !bad && inside) atomicOr(&t[entry].x, cont);
+    }
   }
 }
 
