@@ -159,6 +159,7 @@ def lib():
         "alego_pipeline_config": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
         "alego_pipeline_submit": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "alego_pipeline_collect": (C.c_int, [H, C.c_void_p]),
+        "alego_pipeline_timeline": (C.c_int, [H, C.c_int, C.c_void_p]),
         "alego_voxel_grid": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, PI]),
         "alego_timer_mark": (C.c_int, [H, C.c_int]),
         "alego_timer_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, PF]),
@@ -182,7 +183,7 @@ EXPORTED_SYMBOLS = [
     "alego_n_seq", "alego_set_point_stride", "alego_lm_assemble_map", "alego_lm_get_map", "alego_host_alloc", "alego_host_free", "alego_stage_upload", "alego_stage_select", "alego_ip_process", "alego_ip_upload", "alego_ip_run", "alego_ip_get", "alego_lo_extract",
     "alego_lo_get_features", "alego_lo_scan2scan", "alego_lo_get_state", "alego_lo_set_params", "alego_lm_set_map",
     "alego_lm_set_scan", "alego_lm_set_odom", "alego_lm_scan2map", "alego_lm_get_state", "alego_lm_set_params",
-    "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_voxel_grid", "alego_timer_mark",
+    "alego_lm_get_downsampled", "alego_pipeline_step", "alego_pipeline_config", "alego_pipeline_submit", "alego_pipeline_collect", "alego_pipeline_timeline", "alego_voxel_grid", "alego_timer_mark",
     "alego_timer_elapsed_ms", "alego_profile_enable", "alego_profile_reset", "alego_profile_count", "alego_profile_get",
     "alego_launch_count", "alego_debug_get", "alego_lo_adjust_distortion", "alego_lc_icp",
 ]
@@ -397,6 +398,13 @@ class Alego:
         poses = np.zeros((self.n_seq, 12), np.float64) if want_poses else None
         self._chk(self.L.alego_pipeline_collect(self.h, _ptr(poses)))
         return poses
+
+    def pipeline_timeline(self, on=True):
+        """Switch the per-step timing events on/off; returns the timeline of the step collected last (ms since the first timed
+        submit): [H2D starts, H2D done, front end starts, front end done, poses on the host]."""
+        t = np.zeros(5, np.float32)
+        self._chk(self.L.alego_pipeline_timeline(self.h, int(on), _ptr(t)))
+        return t
 
     def pipeline_step(self, buf=None, n=None, want_poses=True):
         poses = np.zeros((self.n_seq, 12), np.float64) if want_poses else None

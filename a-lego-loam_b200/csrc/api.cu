@@ -315,7 +315,12 @@ void alego_destroy(AlegoHandle *h) {
     if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
     if (h->ev_consumed[k]) cudaEventDestroy(h->ev_consumed[k]);
     if (h->ev_pose[k]) cudaEventDestroy(h->ev_pose[k]);
+    for (int e = 0; e < 5; ++e)
+      if (h->ev_t[k][e]) cudaEventDestroy(h->ev_t[k][e]);
   }
+  if (h->ev_t_origin) cudaEventDestroy(h->ev_t_origin);
+  for (void *p : h->scratch)
+    if (p) cudaFree(p);
   if (h->ev_lo_done) cudaEventDestroy(h->ev_lo_done);
   if (h->ev_side_tail) cudaEventDestroy(h->ev_side_tail);
   for (auto &g : h->graphs)
@@ -1059,16 +1064,28 @@ int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t 
   std::memcpy(h->h_n_pts_slot[slot], n_points, (size_t)h->B * sizeof(int32_t));
   // the staging buffer may still be read by the pass submitted two steps ago
   if (h->consumed_valid[slot]) CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+  const bool tl = h->timeline_on;
+  if (tl && !h->ev_t_origin) {
+    CUDA_TRY(h, cudaEventCreate(&h->ev_t_origin));
+    for (int k = 0; k < ALEGO_INFLIGHT; ++k)
+      for (int e = 0; e < 5; ++e) CUDA_TRY(h, cudaEventCreate(&h->ev_t[k][e]));
+    CUDA_TRY(h, cudaEventRecord(h->ev_t_origin, h->copy_stream));
+  }
+  if (tl) CUDA_TRY(h, cudaEventRecord(h->ev_t[slot][0], h->copy_stream));
   int rc = upload_into(h, h->raw_slot[slot], h->n_pts_slot[slot], xyzi_host, h->h_n_pts_slot[slot], h->copy_stream);
   if (rc != ALEGO_OK) return rc;
+  if (tl) CUDA_TRY(h, cudaEventRecord(h->ev_t[slot][1], h->copy_stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+  if (tl) CUDA_TRY(h, cudaEventRecord(h->ev_t[slot][2], h->stream));
   h->raw = h->raw_slot[slot];
   h->n_pts = h->n_pts_slot[slot];
   if ((rc = pipeline_enqueue(h, h->ev_consumed[slot])) != ALEGO_OK) return rc;
   h->consumed_valid[slot] = true;
+  if (tl) CUDA_TRY(h, cudaEventRecord(h->ev_t[slot][3], h->stream));  // front end (IP + LO) of this step done
   cudaStream_t ps = pose_stream(h);
   CUDA_TRY(h, cudaMemcpyAsync(h->h_pose_slot[slot], h->d_pose, (size_t)h->B * 12 * sizeof(double), cudaMemcpyDeviceToHost, ps));
+  if (tl) CUDA_TRY(h, cudaEventRecord(h->ev_t[slot][4], ps));
   CUDA_TRY(h, cudaEventRecord(h->ev_pose[slot], ps));
   if (ps == h->side_stream) CUDA_TRY(h, cudaEventRecord(h->ev_side_tail, ps));
   ++h->n_submitted;
@@ -1082,7 +1099,20 @@ int alego_pipeline_collect(AlegoHandle *h, double *poses_out) {
   const int slot = (int)(h->n_collected % ALEGO_INFLIGHT);
   CUDA_TRY(h, cudaEventSynchronize(h->ev_pose[slot]));
   if (poses_out) std::memcpy(poses_out, h->h_pose_slot[slot], (size_t)h->B * 12 * sizeof(double));
+  if (h->timeline_on && h->ev_t_origin)
+    for (int e = 0; e < 5; ++e) CUDA_TRY(h, cudaEventElapsedTime(&h->last_timeline[e], h->ev_t_origin, h->ev_t[slot][e]));
   ++h->n_collected;
+  return ALEGO_OK;
+}
+
+int alego_pipeline_timeline(AlegoHandle *h, int on, float *t_ms) {
+  if (!h) return ALEGO_BAD_ARG;
+  if (h->n_submitted != h->n_collected && (on != 0) != h->timeline_on) {
+    h->err = "alego_pipeline_timeline: switch while steps are in flight";
+    return ALEGO_NOT_READY;
+  }
+  h->timeline_on = on != 0;
+  if (t_ms) std::memcpy(t_ms, h->last_timeline, sizeof h->last_timeline);
   return ALEGO_OK;
 }
 

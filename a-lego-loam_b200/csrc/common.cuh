@@ -90,6 +90,13 @@ struct AlegoHandle {
   cudaEvent_t ev_g_fork = nullptr, ev_g_lo = nullptr, ev_g_tail = nullptr;  // fork / join inside a capture
   cudaEvent_t ev_copied[ALEGO_INFLIGHT] = {}, ev_consumed[ALEGO_INFLIGHT] = {}, ev_pose[ALEGO_INFLIGHT] = {};
   bool consumed_valid[ALEGO_INFLIGHT] = {};
+  // grow-only device scratch of the per-keyframe / stand-alone entry points (local-map assembly, alego_voxel_grid)
+  void *scratch[5] = {};
+  size_t scratch_bytes[5] = {};
+  // timeline of the asynchronous steps (alego_pipeline_timeline): timing events per slot, ms since the first submit
+  cudaEvent_t ev_t_origin = nullptr, ev_t[ALEGO_INFLIGHT][5] = {};
+  bool timeline_on = false;
+  float last_timeline[5] = {0, 0, 0, 0, 0};
   long long n_submitted = 0, n_collected = 0;
   std::string err;
   int64_t launches = 0;

@@ -769,16 +769,32 @@ static int lm_ensure_ds_buffers(AlegoHandle *h, int need_c, int need_s, int need
   return ALEGO_OK;
 }
 
+// grow-only scratch slot k of the handle (cudaFree of the outgrown buffer waits for the work that still uses it)
+static int scratch_get(AlegoHandle *h, int k, size_t bytes, void **out) {
+  if (bytes > h->scratch_bytes[k]) {
+    if (h->scratch[k]) cudaFree(h->scratch[k]);
+    h->scratch[k] = nullptr;
+    h->scratch_bytes[k] = 0;
+    const size_t want = bytes + bytes / 4;
+    CUDA_TRY(h, cudaMalloc(&h->scratch[k], want));
+    h->scratch_bytes[k] = want;
+  }
+  *out = h->scratch[k];
+  return ALEGO_OK;
+}
+
 int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float *out_xyzi, int *n_out) {
   cudaStream_t s = h->stream;
   if (n == 0) { *n_out = 0; return ALEGO_OK; }
-  float4 *d_in = nullptr, *d_out = nullptr;
-  u64 *d_keys = nullptr;
-  int *d_n = nullptr;
-  CUDA_TRY(h, cudaMalloc(&d_in, (size_t)n * sizeof(float4)));
-  CUDA_TRY(h, cudaMalloc(&d_out, (size_t)n * sizeof(float4)));
-  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)2 * n * sizeof(u64)));
-  CUDA_TRY(h, cudaMalloc(&d_n, sizeof(int)));
+  void *v_in, *v_out, *v_keys, *v_n;
+  int rc;
+  if ((rc = scratch_get(h, 0, (size_t)n * sizeof(float4), &v_in)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 1, (size_t)2 * n * sizeof(u64), &v_keys)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 2, (size_t)n * sizeof(float4), &v_out)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 3, 64, &v_n)) != ALEGO_OK) return rc;
+  float4 *d_in = static_cast<float4 *>(v_in), *d_out = static_cast<float4 *>(v_out);
+  u64 *d_keys = static_cast<u64 *>(v_keys);
+  int *d_n = static_cast<int *>(v_n);
   CUDA_TRY(h, cudaMemcpyAsync(d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM_EXACT));
   { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM_EXACT, s>>>(d_in, n, leaf, d_out, d_keys, d_n); }
@@ -789,7 +805,6 @@ int voxel_grid_host(AlegoHandle *h, const float *xyzi, int n, float leaf, float 
     CUDA_TRY(h, cudaMemcpyAsync(out_xyzi, d_out, (size_t)*n_out * sizeof(float4), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
   }
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_n);
   return ALEGO_OK;
 }
 
@@ -822,7 +837,7 @@ __global__ void __launch_bounds__(256) lm_kf_transform_kernel(float4 *__restrict
 }  // namespace
 
 // segs: n_seg host clouds (pointer, count) concatenated in order, transformed by M[s >> mat_shift], VoxelGrid(leaf) into
-// dst[0..*] on the device, count into n_dst (device).  Scratch is allocated per call: this runs once per keyframe.
+// dst[0..*] on the device, count into n_dst (device).  Scratch is pooled in the handle (grow-only); no synchronisation.
 int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *seg_n, int n_seg, const float *M_host, int n_mat,
                       int mat_shift, float leaf, float4 *dst, int *n_dst) {
   cudaStream_t s = h->stream;
@@ -833,14 +848,16 @@ int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *se
     CUDA_TRY(h, cudaMemsetAsync(n_dst, 0, sizeof(int), s));
     return ALEGO_OK;
   }
-  float4 *d_in = nullptr;
-  u64 *d_keys = nullptr;
-  int *d_off = nullptr;
-  float *d_M = nullptr;
-  CUDA_TRY(h, cudaMalloc(&d_in, (size_t)n * sizeof(float4)));
-  CUDA_TRY(h, cudaMalloc(&d_keys, (size_t)2 * n * sizeof(u64)));
-  CUDA_TRY(h, cudaMalloc(&d_off, (size_t)(n_seg + 1) * sizeof(int)));
-  CUDA_TRY(h, cudaMalloc(&d_M, (size_t)n_mat * 12 * sizeof(float)));
+  void *v_in, *v_keys, *v_off, *v_M;
+  int rc;
+  if ((rc = scratch_get(h, 0, (size_t)n * sizeof(float4), &v_in)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 1, (size_t)2 * n * sizeof(u64), &v_keys)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 3, (size_t)(n_seg + 1) * sizeof(int), &v_off)) != ALEGO_OK) return rc;
+  if ((rc = scratch_get(h, 4, (size_t)n_mat * 12 * sizeof(float), &v_M)) != ALEGO_OK) return rc;
+  float4 *d_in = static_cast<float4 *>(v_in);
+  u64 *d_keys = static_cast<u64 *>(v_keys);
+  int *d_off = static_cast<int *>(v_off);
+  float *d_M = static_cast<float *>(v_M);
   for (int k = 0; k < n_seg; ++k)
     if (seg_n[k] > 0)
       CUDA_TRY(h, cudaMemcpyAsync(d_in + off[k], seg_ptr[k], (size_t)seg_n[k] * sizeof(float4), cudaMemcpyHostToDevice, s));
@@ -851,7 +868,7 @@ int lm_assemble_cloud(AlegoHandle *h, const float *const *seg_ptr, const int *se
   CUDA_TRY(h, cudaFuncSetAttribute(voxel_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LMV_SMEM_EXACT));
   { LAUNCH(h, "voxel_single"); voxel_single_kernel<<<1, LMV_THREADS, LMV_SMEM_EXACT, s>>>(d_in, n, leaf, dst, d_keys, n_dst); }
   CUDA_TRY(h, cudaGetLastError());
-  CUDA_TRY(h, cudaStreamSynchronize(s));  // the host clouds and the scratch are released on return
-  cudaFree(d_in); cudaFree(d_keys); cudaFree(d_off); cudaFree(d_M);
+  // No synchronisation: the host clouds are pageable memory (copied to the driver's staging buffers before cudaMemcpyAsync
+  // returns), the offsets / matrices likewise, and the scratch stays with the handle; everything later is ordered by the stream.
   return ALEGO_OK;
 }

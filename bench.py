@@ -545,7 +545,7 @@ def main():
         B = args.n_seq
         unique_ids = list(range(min(N_UNIQUE, B)))
     U = len(unique_ids)
-    seqs = make_sequences(alego, P, 3 * n_steps, args.map_corner, args.map_surf, ids=unique_ids, map_order=args.map_order)
+    seqs = make_sequences(alego, P, 4 * n_steps, args.map_corner, args.map_surf, ids=unique_ids, map_order=args.map_order)
     g = alego.Alego(P, n_seq=B, device=device)
     g.pipeline_config(lm_every=args.lm_every, rebuild_map_index_every_step=True, graphs=args.graphs)
     g.set_point_stride(args.point_stride)
@@ -669,6 +669,36 @@ def main():
     prof = g.profile()
     g.profile_enable(False)
     snapshot()
+
+    # ---------------- pass D: pass B again, untimed, with per-step timing events ----------------
+    # where a step's time goes (copy engine vs SMs, and how they overlap); the next n_steps sweeps of every sequence
+    fill(3 * n_steps)
+    g.pipeline_timeline(True)
+    tl = []
+    for t in range(W, W + K):
+        if t - W >= DEPTH:
+            g.pipeline_collect(want_poses=False)
+            tl.append(g.pipeline_timeline(True).copy())
+        g.pipeline_submit(host[t], host_n[t])
+    for _ in range(min(K, DEPTH)):
+        g.pipeline_collect(want_poses=False)
+        tl.append(g.pipeline_timeline(True).copy())
+    g.pipeline_timeline(False)
+    tl = np.array(tl, np.float64)
+    timeline = None
+    if len(tl) >= 3:
+        body = tl[1:]  # the first step has nothing to overlap with
+        timeline = {"h2d_ms": round(float(np.mean(body[:, 1] - body[:, 0])), 3),
+                    "front_end_ms": round(float(np.mean(body[:, 3] - body[:, 2])), 3),
+                    "submit_to_poses_ms": round(float(np.mean(body[:, 4] - body[:, 0])), 3),
+                    "step_interval_ms": round(float((tl[-1, 4] - tl[0, 4]) / (len(tl) - 1)), 3),
+                    "copy_engine_idle_between_steps_ms": round(float(np.mean(tl[1:, 0] - tl[:-1, 1])), 3),
+                    "front_end_waits_for_copy_ms": round(float(np.mean(np.maximum(body[:, 2] - np.maximum(tl[:-1, 3], body[:, 1]), 0.0))), 3),
+                    "last_steps_ms": [[round(float(v - tl[-4:][0, 0]), 3) for v in row] for row in tl[-4:]],
+                    "note": "CUDA events per step of an extra, untimed run of the same loop: H2D copy (copy stream), front end = "
+                            "ImageProjection + LaserOdometry (main stream), poses = after LaserMapping (side stream) + D2H; last_steps_ms rows = "
+                            "[H2D starts, H2D done, front end starts, front end done, poses on host]"}
+
     kept = float(np.mean([len(g.debug("segmentedCloudColInd", b)) for b in range(U)])) * B
     lm_reports = [g.solve_report("lm", b) for b in range(U)]
     lo_reports = [g.solve_report("lo", b) for b in range(U)]
@@ -727,7 +757,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(st["points"] * 4 * PS + B * 4), "d2h_bytes_per_step": B * 12 * 8,
                     "ms_per_step": ms_e2e_max / K, "host_wall_ms_per_step": ms_e2e_host / K, "device_event_ms_per_step": ms_e2e_dev / K,
-                    "h2d_probe_gbs": round(h2d_probe_gbs, 1),
+                    "h2d_probe_gbs": round(h2d_probe_gbs, 1), "timeline": timeline,
                     "api": "alego_pipeline_submit/_collect, pinned host sweeps, 3 steps in flight (H2D of sweep t+1 overlaps the pass over sweep t)"},
             "gpu_launches": int(launches),
             "lm": lm_block(kernels, lm_reports, lo_reports, B),

@@ -246,6 +246,11 @@ int alego_pipeline_step(AlegoHandle *h, const float *xyzi_host, const int32_t *n
  * poses (layout as alego_pipeline_step; poses_out may be NULL). */
 int alego_pipeline_submit(AlegoHandle *h, const float *xyzi_host, const int32_t *n_points);
 int alego_pipeline_collect(AlegoHandle *h, double *poses_out);
+/* Diagnostics of the asynchronous form (no reference counterpart; the reference logs per-stage TicToc times instead,
+ * laserMapping.cpp:344-477): with on != 0 every submitted step records CUDA timing events, and t_ms (may be NULL) receives the
+ * timeline of the step collected LAST, in ms since the first timed submit: [0] H2D copy starts, [1] H2D copy done,
+ * [2] front end (ImageProjection + LaserOdometry) starts on the main stream, [3] front end done, [4] poses in host memory. */
+int alego_pipeline_timeline(AlegoHandle *h, int on, float *t_ms);
 /* lm_every: run LM on every k-th sweep (reference: 2, laserMapping.cpp:112); 0 disables LM.
  * rebuild_map_index_every_step: rebuild the local-map search index on every mapped sweep, like the reference's kd-tree
  * builds (laserMapping.cpp:356-357), instead of only after alego_lm_set_map.  options: 0 default — the LaserMapping stage

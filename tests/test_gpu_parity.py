@@ -633,3 +633,59 @@ def test_async_submit_collect_matches_sync(alego):
     buf, n = g.pack_scans(sweeps[0])
     assert g.pipeline_step(buf, n).shape == (len(seeds), 12)
     g.close()
+
+
+def test_async_packed_batch64_against_chain(alego, ob):
+    """The benchmark's configuration at a batch the CPU chain can follow: 64 sequences (4 unique, 16 slots each), 64 x 1800 sweeps
+    as packed x,y,z, alego_pipeline_submit / _collect with three steps in flight, LaserMapping on the side stream against 50 k corner
+    + 200 k surf local maps that are pcl::VoxelGrid output (voxel-row index), re-indexed on every mapped sweep.  Every slot's poses
+    against the CPU chain of its sequence (north_star tolerance), replicas bit-identical."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    U, REP, T = 4, 16, 4
+    B = U * REP
+    worlds = [alego.SynthWorld(seed=20 + u) for u in range(U)]
+    maps = []
+    for u, w in enumerate(worlds):
+        cm, sm = w.make_map(75000, 320000, seed=20 + u, radius=80.0)
+        cm, sm = ob.voxel_grid(cm, P.lm_corner_leaf)[0][:50000], ob.voxel_grid(sm, P.lm_surf_leaf)[0][:200000]
+        maps.append((cm, sm))
+    sweeps = [[w.render(P, alego.trajectory_pose(t, seed=20 + u), noise_seed=900 + 10 * u + t) for u, w in enumerate(worlds)] for t in range(T)]
+    # CPU chains
+    want = []
+    for u in range(U):
+        o = ob.Oracle(P, lm_every=1, stable_voxel=False)
+        o.lm_set_map(*maps[u])
+        per = []
+        for t in range(T):
+            o.pipeline_step(sweeps[t][u])
+            per.append((np.array(o.get("lo_params")), np.array(o.get("lm_params"))))
+        want.append(per)
+    g = alego.Alego(P, n_seq=B)
+    g.set_point_stride(3)
+    for b in range(B):
+        g.lm_set_map(b, *maps[b % U])
+    g.pipeline_config(lm_every=1, rebuild_map_index_every_step=True, overlap_map_build=True)
+    D = 3
+    bufs = [alego.pinned_empty((B, g.max_points, 3), np.float32) for _ in range(D)]
+    ns = [np.zeros(B, np.int32) for _ in range(D)]
+    got = []
+    for t in range(T):
+        if t >= D:
+            got.append(g.pipeline_collect())
+        b_, n_ = g.pack_scans([sweeps[t][b % U] for b in range(B)])
+        bufs[t % D][:] = b_
+        ns[t % D][:] = n_
+        g.pipeline_submit(bufs[t % D], ns[t % D])
+    while len(got) < T:
+        got.append(g.pipeline_collect())
+    assert int(g.debug("map_index_kind")[0]) == 1  # the surf maps went through the voxel-row index
+    for t in range(T):
+        for b in range(B):
+            lo_w, lm_w = want[b % U][t]
+            assert np.abs(got[t][b, 3:9] - lm_w).max() < POSE_TOL, (t, b)
+            assert np.array_equal(got[t][b], got[t][b % U]), (t, b)  # nothing on the path depends on the slot
+    for b in range(0, B, 7):
+        assert np.abs(g.debug("lo_params", b) - want[b % U][T - 1][0]).max() < POSE_TOL, b
+    rep = g.solve_report("lm", B - 1)
+    assert rep["status"] == alego.OK and rep["n_surf"] > 100
+    g.close()

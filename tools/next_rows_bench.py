@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timings of the SURVEY §8f rows N2 (adjustDistortion) and N4 (loop-closure ICP) on the GPU box, next to the CPU restatement
+"""Timings of the SURVEY §8f rows N1 (local-map assembly), N2 (adjustDistortion) and N4 (loop-closure ICP) on the GPU box, next to the CPU restatement
 (oracle, one core).  Per-kernel times come from the library's CUDA-event profile (alego_profile_*), the call times are host
 wall clock around the C-ABI call (host clouds in, result out).  Prints one JSON object."""
 import json
@@ -18,7 +18,7 @@ import test_next_rows as T
 
 alego = alego_pkg.load()
 out = {}
-ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else "all"  # icp | distortion | all
+ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else "all"  # icp | distortion | assemble | all
 QUICK = "--quick" in sys.argv  # one repetition, small batch: for runs under ncu
 
 P = alego.default_params(1)
@@ -91,5 +91,52 @@ if ONLY in ("all", "distortion"):
         "gpu_walk_kernel_ms_per_launch": round(prof.get("lo_adjust_walk", (0, 0.0))[1] / max(prof.get("lo_adjust_walk", (1, 0.0))[0], 1), 4),
         "algorithmic_GBps": round(sum(M) * (16 + 16 + 4) / max(k_ms / max(k_n, 1), 1e-9) / 1e6, 1),
         "cpu_oracle_ms_one_sequence": round(1e3 * t_cpu, 3),
+    }
+if ONLY in ("all", "assemble"):
+    # ---- N1: a 50-keyframe window of 64 x 1800 sweeps (laserMapping.cpp:206-243, 316-319): every keyframe = the three downsampled
+    #      clouds LaserMapping stores for a frame (:503-510) and its pose; the window is transformed, concatenated and voxelised ----
+    P64 = alego.default_params(alego.PRESET_HDL64_1800)
+    seed = 3
+    wd = alego.SynthWorld(seed=seed)
+    g3 = alego.Alego(P64, n_seq=1)
+    empty = np.zeros((0, 4), np.float32)
+    g3.lm_set_map(0, empty, empty)
+    g3.pipeline_config(lm_every=1)
+    K = 8 if QUICK else 50
+    ck, sk, ok_, poses6 = [], [], [], []
+    for t in range(K):
+        scan = wd.render(P64, alego.trajectory_pose(t, seed=seed), noise_seed=700 + t)
+        buf, n = g3.pack_scans([scan])
+        g3.pipeline_step(buf, n)
+        c, s_, o_ = g3.lm_get_downsampled(0)
+        ck.append(c); sk.append(s_); ok_.append(o_)
+        x, y, z, yaw = alego.trajectory_pose(t, seed=seed)
+        poses6.append(np.array([x, y, z, 0.0, 0.0, yaw], np.float32))  # ground-truth key poses: a consistent window
+    poses6 = np.stack(poses6)
+    g3.lm_assemble_map(0, ck, sk, ok_, poses6)  # scratch growth + warm-up
+    g3.synchronize()
+    g3.profile_enable(True)
+    g3.profile_reset()
+    ts = []
+    for _ in range(1 if QUICK else 5):
+        t0 = time.perf_counter()
+        g3.lm_assemble_map(0, ck, sk, ok_, poses6)
+        g3.synchronize()
+        ts.append(time.perf_counter() - t0)
+    prof = g3.profile()
+    g3.profile_enable(False)
+    gc, gs = g3.lm_get_map(0)
+    t0 = time.perf_counter()
+    cm, sm, _ = ob.lm_assemble_map(ck, sk, ok_, poses6, P64.lm_corner_leaf, P64.lm_surf_leaf, stable=False)
+    t_cpu = time.perf_counter() - t0
+    out["assemble_map"] = {
+        "keyframes": K, "corner_points_in": int(sum(len(c) for c in ck)), "surf_points_in": int(sum(len(a) + len(b) for a, b in zip(sk, ok_))),
+        "corner_points_out": len(gc), "surf_points_out": len(gs),
+        "gpu_call_ms_median": round(1e3 * float(np.median(ts)), 3),
+        "gpu_kernels_ms_per_call": {k: round(v[1] / max(len(ts), 1), 4) for k, v in prof.items()},
+        "cpu_oracle_ms": round(1e3 * t_cpu, 1),
+        "bit_exact_vs_cpu": bool(np.array_equal(gc, cm) and np.array_equal(gs, sm)),
+        "note": "gpu_call = host clouds (pageable) in, H2D of the window, transform, VoxelGrid in pcl's record order, map left on the "
+                "device; runs once per saved keyframe (laserMapping.cpp:491-545), not per sweep",
     }
 print(json.dumps(out, indent=1))
