@@ -691,11 +691,11 @@ int lm_scan2map_device(AlegoHandle *h, int *guard_dev, bool write_pose, bool ind
         h->lm_surf_total_ds, cc, cs, co, h->lm_n, h->vox_sort, sort_c, sort_s, sort_o, cc, cs + co, co, h->lmv_state);
   };
   voxel_stage("lm_voxel_keys_3", 0, 3, 0);
-  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_3");
+  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_3", 4, 1);  // surf lists first
   if (rc != ALEGO_OK) return rc;
   voxel_stage("lm_voxel_finish_3", 0, 3, 1);
   voxel_stage("lm_voxel_keys_total", 3, 1, 0);
-  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_total");
+  rc = vox_order_lists_by_cta(h, h->lmv_state, 4 * B, h->vox_sort, h->vox_sort, s, "lm_voxel_order_total", 4, 3);
   if (rc != ALEGO_OK) return rc;
   voxel_stage("lm_voxel_finish_total", 3, 1, 1);
   if (!index_ready && (h->rebuild_map_every_step || !h->map_index_valid)) {  // the reference rebuilds both kd-trees every mapped frame (:356-357)

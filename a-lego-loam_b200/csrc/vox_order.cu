@@ -39,6 +39,31 @@ vox_order_cta_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_a
   if (st.done || st.nv != n || n <= 16 || n < min_n) return;  // uniform
   block_introsort_ws<VOC_WARPS>(buf_a + st.off, reinterpret_cast<int *>(buf_b + st.off_b), n, &s_q, &s_big, s_wpos, s_buf);
 }
+
+// LaserMapping's batch: `group` lists per sequence (corner, surf, outlier, union), the surf list an order of magnitude longer than
+// the others.  A launch lasts as long as its longest list, and a list is as fast as the warps that share it: 16 warps per CTA (two
+// CTAs per SM, so the 256 long lists of a full batch are one wave), and the long kind is issued FIRST (first_kind) so that the short
+// lists fill the slots it frees instead of the other way round.  Dynamic shared memory (52 KB: above the static limit).
+#define VOX_WIDE_WARPS 16
+#define VOX_WIDE_SMEM (((sizeof(IswShared) + 15) & ~(size_t)15) + ((sizeof(IswBig) + 15) & ~(size_t)15) + \
+                       (size_t)VOX_WIDE_WARPS * ISB_REG * (sizeof(u64) + sizeof(unsigned short)))
+__global__ void __launch_bounds__(VOX_WIDE_WARPS * 32, 2)
+vox_order_wide_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int min_n, int group, int n_groups,
+                      int first_kind) {
+  extern __shared__ __align__(16) unsigned char vow_smem[];
+  IswShared *q = reinterpret_cast<IswShared *>(vow_smem);
+  IswBig *big = reinterpret_cast<IswBig *>(vow_smem + ((sizeof(IswShared) + 15) & ~(size_t)15));
+  u64 *wbuf = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(big) + ((sizeof(IswBig) + 15) & ~(size_t)15));
+  unsigned short *wpos = reinterpret_cast<unsigned short *>(wbuf + (size_t)VOX_WIDE_WARPS * ISB_REG);
+  // block i -> (kind, sequence): kinds in the order first_kind, first_kind + 1, ... (mod group), sequences innermost
+  const int k = blockIdx.x / n_groups, b = blockIdx.x - k * n_groups;
+  int kind = first_kind + k;
+  if (kind >= group) kind -= group;
+  const VoxState &st = state[b * group + kind];
+  const int n = st.n;
+  if (st.done || st.nv != n || n <= 16 || n < min_n) return;  // uniform
+  block_introsort_ws<VOX_WIDE_WARPS>(buf_a + st.off, reinterpret_cast<int *>(buf_b + st.off_b), n, q, big, wpos, wbuf);
+}
 }  // namespace
 
 int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag) {
@@ -52,9 +77,17 @@ int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, 
   return ALEGO_OK;
 }
 
-int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag) {
+int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag,
+                           int group, int first_kind) {
   // same routing by length (a batch whose lists range from a few hundred to ten thousand records: LaserMapping's clouds)
-  { LAUNCH(h, tag); vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1); }
+  static bool attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!attr_set[h->dev]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(vox_order_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_WIDE_SMEM));
+    attr_set[h->dev] = true;
+  }
+  { LAUNCH(h, tag);
+    vox_order_wide_kernel<<<n_lists, VOX_WIDE_WARPS * 32, VOX_WIDE_SMEM, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1, group, n_lists / group,
+                                                                             first_kind); }
   { std::string t2 = std::string(tag) + "_short"; LAUNCH(h, t2.c_str());
     vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_WARP_MAX); }
   CUDA_TRY(h, cudaGetLastError());
