@@ -15,12 +15,20 @@ namespace {
 #define VO_WARP_MAX 2048
 #define VO_RING_WARP_MAX 2048  // 640 sends the dense near-range rings to the CTA kernel: 0.25 + 0.57 ms instead of 0.52 (issue-bound either way)
 __global__ void __launch_bounds__(VOW_WARPS * 32)
-vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int max_n) {
+vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int max_n, int group) {
   __shared__ unsigned short s_wpos[VOW_WARPS * ISB_REG];
   __shared__ u64 s_buf[VOW_WARPS * ISB_REG];  // per warp: its copy of a short range / heapsort buffer
   const int warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * VOW_WARPS + warp;
+  int c = blockIdx.x * VOW_WARPS + warp;
   if (c >= n_lists) return;
+  // group = lists per sequence, a multiple of the warps per CTA (the rings of a sweep): issue the CTAs ring block by ring block
+  // across all sequences instead of sequence by sequence.  The low rings (ground, near range) hold the longest lists; started
+  // first, they are not what the launch ends on.
+  if (group > 0) {
+    const int per = group / VOW_WARPS, n_seq = n_lists / group;
+    const int rb = blockIdx.x / n_seq, b = blockIdx.x - rb * n_seq;
+    if (rb < per) c = b * group + rb * VOW_WARPS + warp;
+  }
   const int n = state[c].n;
   if (state[c].done || state[c].nv != n || n <= 16 || n > max_n) return;
   isb_warp_finish(buf_a + state[c].off, reinterpret_cast<int *>(buf_b + state[c].off_b), 0, n, 2 * (31 - __clz(n)), s_wpos + warp * ISB_REG,
@@ -66,11 +74,13 @@ vox_order_wide_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_
 }
 }  // namespace
 
-int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag) {
+int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag,
+                            int group) {
   // a list is one warp's serial work, and a launch of 16 k lists is about one wave: its duration is the LONGEST list's.  Lists
   // above VO_RING_WARP_MAX records (the dense near-range rings) therefore go to work-sharing CTAs (the two kernels touch
   // disjoint lists)
-  { LAUNCH(h, tag); vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_RING_WARP_MAX); }
+  { LAUNCH(h, tag); vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_RING_WARP_MAX,
+                                                                               group % VOW_WARPS == 0 && n_lists % group == 0 ? group : 0); }
   { std::string t2 = std::string(tag) + "_long"; LAUNCH(h, t2.c_str());
     vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_RING_WARP_MAX + 1); }
   CUDA_TRY(h, cudaGetLastError());
@@ -89,7 +99,7 @@ int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u
     vox_order_wide_kernel<<<n_lists, VOX_WIDE_WARPS * 32, VOX_WIDE_SMEM, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1, group, n_lists / group,
                                                                              first_kind); }
   { std::string t2 = std::string(tag) + "_short"; LAUNCH(h, t2.c_str());
-    vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_WARP_MAX); }
+    vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_WARP_MAX, 0); }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }
