@@ -201,6 +201,8 @@ class LaserOdometry : public nodelet::Nodelet {
     pub_odom_ = nh_.advertise<nav_msgs::Odometry>("/odom/lidar", 10);
     pub_surf_last_ = nh_.advertise<sensor_msgs::PointCloud2>("/surf_last", 10);
     pub_corner_last_ = nh_.advertise<sensor_msgs::PointCloud2>("/corner_last", 10);
+    pub_outlier_last_ = nh_.advertise<sensor_msgs::PointCloud2>("/outlier_last", 10);
+    ip_view_.reset(new alego::ImageProjection(*ctx));  // read access to the sweep's segmented / outlier clouds on the shared handle
     sub_segmented_info_ = nh_.subscribe<alego::cloud_info>("/seg_info", 10, &LaserOdometry::segInfoHandler, this);
     sub_imu_ = nh_.subscribe<sensor_msgs::Imu>("/imu/data", 100, &LaserOdometry::imuHandler, this);
   }
@@ -234,23 +236,33 @@ class LaserOdometry : public nodelet::Nodelet {
     nav_msgs::OdometryPtr odom(new nav_msgs::Odometry);  // :513-525
     fill_odometry(*odom, msg->header.stamp, "/odom", t_w, r_w);
     pub_odom_.publish(odom);
-    if (pub_surf_last_.getNumSubscribers() > 0 || pub_corner_last_.getNumSubscribers() > 0) {  // :537-546
-      alego::PointCloud less_flat;
+    // corner_last_ / surf_last_ / outlier of the sweep for LaserMapping and any recorder (:531-552)
+    if (pub_surf_last_.getNumSubscribers() > 0 || pub_corner_last_.getNumSubscribers() > 0 || pub_outlier_last_.getNumSubscribers() > 0) {
+      alego::PointCloud less_flat, seg, outlier, less_sharp_cloud;
       std::vector<int32_t> sharp, less_sharp, flat;
-      if (core_->features(0, &sharp, &less_sharp, &flat, &less_flat) == ALEGO_OK) {
+      if (core_->features(0, &sharp, &less_sharp, &flat, &less_flat) == ALEGO_OK &&
+          ip_view_->results(0, nullptr, &seg, &outlier) == ALEGO_OK) {
+        less_sharp_cloud.reserve(less_sharp.size());
+        for (int32_t i : less_sharp)
+          if (i >= 0 && (size_t)i < seg.size()) less_sharp_cloud.push_back(seg[(size_t)i]);  // corner_less_sharp_ (:209, :223)
         std_msgs::Header h = msg->header;
         h.frame_id = "/laser";
-        sensor_msgs::PointCloud2Ptr c(new sensor_msgs::PointCloud2);
-        to_msg(less_flat, h, *c);
-        pub_surf_last_.publish(c);
+        const alego::PointCloud *clouds[3] = {&less_sharp_cloud, &less_flat, &outlier};
+        ros::Publisher *pubs[3] = {&pub_corner_last_, &pub_surf_last_, &pub_outlier_last_};
+        for (int k = 0; k < 3; ++k) {
+          sensor_msgs::PointCloud2Ptr c(new sensor_msgs::PointCloud2);
+          to_msg(*clouds[k], h, *c);
+          pubs[k]->publish(c);
+        }
       }
     }
   }
 
   ros::NodeHandle nh_, pnh_;
   ros::Subscriber sub_segmented_info_, sub_imu_;
-  ros::Publisher pub_odom_, pub_surf_last_, pub_corner_last_;
+  ros::Publisher pub_odom_, pub_surf_last_, pub_corner_last_, pub_outlier_last_;
   std::unique_ptr<alego::LaserOdometry> core_;
+  std::unique_ptr<alego::ImageProjection> ip_view_;
   bool adjust_distortion_ = false;
 };
 
