@@ -629,6 +629,20 @@ def test_async_submit_collect_matches_sync(alego):
         g.pipeline_collect()                     # nothing in flight
     for t in range(T):
         assert np.array_equal(got[t], ref[t]), "sweep %d" % t
+    # per-step timing events (alego_pipeline_timeline): H2D starts <= H2D done <= front end starts <= front end done <= poses
+    g.pipeline_timeline(True)
+    rows = []
+    for t in range(3):
+        b_, n_ = g.pack_scans(sweeps[t])
+        bufs[t % D][:] = b_
+        ns[t % D][:] = n_
+        g.pipeline_submit(bufs[t % D], ns[t % D])
+    for _ in range(3):
+        g.pipeline_collect()
+        rows.append(g.pipeline_timeline(True).copy())
+    g.pipeline_timeline(False)
+    rows = np.array(rows)
+    assert np.all(np.diff(rows, axis=1) >= 0) and np.all(np.diff(rows[:, 4]) > 0) and rows[-1, 4] < 1e4, rows
     # and the synchronous call still works afterwards on the same handle
     buf, n = g.pack_scans(sweeps[0])
     assert g.pipeline_step(buf, n).shape == (len(seeds), 12)
