@@ -428,17 +428,17 @@ __device__ void block_introsort_partitions(unsigned long long *e, int *pos, int 
 
 struct IswShared {
   int head, tail, outstanding, err;
-  int4 items[ISW_CAP];  // x = f, y = l, z = depth limit left
-  int ready[ISW_CAP];
+  // one word per task, written once by its producer with atomicExch and read by its consumer with an atomic read: bit 63 = valid,
+  // depth limit left << 48, l << 24, f (ranges of lists below 2^24 records).  A single-word message needs no separate "ready" flag.
+  unsigned long long task[ISW_CAP];
 };
 
 __device__ __forceinline__ bool isw_push(IswShared *q, int f, int l, int depth) {
   const int slot = atomicAdd(&q->tail, 1);
   if (slot >= ISW_CAP) return false;  // queue exhausted: the caller keeps the range
   atomicAdd(&q->outstanding, 1);
-  q->items[slot] = make_int4(f, l, depth, 0);
-  __threadfence_block();
-  atomicExch(&q->ready[slot], 1);
+  __threadfence_block();  // release: the records of [f, l) this warp has just moved are visible before the task is
+  atomicExch(&q->task[slot], (1ull << 63) | ((unsigned long long)depth << 48) | ((unsigned long long)l << 24) | (unsigned long long)f);
   return true;
 }
 
@@ -466,19 +466,21 @@ __device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, 
     if (lane == 0) slot = atomicAdd(&q->head, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= ISW_CAP) return;
-    int got = 0;
+    unsigned long long task = 0ull;
     if (lane == 0) {
       unsigned spins = 0;
       while (true) {
-        if (*reinterpret_cast<volatile int *>(&q->ready[slot])) { got = 1; break; }
-        if (*reinterpret_cast<volatile int *>(&q->outstanding) <= 0) break;  // nothing left that could fill this slot
+        task = atomicOr(&q->task[slot], 0ull);  // atomic read
+        if (task) break;
+        if (atomicAdd(&q->outstanding, 0) <= 0) break;  // nothing left that could fill this slot
         __nanosleep(100);
         if (++spins > (1u << 23)) { q->err = 1; break; }  // watchdog (~1 s): give up instead of hanging
       }
     }
-    got = __shfl_sync(0xffffffffu, got, 0);
-    if (!got) return;
-    const int4 it = q->items[slot];
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (!task) return;
+    __threadfence_block();  // acquire: the producer's records
+    const int4 it = make_int4((int)(task & 0xffffffull), (int)((task >> 24) & 0xffffffull), (int)((task >> 48) & 0xffull), 0);
     uint2 st[40];  // private stack: y = l | depth << 24
     int sp = 0;
     st[sp++] = make_uint2((unsigned)it.x, (unsigned)it.y | ((unsigned)it.z << 24));
@@ -530,7 +532,8 @@ template <int NW>
 __device__ void block_introsort_ws(unsigned long long *e, int *pos, int n, IswShared *q, IswBig *big, unsigned short *wpos_all,
                                    unsigned long long *wbuf_all) {
   if (n <= 16) return;  // uniform
-  for (int t = threadIdx.x; t < ISW_CAP; t += NW * 32) q->ready[t] = 0;
+  if (n >= (1 << 24)) __trap();  // task words and stack entries carry 24-bit positions
+  for (int t = threadIdx.x; t < ISW_CAP; t += NW * 32) q->task[t] = 0ull;
   int depth = 2 * (31 - __clz(n));
   if (threadIdx.x == 0) {
     q->head = 0; q->tail = 0; q->outstanding = 0; q->err = 0;

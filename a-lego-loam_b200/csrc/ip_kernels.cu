@@ -339,16 +339,28 @@ __global__ void __launch_bounds__(256) ccl_strip_kernel(uint8_t *flags, int *__r
   __syncthreads();
   // flatten by pointer jumping: the vertical joins chain the runs of a column row by row (up to R hops), so every cell chasing
   // its own root would walk those chains serially; halving all paths together needs about log2(R) sweeps
+  // (Jacobi sweeps: all reads of a sweep before its writes, so that no thread reads a label another one is replacing)
   {
     bool changed;
     do {
       changed = false;
-      for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int l = s_lab[idx];
-        if (l < 0) continue;
-        const int ll = s_lab[l];
-        if (ll != l) { s_lab[idx] = ll; changed = true; }
+      int nl[CCL_CELLS / 256];
+#pragma unroll
+      for (int k = 0; k < CCL_CELLS / 256; ++k) {
+        const int idx = threadIdx.x + k * 256;
+        nl[k] = -2;
+        if (idx < n) {
+          const int l = s_lab[idx];
+          if (l >= 0) {
+            const int ll = s_lab[s_lab[s_lab[l]]];  // three jumps per sweep: a third of the barriers
+            if (ll != l) nl[k] = ll;
+          }
+        }
       }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CCL_CELLS / 256; ++k)
+        if (nl[k] != -2) { s_lab[threadIdx.x + k * 256] = nl[k]; changed = true; }
       changed = __syncthreads_or(changed) != 0;
     } while (changed);
   }

@@ -409,6 +409,10 @@ def algorithmic_bytes(name, st):
         "lo_lfv_finish": (8.0 + 16.0) * kept + 16.0 * st.get("less_flat_pts", 0.0),
         # §8 d4 K14/K15: 16 B query + 5 x 16 B neighbours + 40 B result per query (candidate buckets come on top: see "traffic")
         "lm_knn_corner": 136.0 * qc, "lm_knn_surf": 136.0 * qs,
+        # the fit that follows: 5 indices + query + 5 neighbours in, one correspondence block out (80 B edge, 64 B plane)
+        "lm_fit_corner": (20.0 + 16.0 + 80.0 + 80.0) * qc, "lm_fit_surf": (20.0 + 16.0 + 80.0 + 64.0) * qs,
+        # K11/K12 (scan-to-scan): the same 56 B per residual block per pass
+        "lo_solve_surf": 56.0 * 2.0 * st.get("lo_surf_resid_iters", 0.0), "lo_solve_corner": 56.0 * 2.0 * st.get("lo_corner_resid_iters", 0.0),
         # §8 d4 K16: 56 B per residual block per pass, 2 passes per LM iteration
         "lm_solve": 56.0 * 2.0 * st.get("lm_resid_iters", 0.0),
     }
@@ -720,7 +724,11 @@ def main():
               "map_surf_pts": float(B * np.mean([len(q["map_surf"]) for q in seqs])),
               "map_corner_pts": float(B * np.mean([len(q["map_corner"]) for q in seqs])),
               "lm_corner_queries": lm_queries[0], "lm_surf_queries": lm_queries[1],
-              "lm_resid_iters": B * float(np.mean([(r["n_corner"] + r["n_surf"]) * r["iterations"] for r in lm_reports]))}
+              "lm_resid_iters": B * float(np.mean([(r["n_corner"] + r["n_surf"]) * r["iterations"] for r in lm_reports])),
+              # LaserOdometry: surf solve then corner solve, fixed iteration counts (laserOdometry.cpp:326, :410-421, :484-502)
+              # (the report carries the iterations of both solves together: halves)
+              "lo_surf_resid_iters": B * float(np.mean([r["n_surf"] * r["iterations"] / 2.0 for r in lo_reports])),
+              "lo_corner_resid_iters": B * float(np.mean([r["n_corner"] * r["iterations"] / 2.0 for r in lo_reports]))}
         total_kernel_ms = sum(ms for _, ms in prof.values())
         kernels = {}
         for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
