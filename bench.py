@@ -179,17 +179,29 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# launch tag (what the per-kernel profile is keyed by) -> kernel function of the ncu launch list, and which of its launches: a
+# function launched for several purposes per step (the ordering kernels) is identified by its longest launch
+TRAFFIC_KEY = {
+    "lo_lfv_order": ("vox_order_warp", "longest"), "lm_voxel_order_3": ("vox_order_wide", "longest"),
+    "maprows_fill_map_surf": ("mr_fill", "mean"), "maprows_bbox_map_surf": ("mr_bbox", "mean"), "maprows_clear_map_surf": ("mr_clear", "mean"),
+    "lm_knn_surf": ("lm_knn_rows", "mean"), "lm_knn_corner": ("lm_knn", "mean"), "lm_solve": ("lm_solve<128, 2>", "mean"),
+    "lm_fit_surf": ("lm_fit<0>", "mean"), "lm_fit_corner": ("lm_fit<1>", "mean"),
+    "lo_assoc_surf": ("lo_assoc<1, 8>", "mean"), "lo_assoc_corner": ("lo_assoc<0, 32>", "mean"),
+}
+
+
 def ncu_traffic(kernel, n_seq, preset, stride):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this
-    same command line (profiles/*_ncu_traffic.json, newest first); None when no capture matches the configuration."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu launch list of this same command
+    line (profiles/*_ncu_traffic.json, newest first); None when no capture matches the configuration."""
     import glob
+    func, which = TRAFFIC_KEY.get(kernel, (kernel, "mean"))
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")), reverse=True):
         try:
             d = json.load(open(f))
         except Exception:
             continue
         if d.get("n_seq") == n_seq and d.get("preset") == preset and d.get("point_stride") == stride:
-            v = d.get("dram_bytes_per_launch", {}).get(kernel)
+            v = d.get("dram_bytes_longest_launch" if which == "longest" else "dram_bytes_per_launch", {}).get(func)
             if isinstance(v, (int, float)):
                 return float(v), os.path.basename(f)
     return None, None

@@ -21,10 +21,13 @@ for r in rows:
     d[r[imet]] = float(r[ival].replace(",", "")) * scale.get(r[iunit], 1)
 agg = {}
 for d in launch.values():
-    a = agg.setdefault(d["name"], {"n": 0, "us": 0.0, "bytes": 0.0})
+    a = agg.setdefault(d["name"], {"n": 0, "us": 0.0, "bytes": 0.0, "longest_us": -1.0, "longest_bytes": 0.0})
     a["n"] += 1
     a["us"] += d.get("gpu__time_duration.sum", 0.0)
-    a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    by = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    a["bytes"] += by
+    if d.get("gpu__time_duration.sum", 0.0) > a["longest_us"]:  # a function launched for several purposes: its biggest job
+        a["longest_us"], a["longest_bytes"] = d.get("gpu__time_duration.sum", 0.0), by
 tot = sum(a["us"] for a in agg.values())
 print("| kernel | launches | mean us | share of window | DRAM MB / launch | DRAM GB/s |\n|---|---|---|---|---|---|")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
@@ -33,4 +36,5 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
 print("\nwindow: %d launches, %.3f ms of kernel time (serialised, cold-cache: compare SHARES with bench.py's, not absolutes)" % (len(launch), tot / 1e3))
 json.dump({"n_seq": n_seq, "preset": preset, "point_stride": stride, "source": path,
            "note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by kernel function name (launch-list capture)",
-           "dram_bytes_per_launch": {k.replace("_kernel", ""): a["bytes"] / a["n"] for k, a in agg.items()}}, open(out_json, "w"), indent=1)
+           "dram_bytes_per_launch": {k.replace("_kernel", ""): a["bytes"] / a["n"] for k, a in agg.items()},
+           "dram_bytes_longest_launch": {k.replace("_kernel", ""): a["longest_bytes"] for k, a in agg.items()}}, open(out_json, "w"), indent=1)
