@@ -439,8 +439,12 @@ static int upload_into(AlegoHandle *h, float4 *raw, int *n_dev, const float *xyz
   CUDA_TRY(h, cudaMemcpyAsync(n_dev, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, st));
   const size_t pt_bytes = (size_t)h->in_stride * sizeof(float), row = (size_t)h->Nmax * h->in_stride;  // floats per sequence
   float *dst = reinterpret_cast<float *>(raw);
-  if (total * 10 >= (size_t)h->B * h->Nmax * 9) {  // nearly full rows: one DMA
-    CUDA_TRY(h, cudaMemcpyAsync(dst, xyzi_host, (size_t)h->B * h->Nmax * pt_bytes, cudaMemcpyHostToDevice, st));
+  if (total * 10 >= (size_t)h->B * h->Nmax * 9) {  // nearly full rows: one strided DMA of the longest row's width
+    int widest = 0;
+    for (int b = 0; b < h->B; ++b) widest = std::max(widest, n_points[b]);
+    if (widest > 0)
+      CUDA_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->Nmax * pt_bytes, xyzi_host, (size_t)h->Nmax * pt_bytes, (size_t)widest * pt_bytes, (size_t)h->B,
+                                    cudaMemcpyHostToDevice, st));
   } else {
     for (int b = 0; b < h->B; ++b)
       if (n_points[b] > 0)
