@@ -6,6 +6,8 @@
 //                          the batch itself supplies the parallelism, nothing ever waits on a barrier)
 //   vox_order_cta_kernel   one CTA per list, the warps share the ranges through a shared-memory queue — LaserMapping's clouds
 //                          (hundreds to ~15 k records: the top levels fan out over 1, 2, 4 ... warps)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sort_voxel.cuh"
 #include "vox_order.cuh"
@@ -74,12 +76,42 @@ vox_order_wide_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_
 }
 }  // namespace
 
+static int vox_wide_attr(AlegoHandle *h) {
+  static bool attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
+  if (!attr_set[h->dev]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(vox_order_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_WIDE_SMEM));
+    attr_set[h->dev] = true;
+  }
+  return ALEGO_OK;
+}
+
+// below this many lists in a launch the batch does not fill the GPU with one warp per list (148 SMs x 32 resident warps): the
+// launch then lasts as long as ONE warp needs for the longest list, and sharing a list among the warps of a CTA pays
+#define VO_SMALL_BATCH_LISTS 1024
+#define VO_SMALL_BATCH_SPLIT 256
+
 int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag,
                             int group) {
+  static const int small_batch = [] {  // tuning override (tools/latency.py compares both routings)
+    const char *e = getenv("ALEGO_ORDER_SMALL_BATCH_LISTS");
+    return e ? atoi(e) : VO_SMALL_BATCH_LISTS;
+  }();
+  if (n_lists <= small_batch) {
+    // latency regime (a few sequences): 16 warps per list for everything a warp would not finish in its shared-memory copy
+    const int rc = vox_wide_attr(h);
+    if (rc != ALEGO_OK) return rc;
+    { LAUNCH(h, tag);
+      vox_order_wide_kernel<<<n_lists, VOX_WIDE_WARPS * 32, VOX_WIDE_SMEM, s>>>(state, buf_a, buf_b, VO_SMALL_BATCH_SPLIT + 1, 1, n_lists, 0); }
+    { std::string t2 = std::string(tag) + "_short"; LAUNCH(h, t2.c_str());
+      vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_SMALL_BATCH_SPLIT, 0); }
+    CUDA_TRY(h, cudaGetLastError());
+    return ALEGO_OK;
+  }
   // a list is one warp's serial work, and a launch of 16 k lists is about one wave: its duration is the LONGEST list's.  Lists
   // above VO_RING_WARP_MAX records (the dense near-range rings) therefore go to work-sharing CTAs (the two kernels touch
   // disjoint lists)
-  { LAUNCH(h, tag); vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_RING_WARP_MAX,
+  { LAUNCH(h, tag);
+    vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_RING_WARP_MAX,
                                                                                group % VOW_WARPS == 0 && n_lists % group == 0 ? group : 0); }
   { std::string t2 = std::string(tag) + "_long"; LAUNCH(h, t2.c_str());
     vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_RING_WARP_MAX + 1); }
@@ -90,11 +122,8 @@ int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, 
 int vox_order_lists_by_cta(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag,
                            int group, int first_kind) {
   // same routing by length (a batch whose lists range from a few hundred to ten thousand records: LaserMapping's clouds)
-  static bool attr_set[ALEGO_MAX_DEVICES] = {};  // cudaFuncSetAttribute is per device
-  if (!attr_set[h->dev]) {
-    CUDA_TRY(h, cudaFuncSetAttribute(vox_order_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_WIDE_SMEM));
-    attr_set[h->dev] = true;
-  }
+  const int rc = vox_wide_attr(h);
+  if (rc != ALEGO_OK) return rc;
   { LAUNCH(h, tag);
     vox_order_wide_kernel<<<n_lists, VOX_WIDE_WARPS * 32, VOX_WIDE_SMEM, s>>>(state, buf_a, buf_b, VO_WARP_MAX + 1, group, n_lists / group,
                                                                              first_kind); }
