@@ -99,12 +99,13 @@ __device__ __forceinline__ int isb_warp_partition_regs(unsigned long long *e, in
     }
     if (isL && !sL) first_keep_L = min(first_keep_L, t);
     if (sR) min_swap_R = min(min_swap_R, t);
-    K += __popc(__ballot_sync(full, sL));
+    if (sL) K = cL + 1;  // the swapping left stoppers are the first K of them: the last one seen carries the count
     runL += __popc(mL);
     runR += __popc(mR);
   }
   first_keep_L = __reduce_min_sync(full, first_keep_L);
   min_swap_R = __reduce_min_sync(full, min_swap_R);
+  K = __reduce_max_sync(full, K);
   __syncwarp();
   isb_warp_swaps(e, posL, posR, wpos, f, half, K);
   __syncwarp();
@@ -126,6 +127,52 @@ __device__ __forceinline__ int isb_warp_partition(unsigned long long *e, int *po
   if (m <= 64) return isb_warp_partition_regs<2>(e, posL, posR, wpos, f, l, p, half);
   if (m <= 128) return isb_warp_partition_regs<4>(e, posL, posR, wpos, f, l, p, half);
   if (m <= ISB_REG) return isb_warp_partition_regs<ISB_REG / 32>(e, posL, posR, wpos, f, l, p, half);
+  if (m <= 0xffff) {
+    // One sweep: the offsets of ALL left stoppers (keys >= pivot) and of all right stoppers (keys <= pivot), both in ascending
+    // order, as 16-bit offsets from f — 2m of them fit the m ints of scratch the range owns.  The k-th exchange pairs the k-th left
+    // stopper with the k-th right stopper from the top; exchanges happen while the former lies before the latter, which is
+    // monotone in k, so their number is found by one ballot per 32 pairs (no second pass over the keys to count the right
+    // stoppers first).
+    unsigned short *PL = reinterpret_cast<unsigned short *>(pos + f + 1), *PR = PL + m;
+    int nL = 0, nR = 0;
+    for (int c = lo; c < l; c += 128) {
+      unsigned k4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = c + q * 32 + lane;
+        k4[q] = t < l ? isb_key_at(e, t) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = c + q * 32 + lane;
+        const bool v = t < l;
+        const bool isL = v && k4[q] >= p, isR = v && k4[q] <= p;
+        const unsigned mL = __ballot_sync(full, isL), mR = __ballot_sync(full, isR);
+        if (isL) PL[nL + __popc(mL & lt_mask)] = (unsigned short)(t - f);
+        if (isR) PR[nR + __popc(mR & lt_mask)] = (unsigned short)(t - f);
+        nL += __popc(mL);
+        nR += __popc(mR);
+      }
+    }
+    __syncwarp();
+    const int np = min(nL, nR);
+    int K = 0;
+    for (int k0 = 0; k0 < np; k0 += 32) {
+      const int k = k0 + lane;
+      const unsigned ok = __ballot_sync(full, k < np && PL[k] < PR[nR - 1 - k]);
+      K += __popc(ok);
+      if (ok != full) break;
+    }
+    const int keep = K < nL ? f + PL[K] : 0x7fffffff, swp = K > 0 ? f + PR[nR - K] : l;
+    for (int k = lane; k < K; k += 32) {
+      const int a = f + PL[k], c2 = f + PR[nR - 1 - k];
+      const unsigned long long ea = e[a], ec = e[c2];
+      e[a] = ec;
+      e[c2] = ea;
+    }
+    __syncwarp();
+    return min(keep, swp);
+  }
   int runL = 0, runR = 0, K = 0, first_keep_L = 0x7fffffff, min_swap_R = l, totR = 0;
   // longer ranges: two sweeps, several chunks of loads in flight at a time
   for (int c = lo; c < l; c += 128) {
@@ -202,10 +249,9 @@ __device__ __forceinline__ void isb_warp_small(unsigned long long *e, int f, int
     int sidx;
     if (ka < kb) sidx = kb < kc ? ib : (ka < kc ? ic : ia);
     else sidx = ka < kc ? ia : (kb < kc ? ic : ib);
-    const unsigned long long ra = __shfl_sync(full, rec, a), rs = __shfl_sync(full, rec, sidx);
-    if (lane == a) rec = rs;
-    else if (lane == sidx) rec = ra;
-    const unsigned p = (unsigned)(rs >> 32), k = (unsigned)(rec >> 32);
+    // exchange records a <-> sidx with one shuffle (every other lane reads itself); the pivot key is the median just chosen
+    rec = __shfl_sync(full, rec, lane == a ? sidx : (lane == sidx ? a : lane));
+    const unsigned p = sidx == ia ? ka : (sidx == ib ? kb : kc), k = (unsigned)(rec >> 32);
     // std::__unguarded_partition(a + 1, b, pivot at a)
     const bool in = lane > a && lane < b;
     const bool isL = in && k >= p, isR = in && k <= p;
