@@ -2,10 +2,12 @@
 // what turns the device's VoxelGrid into pcl::VoxelGrid's exact record order (laserOdometry.cpp:288-293, laserMapping.cpp:325-342):
 // the kernels that build the (voxel, point) record lists leave a VoxState per list, the kernels here partition, the finish kernels
 // apply the stable radix sort.  A list stays with one SM from start to finish (its few KB are then served from L1):
-//   vox_order_warp_kernel  one WARP per list, private stack  — the 16 k per-ring lists of LaserOdometry (a few hundred records each:
-//                          the batch itself supplies the parallelism, nothing ever waits on a barrier)
-//   vox_order_cta_kernel   one CTA per list, the warps share the ranges through a shared-memory queue — LaserMapping's clouds
-//                          (hundreds to ~15 k records: the top levels fan out over 1, 2, 4 ... warps)
+//   vox_order_warp_kernel  one WARP per list, private stack  — the 16 k per-ring lists of LaserOdometry (a few hundred to 2 k records
+//                          each: the batch itself supplies the parallelism, nothing ever waits on a barrier)
+//   vox_order_wide_kernel  one CTA of 16 warps per list, the warps share the ranges through a shared-memory queue — LaserMapping's
+//                          clouds (hundreds to ~20 k records: the top levels fan out over 1, 2, 4 ... warps), and the ring lists too
+//                          when a launch holds too few lists to fill the GPU with one warp each (latency regime)
+//   vox_order_cta_kernel   the same with 8 warps and static shared memory: ring lists above 2048 records in a large batch
 #include <cstdlib>
 
 #include "common.cuh"
