@@ -574,7 +574,7 @@ int lo_extract_device(AlegoHandle *h) {
   { LAUNCH(h, "lo_lfv_keys");
     lo_lfv_keys_kernel<<<dim3(R, B), LFV_WARPS * 32, 0, s>>>(h->seg_cloud, h->flabel, h->start_ring, h->end_ring, h->lf_stage,
                                                              h->sort_scratch, h->lfv_state, R, RC, (float)h->P.less_flat_leaf); }
-  const int rc_q = vox_order_lists_by_warp(h, h->lfv_state, B * R, h->sort_scratch, h->lfv_keys, s, "lo_lfv_order", R);
+  const int rc_q = vox_order_lists_by_warp(h, h->lfv_state, B * R, h->sort_scratch, h->lfv_keys, s, "lo_lfv_order", R, C);
   if (rc_q != ALEGO_OK) return rc_q;
   { LAUNCH(h, "lo_lfv_finish");
     lo_lfv_finish_kernel<<<dim3(R, B), LFV_WARPS * 32, 0, s>>>(h->seg_cloud, h->start_ring, h->lf_stage, h->ring_feat_cnt, h->sort_scratch,

@@ -7,7 +7,7 @@
 //   vox_order_wide_kernel  one CTA of 16 warps per list, the warps share the ranges through a shared-memory queue — LaserMapping's
 //                          clouds (hundreds to ~20 k records: the top levels fan out over 1, 2, 4 ... warps), and the ring lists too
 //                          when a launch holds too few lists to fill the GPU with one warp each (latency regime)
-//   vox_order_cta_kernel   the same with 8 warps and static shared memory: ring lists above 2048 records in a large batch
+//                          and ring lists above 2048 records (sweeps wider than 2048 columns) in a large batch
 #include <cstdlib>
 
 #include "common.cuh"
@@ -37,19 +37,6 @@ vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__re
   if (state[c].done || state[c].nv != n || n <= 16 || n > max_n) return;
   isb_warp_finish(buf_a + state[c].off, reinterpret_cast<int *>(buf_b + state[c].off_b), 0, n, 2 * (31 - __clz(n)), s_wpos + warp * ISB_REG,
                   s_buf + (size_t)warp * ISB_REG, s_buf + (size_t)warp * ISB_REG);
-}
-
-#define VOC_WARPS 8
-__global__ void __launch_bounds__(VOC_WARPS * 32)
-vox_order_cta_kernel(const VoxState *__restrict__ state, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int min_n) {
-  __shared__ IswShared s_q;
-  __shared__ IswBig s_big;
-  __shared__ unsigned short s_wpos[VOC_WARPS * ISB_REG];
-  __shared__ u64 s_buf[VOC_WARPS * ISB_REG];
-  const VoxState &st = state[blockIdx.x];
-  const int n = st.n;
-  if (st.done || st.nv != n || n <= 16 || n < min_n) return;  // uniform
-  block_introsort_ws<VOC_WARPS>(buf_a + st.off, reinterpret_cast<int *>(buf_b + st.off_b), n, &s_q, &s_big, s_wpos, s_buf);
 }
 
 // LaserMapping's batch: `group` lists per sequence (corner, surf, outlier, union), the surf list an order of magnitude longer than
@@ -93,7 +80,7 @@ static int vox_wide_attr(AlegoHandle *h) {
 #define VO_SMALL_BATCH_SPLIT 256
 
 int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, u64 *buf_a, u64 *buf_b, cudaStream_t s, const char *tag,
-                            int group) {
+                            int group, int max_len) {
   static const int small_batch = [] {  // tuning override (tools/latency.py compares both routings)
     const char *e = getenv("ALEGO_ORDER_SMALL_BATCH_LISTS");
     return e ? atoi(e) : VO_SMALL_BATCH_LISTS;
@@ -110,13 +97,18 @@ int vox_order_lists_by_warp(AlegoHandle *h, const VoxState *state, int n_lists, 
     return ALEGO_OK;
   }
   // a list is one warp's serial work, and a launch of 16 k lists is about one wave: its duration is the LONGEST list's.  Lists
-  // above VO_RING_WARP_MAX records (the dense near-range rings) therefore go to work-sharing CTAs (the two kernels touch
-  // disjoint lists)
+  // above VO_RING_WARP_MAX records (possible only for sweeps wider than that many columns) therefore go to work-sharing CTAs
+  // (the two kernels touch disjoint lists)
   { LAUNCH(h, tag);
     vox_order_warp_kernel<<<div_up(n_lists, VOW_WARPS), VOW_WARPS * 32, 0, s>>>(state, n_lists, buf_a, buf_b, VO_RING_WARP_MAX,
                                                                                group % VOW_WARPS == 0 && n_lists % group == 0 ? group : 0); }
-  { std::string t2 = std::string(tag) + "_long"; LAUNCH(h, t2.c_str());
-    vox_order_cta_kernel<<<n_lists, VOC_WARPS * 32, 0, s>>>(state, buf_a, buf_b, VO_RING_WARP_MAX + 1); }
+  if (max_len > VO_RING_WARP_MAX) {
+    const int rc = vox_wide_attr(h);
+    if (rc != ALEGO_OK) return rc;
+    std::string t2 = std::string(tag) + "_long";
+    LAUNCH(h, t2.c_str());
+    vox_order_wide_kernel<<<n_lists, VOX_WIDE_WARPS * 32, VOX_WIDE_SMEM, s>>>(state, buf_a, buf_b, VO_RING_WARP_MAX + 1, 1, n_lists, 0);
+  }
   CUDA_TRY(h, cudaGetLastError());
   return ALEGO_OK;
 }
