@@ -703,3 +703,28 @@ def test_async_packed_batch64_against_chain(alego, ob):
     rep = g.solve_report("lm", B - 1)
     assert rep["status"] == alego.OK and rep["n_surf"] > 100
     g.close()
+
+
+def test_wide_sweep_ring_lists_above_2048(alego, ob):
+    """A sweep wider than 2048 columns (64 x 4096): the ground rings' less-flat lists exceed what one warp orders, in a batch large
+    enough (> 1024 lists per launch) that the batch routing applies — those lists go to the work-sharing CTAs (`lo_lfv_order_long`).
+    ImageProjection and the features, per-ring VoxelGrid included, bit-exact against the oracle."""
+    P = alego.default_params(alego.PRESET_HDL64_1800)
+    P.horizon_scan = 4096
+    P.ang_res_x = 360.0 / 4096
+    w = alego.SynthWorld(seed=7)
+    scan = w.render(P, alego.trajectory_pose(0, seed=7), noise_seed=77)
+    B = 20  # 20 x 64 = 1280 ring lists
+    g = alego.Alego(P, n_seq=B)
+    buf, n = g.pack_scans([scan] * B)
+    g.ip_process(buf, n)
+    g.lo_extract()
+    o = ob.Oracle(P)
+    assert o.ip(scan) == 0
+    o.lo_features()
+    sr, er = o.get("startRingIndex"), o.get("endRingIndex")
+    assert int(np.max(er - sr)) > 2600  # rings long enough that their less-flat lists exceed 2048 records
+    for b in (0, B // 2, B - 1):
+        check_ip(g, o, b, "wide seq%d" % b)
+        check_features(g, o, b, "wide seq%d" % b)
+    g.close()
