@@ -728,3 +728,34 @@ def test_wide_sweep_ring_lists_above_2048(alego, ob):
         check_ip(g, o, b, "wide seq%d" % b)
         check_features(g, o, b, "wide seq%d" % b)
     g.close()
+
+
+def test_batch_beyond_one_wave_of_solver_ctas(alego, ob):
+    """160 sequences: more than the GPU has SMs, so lm_solve takes its two-CTAs-per-SM shape (128 threads, 100 KB of staged blocks)
+    and lo_solve runs more than one CTA per SM everywhere.  Two unique sequences over the slots, three sweeps, every 20th slot
+    against the CPU chain; the traces of a slot's solves equal those of the same sequence in the first slots."""
+    P = alego.default_params(alego.PRESET_VLP16_1800)
+    U, B, T = 2, 160, 3
+    worlds = [alego.SynthWorld(seed=40 + u) for u in range(U)]
+    maps = [w.make_map(5000, 24000, seed=40 + u, radius=60.0) for u, w in enumerate(worlds)]
+    oracles = [ob.Oracle(P, lm_every=1, stable_voxel=False) for _ in range(U)]
+    g = alego.Alego(P, n_seq=B)
+    for u in range(U):
+        oracles[u].lm_set_map(*maps[u])
+    for b in range(B):
+        g.lm_set_map(b, *maps[b % U])
+    g.pipeline_config(lm_every=1)
+    for t in range(T):
+        scans = [w.render(P, alego.trajectory_pose(t, seed=40 + u), noise_seed=400 + 10 * u + t) for u, w in enumerate(worlds)]
+        buf, n = g.pack_scans([scans[b % U] for b in range(B)])
+        poses = g.pipeline_step(buf, n)
+        for u in range(U):
+            oracles[u].pipeline_step(scans[u])
+        for b in list(range(0, B, 20)) + [B - 1]:
+            o = oracles[b % U]
+            assert np.abs(poses[b, 3:9] - o.get("lm_params")).max() < POSE_TOL, (t, b)
+            assert np.abs(g.debug("lo_params", b) - o.get("lo_params")).max() < POSE_TOL, (t, b)
+            rep, orep = g.solve_report("lm", b), o.report("lm")
+            assert rep["iterations"] == orep["iterations"] and rep["n_surf"] == orep["n_surf"], (t, b, rep, orep)
+            assert np.array_equal(poses[b], poses[b % U]), (t, b)
+    g.close()
