@@ -16,7 +16,7 @@
 
 namespace {
 #define VOW_WARPS 8
-#define VO_WARP_MAX 2048
+#define VO_WARP_MAX 512
 #define VO_RING_WARP_MAX 2048  // 640 sends the dense near-range rings to the CTA kernel: 0.25 + 0.57 ms instead of 0.52 (issue-bound either way)
 __global__ void __launch_bounds__(VOW_WARPS * 32)
 vox_order_warp_kernel(const VoxState *__restrict__ state, int n_lists, u64 *__restrict__ buf_a, u64 *__restrict__ buf_b, int max_n, int group) {
