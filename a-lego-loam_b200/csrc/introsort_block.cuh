@@ -579,7 +579,7 @@ __device__ __forceinline__ void isw_worker(IswShared *q, unsigned long long *e, 
 // pos: n ints of scratch.  wpos_all / wbuf_all: per-warp shared scratch (NW x ISB_REG 16-bit positions; NW x ISB_REG records: the
 // warp's copy of a short range, also the heapsort buffer).  Every thread of the CTA must call; ends with a barrier.
 #define ISW_BIG 2048
-#define ISW_MAX_BIG 64  // lists of up to ISW_BIG * ISW_MAX_BIG = 131072 records
+#define ISW_MAX_BIG 256  // lists of up to ISW_BIG * ISW_MAX_BIG = 524288 records start with cooperative partitions
 struct IswBig {
   IsbShared coop;
   int2 range[2][ISW_MAX_BIG];

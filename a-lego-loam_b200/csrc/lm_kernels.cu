@@ -72,7 +72,13 @@ __global__ void lm_prepare_kernel(const int *use_ext, const Pose *lo_pose, Pose 
 // memory); sized so that two CTAs still share an SM
 #define LMV_EXACT_RECORDS 4608
 #define LMV_VOX_BYTES ((sizeof(VoxShared<LMV_WARPS>) + 15) & ~(size_t)15)
-#define LMV_SMEM_EXACT (LMV_VOX_BYTES + (size_t)LMV_EXACT_RECORDS * sizeof(u64))  // voxel_single: the one-CTA, all-in-one variant
+// voxel_single (the one-CTA, all-in-one variant: alego_voxel_grid, local-map assembly): behind the counters either the records of a
+// short list, or — for a longer one — the work-sharing scratch of its 32 warps (task queue, cooperative-phase ranges, per-warp range
+// copies and swap positions)
+#define LMV_WS_BYTES (((sizeof(IswShared) + 15) & ~(size_t)15) + ((sizeof(IswBig) + 15) & ~(size_t)15) + \
+                      (size_t)LMV_WARPS * ISB_REG * (sizeof(u64) + sizeof(unsigned short)))
+#define LMV_EXACT_BYTES ((size_t)LMV_EXACT_RECORDS * sizeof(u64))
+#define LMV_SMEM_EXACT (LMV_VOX_BYTES + (LMV_WS_BYTES > LMV_EXACT_BYTES ? LMV_WS_BYTES : LMV_EXACT_BYTES))
 #define LMV_SMEM LMV_VOX_BYTES
 __device__ __forceinline__ VoxExact lmv_exact(uint8_t *smem, IsbShared *isb) {
   VoxExact ex;
@@ -83,6 +89,12 @@ __device__ __forceinline__ VoxExact lmv_exact(uint8_t *smem, IsbShared *isb) {
   ex.list_cap = 0;
   ex.isb = isb;
   ex.wpos = nullptr;
+  // the same bytes, laid out for a list that does not fit them
+  uint8_t *w = smem + LMV_VOX_BYTES;
+  ex.wq = reinterpret_cast<IswShared *>(w);
+  ex.wbig = reinterpret_cast<IswBig *>(w + ((sizeof(IswShared) + 15) & ~(size_t)15));
+  ex.wbuf_all = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(ex.wbig) + ((sizeof(IswBig) + 15) & ~(size_t)15));
+  ex.wpos_all = reinterpret_cast<unsigned short *>(ex.wbuf_all + (size_t)LMV_WARPS * ISB_REG);
   return ex;
 }
 // kind 0 corner (leaf lm_corner_leaf), 1 surf, 2 outlier : blockIdx.y selects; kind 3 = surf_total (own launches).

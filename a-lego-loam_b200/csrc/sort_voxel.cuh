@@ -49,6 +49,12 @@ struct VoxExact {
   int list_cap;
   IsbShared *isb;
   unsigned short *wpos;  // optional shared memory: (warps of the CTA) x ISB_REG swap positions of short ranges
+  // optional: work-sharing scratch (introsort_block.cuh block_introsort_ws) for lists longer than e_cap — one long list ordered
+  // by all the warps of the CTA through a task queue instead of level by level
+  IswShared *wq;
+  IswBig *wbig;
+  unsigned short *wpos_all;
+  u64 *wbuf_all;
 };
 
 template <int NW>
@@ -470,7 +476,8 @@ __device__ int block_voxel_grid8(const float4 *__restrict__ pts, int n_src, Memb
       lists = reinterpret_cast<uint2 *>(kb + (n + 1) / 2);
       list_cap = n / 17 + 1;
     }
-    block_introsort_partitions<NW>(list, pos, n, lists, list_cap, ex->isb, ex->wpos);
+    if (ex->wq && list == ka) block_introsort_ws<NW>(list, pos, n, ex->wq, ex->wbig, ex->wpos_all, ex->wbuf_all);
+    else block_introsort_partitions<NW>(list, pos, n, lists, list_cap, ex->isb, ex->wpos);
     __syncthreads();
   }
   return block_voxel_finish<NW>(pts, list, kb, out, sh, n, nv, sh->frame.key_bits);
